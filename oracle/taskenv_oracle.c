@@ -539,13 +539,13 @@ void orc_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { philo
 
 /* Random stream contract shared with the CUDA path (DESIGN.md "RNG contract"):
  *   key  = (seed_lo, seed_hi)
- *   ctr  = (global_env_id_lo, global_env_id_hi, episode, decision_index*4 + block)
+ *   ctr  = (global_env_id_lo, global_env_id_hi, episode, decision_index*8 + block), block < 8
  *   block 0 words: [0] action draw  [1] next-leader draw  [2],[3] follower draws 0,1
  *   block 1 words: follower draws 2..5 ; block 2: 6..9 ...
  *   uniform integer in [0,n): (uint64)word * n >> 32
  */
 static uint32_t draw(const orc_env *e, uint32_t decision, int slot) {
-    uint32_t ctr[4] = {(uint32_t)e->gid, (uint32_t)(e->gid >> 32), e->episode, decision * 4u + (uint32_t)(slot >> 2)};
+    uint32_t ctr[4] = {(uint32_t)e->gid, (uint32_t)(e->gid >> 32), e->episode, decision * 8u + (uint32_t)(slot >> 2)};
     uint32_t key[2] = {(uint32_t)e->seed, (uint32_t)(e->seed >> 32)};
     uint32_t out[4]; philox4x32_10(ctr, key, out);
     return out[slot & 3];

@@ -1,0 +1,234 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+  * golden vectors recorded from the real reference (tests/golden/, digests of every decision), and
+  * the C oracle stepped in lock-step on the same inputs (full state diff, used for readable failures and for
+    synthetic instances at the bench's full batch size).
+Bar (BASELINE.json north_star): discrete state bit-exact; times/distances/rewards within 1e-5 relative.  The fp64 event
+clock makes the float state bit-exact too, so the digests are compared exactly; REL documents the contractual tolerance."""
+import numpy as np
+import pytest
+
+from oracle import canon
+from oracle.oracle import OracleEnv
+
+from helpers import METRIC_KEYS, ctasd, pickle_instances, pickle_traces, sweep_instance, sweep_traces
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def gpu_state(env, b, inst):
+    """decode env b and add the derived time_finish (= fl(time_start + time) once feasible, task_env.py:257)."""
+    s = env.export_state([b])[0]
+    s["time_finish"] = np.where(s["feasible"] > 0, s["time_start"] + np.asarray(inst["dur"], np.float64), 0.0)
+    return s
+
+
+def stack_instances(insts):
+    return (np.stack([i["task_xy"] for i in insts]), np.stack([i["depot_xy"] for i in insts]),
+            np.stack([i["req"] for i in insts]).astype(np.int32), np.stack([i["dur"] for i in insts]))
+
+
+def replay_batch(insts, eps, tr, max_wait=10.0):
+    """Replay B recorded episodes in one batch, checking every decision of every env."""
+    import torch
+    from dcmrta_b200 import BatchedTaskEnv
+    B, A, T = len(eps), insts[0]["A"], insts[0]["task_xy"].shape[0]
+    env = BatchedTaskEnv(B, A, T, M=5, max_wait=max_wait)
+    env.load_instances(*stack_instances(insts))
+    n = np.array([len(e["leader"]) for e in eps])
+    FS = 8
+    first = np.array([int(e["leader"][0]) for e in eps], np.int32)
+    env.reset(leaders=first)
+    oracles = [None] * B
+
+    def oracle_at(b, k):
+        """replay env b on the oracle up to decision k (only used to explain a mismatch)."""
+        o = OracleEnv.make(**insts[b], max_wait=max_wait)
+        e = eps[b]
+        o.fused_reset(int(e["leader"][0]))
+        for q in range(k):
+            o.fused_step(int(e["action"][q]), tr.followers(e, q), int(e["leader"][q + 1]) if q + 1 < len(e["leader"]) else -1)
+        return o
+
+    for k in range(int(n.max())):
+        ag, tk, mk = env.agent_obs.cpu().numpy(), env.task_obs.cpu().numpy(), env.mask_u8.cpu().numpy()
+        leaders = env.leader.cpu().numpy()
+        states = env.export_state()
+        for b in range(B):
+            if k >= n[b]:
+                assert states[b]["flags"] & 1, f"env {b} should be done after {n[b]} decisions"
+                continue
+            e = eps[b]
+            assert leaders[b] == e["leader"][k]
+            st = states[b]
+            st["time_finish"] = np.where(st["feasible"] > 0, st["time_start"] + insts[b]["dur"], 0.0)
+            assert st["now"] == e["now"][k], (e["name"], k)
+            if canon.obs_digest(mk[b], ag[b], tk[b]) != int(e["dig_obs"][k]):
+                o = oracle_at(b, k)
+                l = int(e["leader"][k])
+                np.testing.assert_array_equal(mk[b], o.mask(), err_msg=f"{e['name']} mask @ {k}")
+                np.testing.assert_array_equal(ag[b], o.agent_status(l).astype(np.float32), err_msg=f"{e['name']} agent obs @ {k}")
+                np.testing.assert_array_equal(tk[b], o.task_status(l).astype(np.float32), err_msg=f"{e['name']} task obs @ {k}")
+                raise AssertionError(f"{e['name']}: obs digest differs from the reference at decision {k} but matches the oracle")
+            if canon.state_digest(st) != int(e["dig_state"][k]):
+                d = canon.diff_states(st, oracle_at(b, k).export(canon.MC_CANON))
+                raise AssertionError(f"{e['name']}: state differs at decision {k}: {d}")
+        act = np.zeros(B, np.int32)
+        fol = np.full((B, FS), -1, np.int32)
+        nxt = np.full(B, -1, np.int32)
+        for b in range(B):
+            if k < n[b]:
+                e = eps[b]
+                act[b] = e["action"][k]
+                f = tr.followers(e, k)
+                fol[b, :len(f)] = f
+                if k + 1 < n[b]:
+                    nxt[b] = e["leader"][k + 1]
+        env.step(act, fol, nxt)
+        rew, done = env.reward.cpu().numpy(), env.done_u8.cpu().numpy()
+        for b in range(B):
+            if k < n[b]:
+                assert rew[b] == np.float32(eps[b]["reward"][k]), (eps[b]["name"], k)
+                assert bool(done[b]) == (k == n[b] - 1), (eps[b]["name"], k)
+    flags = env.env_flags().cpu().numpy()
+    assert not (flags & 0xF0).any(), "contract-violation bits set during a legal replay"
+    met = env.episode_metrics().cpu().numpy()
+    states = env.export_state()
+    for b in range(B):
+        gold = eps[b]["metrics"]
+        np.testing.assert_allclose(met[b], gold, rtol=1e-12, atol=0, err_msg=eps[b]["name"])
+        for c in (0, 1, 2, 3, 5, 6, 7):                      # everything but waiting_time is bit-exact
+            assert met[b, c] == gold[c], (eps[b]["name"], METRIC_KEYS[c])
+        st = states[b]
+        st["time_finish"] = np.where(st["feasible"] > 0, st["time_start"] + insts[b]["dur"], 0.0)
+        assert canon.state_digest(st) == eps[b]["final_digest"], eps[b]["name"]
+    env.close()
+    return met
+
+
+def test_replay_50_pickles_random_and_greedy():
+    """BASELINE config 2: all 50 testSet_20A_50T_CONDET instances x {random, greedy}, every decision, one batch of 100."""
+    inst = pickle_instances()
+    tr = pickle_traces()
+    eps = [tr.episode(i) for i in range(len(tr))]
+    insts = [inst[int(e["name"].split("/")[0])] for e in eps]
+    met = replay_batch(insts, eps, tr)
+    fin = tr.finished
+    assert np.array_equal(met[:, 1], fin.sum(1) / fin.shape[1])
+
+
+@pytest.mark.parametrize("shape", ["10x20", "20x50", "30x100", "50x200"])
+def test_replay_shape_sweep(shape):
+    tr = sweep_traces()
+    idx = [i for i, nm in enumerate(tr.names) if nm.startswith(shape + "/")]
+    eps = [tr.episode(i) for i in idx]
+    insts = [sweep_instance(tr, e["name"]) for e in eps]
+    replay_batch(insts, eps, tr)
+
+
+def test_ctasd_routes_known_answer():
+    """CTAS-D routes through execute_by_route reproduce the reference's CTAS-D_300s.csv."""
+    import torch
+    from dcmrta_b200 import BatchedTaskEnv
+    inst = pickle_instances()
+    gold = ctasd()
+    B, A, T = 50, 20, 50
+    Lmax = max(len(r) for g in gold for r in g["routes"].values())
+    routes = np.zeros((B, A, Lmax), np.int32)
+    rlen = np.zeros((B, A), np.int32)
+    for b, g in enumerate(gold):
+        for a, r in g["routes"].items():
+            routes[b, int(a), :len(r)] = r
+            rlen[b, int(a)] = len(r)
+    env = BatchedTaskEnv(B, A, T, M=5)
+    env.load_instances(*stack_instances(inst))
+    env.reset()
+    mk = env.execute_by_route(routes, rlen).cpu().numpy()
+    env.set_params(max_wait=100.0)                   # execute_by_route leaves max_waiting_time = 100 (task_env.py:564)
+    met = env.compute_metrics().cpu().numpy()
+    flags = env.env_flags().cpu().numpy()
+    assert not (flags & 0xF0).any()
+    states = env.export_state()
+    for b, g in enumerate(gold):
+        for k, v in g["csv"].items():
+            assert met[b, METRIC_KEYS.index(k)] == pytest.approx(v, rel=1e-14, abs=0), (b, k)
+        for k in ("success_rate", "makespan", "time_cost", "travel_dist", "efficiency", "reward"):
+            assert met[b, METRIC_KEYS.index(k)] == g["ref_here"][k], (b, k)
+        assert met[b, 4] == pytest.approx(g["ref_here"]["waiting_time"], rel=1e-13)
+        assert states[b]["finished"].tolist() == g["finished"]
+        st = states[b]
+        st["time_finish"] = np.where(st["feasible"] > 0, st["time_start"] + inst[b]["dur"], 0.0)
+        assert str(canon.state_digest(st)) == g["final_digest"], b
+    env.close()
+
+
+@pytest.mark.parametrize("policy", ["random", "greedy"])
+def test_inkernel_policy_matches_oracle_on_synthetic(policy):
+    """In-kernel Philox policies + generator vs the oracle running the same RNG contract, synthetic 20A/50T instances,
+    auto-reset across several episodes; sample of envs out of a batch that is not a multiple of the CTA size."""
+    from dcmrta_b200 import BatchedTaskEnv
+    B, A, T, STEPS = 1003, 20, 50, 400
+    env = BatchedTaskEnv(B, A, T, M=5, auto_reset=True, seed=1234, first_gid=10_000)
+    env.generate(max_duration=5.0, random_duration=(policy == "greedy"))
+    inst = {k: v.cpu().numpy() for k, v in env.get_instances().items()}
+    env.reset()
+    sample = [0, 1, 2, 3, 4, 500, 1001, 1002]
+    orcs = []
+    for b in sample:
+        o = OracleEnv.make(A, inst["task_xy"][b], inst["depot_xy"][b], inst["req"][b], inst["dur"][b])
+        o.seed(1234, gid=10_000 + b, episode=0)
+        assert o.fused_reset() == int(env.leader[b])
+        orcs.append(o)
+    episodes = [0] * len(sample)
+    last_metrics = [None] * len(sample)
+    for k in range(STEPS):
+        ag, tk, mk = env.agent_obs[sample].cpu().numpy(), env.task_obs[sample].cpu().numpy(), env.mask_u8[sample].cpu().numpy()
+        for q, o in enumerate(orcs):
+            l = o.leader
+            assert np.array_equal(mk[q], o.mask()), (policy, sample[q], k)
+            assert np.array_equal(ag[q], o.agent_status(l).astype(np.float32)), (policy, sample[q], k)
+            assert np.array_equal(tk[q], o.task_status(l).astype(np.float32)), (policy, sample[q], k)
+        env.step(policy=policy)
+        rew, done, lead = env.reward[sample].cpu().numpy(), env.done_u8[sample].cpu().numpy(), env.leader[sample].cpu().numpy()
+        for q, o in enumerate(orcs):
+            rc, r, d, _, _ = o.fused_step(-1 if policy == "random" else -2)
+            assert rc == 0
+            assert rew[q] == np.float32(r)
+            assert bool(done[q]) == d, (policy, sample[q], k)
+            if d:
+                last_metrics[q] = o.episode_metrics()[0]
+                episodes[q] += 1
+                o.seed(1234, gid=10_000 + sample[q], episode=episodes[q])
+                o.fused_reset()
+            assert lead[q] == o.leader, (policy, sample[q], k)
+    assert min(episodes) >= 2
+    met = env.episode_metrics()[sample].cpu().numpy()
+    for q in range(len(sample)):
+        gold = np.array([last_metrics[q][key] for key in METRIC_KEYS])
+        np.testing.assert_allclose(met[q], gold, rtol=1e-12, atol=0)
+    states = env.export_state(sample)
+    for q, o in enumerate(orcs):
+        st = states[q]
+        st["time_finish"] = np.where(st["feasible"] > 0, st["time_start"] + inst["dur"][sample[q]], 0.0)
+        assert not canon.diff_states(st, o.export(canon.MC_CANON)), (policy, sample[q])
+    assert env.total_steps() == B * STEPS
+    env.close()
+
+
+def test_shard_invariance():
+    """the trajectory of global env k does not depend on the batch it lives in."""
+    from dcmrta_b200 import BatchedTaskEnv
+    A, T = 20, 50
+    big = BatchedTaskEnv(64, A, T, auto_reset=True, seed=7, first_gid=0)
+    big.generate()
+    big.reset()
+    small = BatchedTaskEnv(16, A, T, auto_reset=True, seed=7, first_gid=32)
+    small.generate()
+    small.reset()
+    for _ in range(200):
+        big.step(policy="random")
+        small.step(policy="random")
+    a, b = big.export_raw()[32:48], small.export_raw()
+    assert np.array_equal(a, b)
+    assert np.array_equal(big.task_obs[32:48].cpu().numpy(), small.task_obs.cpu().numpy())
+    big.close(); small.close()
