@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the TaskEnv step on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference [...]                          the reference's CPU implementation of the path
+  torchrun --nproc-per-node N bench.py --gpus N ...               N > 1 (one rank per GPU, env shards, no collective on the data path)
+
+A "step" is one pass of the hot path over one batch: ONE leader decision for every env of the batch (dcm_step:
+apply the choice, coalition/feasibility update, agent update, slot advance, leader choice, observation + mask for the
+next leader), B env-steps per GPU per step.  Workload = BASELINE.json configs[2]: 65,536 synthetic 20A/50T envs per GPU,
+uniform-random policy over unmasked actions (in-kernel Philox), auto-reset, fp64 event clock, fp32 observations.
+
+  value        whole-job env-steps/s, state resident in HBM (CUDA events, max over ranks)
+  e2e          same metric through the host-buffer C-ABI call (dcm_step_host): actions H2D from pinned memory,
+               reward/done/next-leader D2H every step, observations written to the device-resident policy buffers
+  e2e_full_obs as e2e but the observations and mask are also copied to pinned host memory every step (PCIe-bound)
+  roofline     HBM: algorithmic bytes/step (w=8) x B / average k_fused duration vs MEASURED_PEAKS.json
+  cpu_baseline the C oracle port of the reference TaskEnv on the host cores, bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env-steps/sec at 20A/50T"
+UNIT = "env-steps/s"
+FALLBACK_HBM_GBS = 6650.0           # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2000)
+    p.add_argument("--warmup", type=int, default=200)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    p.add_argument("--agents", type=int, default=20)
+    p.add_argument("--tasks", type=int, default=50)
+    p.add_argument("--policy", default="random", choices=["random", "greedy"])
+    p.add_argument("--e2e-steps", type=int, default=200)
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.load(open(f))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(A, T, M=5, w=8):
+    s_static = 2 * w * T + 2 * w + T + w * T
+    s_dyn = T * (M * (1 + w) + 2 * w + 5) + A * (3 * w + 4) + 40
+    s_obs = 4 * 6 * A + 4 * 5 * (T + 1) + (T + 1)
+    return s_static + 2 * s_dyn + s_obs + 16
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for n, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_rollout(A, T, policy, seconds, threads=None, steps_per_thread=None):
+    """All host cores, one env pool per thread (ctypes releases the GIL); returns (steps/s, cores, steps, elapsed)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import OracleEnv, synthetic_instance
+    n = threads or os.cpu_count() or 1
+    pol = 1 if policy == "random" else 2
+    envs = []
+    for t in range(n):
+        pool = []
+        for q in range(8):
+            ia = synthetic_instance(A, T, 5, seed=1234 + 8 * t + q)
+            o = OracleEnv.make(**ia)
+            o.seed(1234, gid=8 * t + q, episode=0)
+            pool.append(o)
+        envs.append(pool)
+    # calibrate on one thread
+    t0 = time.perf_counter()
+    c = envs[0][0].rollout_bench(pol, 20000, seed=1)
+    rate1 = c / (time.perf_counter() - t0)
+    per_env = steps_per_thread // 8 if steps_per_thread else max(2000, int(rate1 * seconds / 8))
+
+    def work(pool):
+        return sum(o.rollout_bench(pol, per_env, seed=2) for o in pool)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n) as ex:
+        total = sum(ex.map(work, envs))
+    dt = time.perf_counter() - t0
+    return total / dt, n, total, dt, rate1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    # warm-up
+    cpu_rollout(args.agents, args.tasks, args.policy, 0.5)
+    # K "steps", each a bounded sample of the workload: the whole run is sized to ~args.cpu_seconds of wall time on all host
+    # threads, i.e. one "step" = total/K decisions spread over the thread pool
+    rate, cores, total, dt, rate1 = cpu_rollout(args.agents, args.tasks, args.policy, args.cpu_seconds)
+    line = {
+        "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"synthetic {args.agents}A/{args.tasks}T TaskEnv, {args.policy} policy, obs+mask built every decision",
+                   "env_steps_timed": total, "threads": cores},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{total} decisions of the C oracle port (oracle/taskenv_oracle.c) over {cores} threads x 8 envs in {dt:.1f}s; "
+                                   f"1-thread rate {rate1:.0f}/s; the Python reference itself ran 455-541 decisions/s/core in the build container (SURVEY.md 6)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dcmrta_b200 import BatchedTaskEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # not launched under torchrun: re-exec ourselves with one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", __file__] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, A, T = args.envs, args.agents, args.tasks
+    env = BatchedTaskEnv(B, A, T, M=5, device=local, auto_reset=True, seed=1234, first_gid=rank * B)
+    env.generate(max_duration=5.0)
+    env.reset()
+    launches0 = env.launch_count()
+    for _ in range(args.warmup):
+        env.step(policy=args.policy)
+    barrier()
+    steps0 = env.total_steps()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches1 = env.launch_count()
+    w0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        env.step(policy=args.policy)
+    ev1.record()
+    torch.cuda.synchronize()
+    w1 = time.time()
+    launched = env.launch_count() - launches1
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    env_steps = env.total_steps() - steps0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([env_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, total_steps = float(t.item()), float(cnt.item())
+    value = total_steps / (ms_max * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call ---------------------------------------------------------------
+    def e2e(full_obs):
+        K = args.e2e_steps
+        env.seed(4321, first_gid=rank * B)
+        env.reset()
+        acts = torch.empty(K + 8, B, dtype=torch.int32).pin_memory()
+        for k in range(K + 8):                      # record a valid action trace (deterministic given the Philox contract)
+            env.step(policy=args.policy)
+            acts[k].copy_(env.used_action, non_blocking=True)
+        torch.cuda.synchronize()
+        env.seed(4321, first_gid=rank * B)
+        env.reset()
+        torch.cuda.synchronize()
+        out = {"next_leader": torch.empty(B, dtype=torch.int32).pin_memory(), "reward": torch.empty(B, dtype=torch.float32).pin_memory(),
+               "done": torch.empty(B, dtype=torch.uint8).pin_memory()}
+        if full_obs:
+            out.update(agent_obs=torch.empty(B, A, 6, dtype=torch.float32).pin_memory(),
+                       task_obs=torch.empty(B, T + 1, 5, dtype=torch.float32).pin_memory(),
+                       mask=torch.empty(B, T + 1, dtype=torch.uint8).pin_memory())
+        for k in range(8):
+            env.step_host(acts[k], out)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(8, K + 8):
+            env.step_host(acts[k], out)             # H2D actions, step, D2H results; returns when the outputs are valid
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        d2h = sum(v.numel() * v.element_size() for v in out.values())
+        return world * B * K / float(tt.item()), 4 * B, d2h
+
+    e_val, e_h2d, e_d2h = e2e(False)
+    f_val, f_h2d, f_d2h = e2e(True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    bytes_step = algorithmic_bytes(A, T)
+    per_launch_s = ms_max * 1e-3 / args.steps
+    achieved = bytes_step * B / per_launch_s / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.load(open(tf)).get(f"{A}x{T}x{B}")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{B} synthetic {A}A/{T}T envs per GPU (BASELINE configs[2]), {args.policy} policy (in-kernel Philox), auto-reset, "
+                               f"fp64 event clock, fp32 obs; one step = one leader decision per env",
+                   "envs_per_gpu": B, "agents": A, "tasks": T, "max_coalition": 5,
+                   "l2": f"state {B * (env.record_bytes() + env.layout['sta_bytes']) / 1e6:.0f} MB + obs {B * 1551 / 1e6:.0f} MB per GPU > 126 MB L2, streamed every step (no flush needed)",
+                   "parallelism": f"env shards x{world}, no data-path collective"},
+        "e2e": {"value": e_val, "unit": UNIT, "h2d_bytes_per_step": e_h2d, "d2h_bytes_per_step": e_d2h,
+                "what": "dcm_step_host: actions from pinned host memory, reward/done/next_leader to pinned host memory every step; obs stay in the device policy buffers"},
+        "e2e_full_obs": {"value": f_val, "unit": UNIT, "h2d_bytes_per_step": f_h2d, "d2h_bytes_per_step": f_d2h,
+                         "what": "as e2e plus agent_obs/task_obs/mask copied to pinned host memory every step"},
+        "gpu_launches": launched, "env_steps_timed": total_steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "k_fused", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
+                     "launch_us": per_launch_s * 1e6},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        rate, cores, total, dt, rate1 = cpu_rollout(A, T, args.policy, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{total} decisions of the C oracle port over {cores} threads x 8 synthetic {A}A/{T}T envs in {dt:.1f}s "
+                                          f"(1 thread: {rate1:.0f}/s); the Python reference ran 455-541 decisions/s/core in the build container"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

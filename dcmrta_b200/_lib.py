@@ -40,7 +40,7 @@ SIGNATURES = {
     "dcm_generate": (i32, [vp, f64, i32, vp]),
     "dcm_get_instances": (i32, [vp, vp, vp, vp, vp, vp]),
     "dcm_reset": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
-    "dcm_step": (i32, [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "dcm_step": (i32, [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "dcm_step_host": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "dcm_episode_metrics": (i32, [vp, vp, vp]),
     "dcm_next_decision": (i32, [vp, vp, vp, vp]),

@@ -59,6 +59,7 @@ class BatchedTaskEnv:
         self.leader = torch.full((self.B,), -1, dtype=torch.int32, device=dev)
         self.reward = torch.zeros(self.B, dtype=torch.float32, device=dev)
         self.done_u8 = torch.zeros(self.B, dtype=torch.uint8, device=dev)
+        self.used_action = torch.full((self.B,), -1, dtype=torch.int32, device=dev)
         self._keep = []
 
     # ---- lifetime ---------------------------------------------------------------------------------------------
@@ -147,7 +148,7 @@ class BatchedTaskEnv:
             fstride = f.shape[1]
         check(lib().dcm_step(self._h, _ptr(a), _ptr(f), fstride, _ptr(nl), POLICY[policy] if isinstance(policy, str) else int(policy),
                              _ptr(self.agent_obs), _ptr(self.task_obs), _ptr(self.mask_u8), _ptr(self.leader), _ptr(self.reward),
-                             _ptr(self.done_u8), self._stream()))
+                             _ptr(self.done_u8), _ptr(self.used_action), self._stream()))
         self._keep = [a, f, nl]          # keep inputs alive until the stream has consumed them
         return self.agent_obs, self.task_obs, self.mask, self.leader, self.reward, self.done
 

@@ -42,7 +42,7 @@ struct EnvArgs {
 struct FusedArgs {
     int mode;                                  // 0 = step, 1 = reset
     const int* action; const int* followers; int fstride; const int* leader_in; const unsigned char* which; int policy;
-    float* agent_obs; float* task_obs; unsigned char* mask; int* next_leader; float* reward; unsigned char* done;
+    float* agent_obs; float* task_obs; unsigned char* mask; int* next_leader; float* reward; unsigned char* done; int* used_action;
     double* metrics;                           // [B,8] last finished episode
 };
 
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32 * DCM_WARPS) k_fused(const __grid_constant_
     unsigned n_steps = h.n_steps, episode = h.episode, flags = h.flags, instance = h.instance, total = h.total_steps;
     int leader = h.leader;
     const Rng rng{E.seed, E.first_gid + (u64)e};
-    float reward_out = 0.f; unsigned char done_out = 0;
+    float reward_out = 0.f; unsigned char done_out = 0; int action_out = -1;
     bool dirty = true;
 
     if (F.mode == 1) {                                                          // ---- dcm_reset
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(32 * DCM_WARPS) k_fused(const __grid_constant_
         }
         if (ok) {
             __syncwarp();
+            action_out = action;
             pending &= ~mm;
             double r = dev_apply_members(R, lane, now, action, mlist, nm, rew, flags);     // :337-341
             reward_out = __double2float_rn(r);
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(32 * DCM_WARPS) k_fused(const __grid_constant_
         if (F.next_leader) F.next_leader[e] = leader;
         if (F.reward) F.reward[e] = reward_out;
         if (F.done) F.done[e] = done_out;
+        if (F.used_action) F.used_action[e] = action_out;
     }
     if (dirty) {
         if (lane == 0) {
@@ -604,7 +606,7 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
 }
 
 int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fstride, const int32_t* next_leader_in, int policy,
-             float* agent_obs, float* task_obs, uint8_t* mask, int32_t* next_leader, float* reward, uint8_t* done, void* stream) {
+             float* agent_obs, float* task_obs, uint8_t* mask, int32_t* next_leader, float* reward, uint8_t* done, int32_t* used_action, void* stream) {
     if (!v) return fail(DCM_ERR_ARG, "dcm_step: env is NULL");
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_step: load or generate instances first");
     if (policy < 0 || policy > 2) return fail(DCM_ERR_ARG, "dcm_step: unknown policy");
@@ -612,7 +614,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     if (followers && fstride < 0) return fail(DCM_ERR_ARG, "dcm_step: negative follower stride");
     FusedArgs F; memset(&F, 0, sizeof F);
     F.mode = 0; F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
-    F.agent_obs = agent_obs; F.task_obs = task_obs; F.mask = mask; F.next_leader = next_leader; F.reward = reward; F.done = done;
+    F.agent_obs = agent_obs; F.task_obs = task_obs; F.mask = mask; F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action;
     F.metrics = v->metrics;
     return launch_fused(v, F, stream);
 }
@@ -636,7 +638,7 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
     const size_t B = v->E.B, A = v->E.L.A, T = v->E.L.T;
     cudaStream_t s = v->hstream;
     if (action) CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
-    rc = dcm_step(v, v->d_action, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, s);
+    rc = dcm_step(v, v->d_action, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
     if (rc) return rc;
     if (agent_obs) CK(cudaMemcpyAsync(agent_obs, v->d_agent, B * A * 6 * 4, cudaMemcpyDeviceToHost, s));
     if (task_obs) CK(cudaMemcpyAsync(task_obs, v->d_task, B * (T + 1) * 5 * 4, cudaMemcpyDeviceToHost, s));

@@ -14,7 +14,10 @@
  *     one is asynchronous on it and performs no host synchronisation.  Calls taking host pointers synchronise.
  *   - a handle owns ALL state in HBM (allocated once in dcm_create), is bound to one device, and is not
  *     thread-safe; distinct handles are independent.
- *   - B envs, A agents (<= 64), T tasks (<= 254), M = max coalition size = member slots per task (<= 16).
+ *   - B envs, A agents (<= 64), T tasks (<= 254), M = max coalition size = member slots per task (<= 16).  Requirements
+ *     must lie in [1, M].  Legal (unmasked) actions never put more than M agents on a task; preset routes can, so a
+ *     handle used for dcm_execute_by_route should be created with M = the largest coalition the routes may form
+ *     (DCM_ENV_ERR_OVERFLOW is raised per env otherwise).
  *   - actions use the reference encoding: 0 = depot, j+1 = task j (task_env.py:307).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns DCM_ERR_DEVICE.
  */
@@ -105,11 +108,12 @@ int dcm_reset(dcm_env* env, const uint8_t* which_d, const int32_t* leader_in_d,
  *   next_leader_in_d [B] i32 the leader np.random.choice(group) returned for the NEXT decision; NULL = Philox
  *   agent_obs_d [B,A,6] f32   task_obs_d [B,T+1,5] f32   mask_d [B,T+1] u8 (1 = forbidden)
  *   next_leader_d [B] i32 (-1 when done)   reward_d [B] f32 (task_env.py:341)   done_d [B] u8
+ *   used_action_d [B] i32 or NULL: the action that was applied (what a built-in policy chose; -1 if the env did not step)
  * Envs already done (and not auto-reset) are left untouched and report done=1. */
 int dcm_step(dcm_env* env, const int32_t* action_d, const int32_t* followers_d, int fstride,
              const int32_t* next_leader_in_d, int policy,
              float* agent_obs_d, float* task_obs_d, uint8_t* mask_d,
-             int32_t* next_leader_d, float* reward_d, uint8_t* done_d, void* stream);
+             int32_t* next_leader_d, float* reward_d, uint8_t* done_d, int32_t* used_action_d, void* stream);
 
 /* Same call with HOST buffers (pageable or pinned): actions are copied in, outputs copied out, the call returns when the
  * outputs are valid.  Any output pointer may be NULL (then it is not copied). */

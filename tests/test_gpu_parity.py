@@ -140,7 +140,7 @@ def test_ctasd_routes_known_answer():
         for a, r in g["routes"].items():
             routes[b, int(a), :len(r)] = r
             rlen[b, int(a)] = len(r)
-    env = BatchedTaskEnv(B, A, T, M=5)
+    env = BatchedTaskEnv(B, A, T, M=8)      # preset routes ignore the mask: coalitions may exceed max_coalition_size
     env.load_instances(*stack_instances(inst))
     env.reset()
     mk = env.execute_by_route(routes, rlen).cpu().numpy()
