@@ -52,7 +52,7 @@ SIGNATURES = {
     "dcm_apply_members": (i32, [vp, vp, vp, i32, vp, vp, vp]),
     "dcm_build_obs": (i32, [vp, vp, vp, vp, vp, vp]),
     "dcm_check_finished": (i32, [vp, vp, vp]),
-    "dcm_compute_metrics": (i32, [vp, vp, vp]),
+    "dcm_compute_metrics": (i32, [vp, vp, vp, vp, vp]),
     "dcm_execute_by_route": (i32, [vp, vp, i32, vp, vp, vp]),
     "dcm_record_bytes": (sz, [vp]),
     "dcm_export_state": (i32, [vp, vp, sz, vp]),

@@ -223,10 +223,13 @@ class BatchedTaskEnv:
         check(lib().dcm_check_finished(self._h, _ptr(f), self._stream()))
         return f.view(torch.bool)
 
-    def compute_metrics(self):
+    def compute_metrics(self, per_element=False):
+        """get_episode_reward + worker.py:103-108 now.  per_element=True also returns the task / agent sum_waiting_time arrays."""
         out = torch.empty(self.B, 8, dtype=torch.float64, device=self.device)
-        check(lib().dcm_compute_metrics(self._h, _ptr(out), self._stream()))
-        return out
+        tw = torch.zeros(self.B, self.T, dtype=torch.float64, device=self.device) if per_element else None
+        aw = torch.zeros(self.B, self.A, dtype=torch.float64, device=self.device) if per_element else None
+        check(lib().dcm_compute_metrics(self._h, _ptr(out), _ptr(tw), _ptr(aw), self._stream()))
+        return (out, tw, aw) if per_element else out
 
     def execute_by_route(self, routes, route_len):
         """pre_set_route + execute_by_route (task_env.py:562-599).  routes [B,A,L] int32 actions, route_len [B,A]."""

@@ -1,12 +1,14 @@
-// dcm_kernels.cu -- sm_100a kernels of the TaskEnv step and the C ABI of include/dcmrta.h.
+// dcm_kernels.cu -- sm_100a kernels of the TaskEnv step and the C ABI of include/dcmrta.h  (v2: thread-per-env).
 //
-// Kernels (all warp-per-env, see dcm_device.cuh):
-//   k_fused<AR>      dcm_reset / dcm_step: one leader decision per env per launch (the hot path)
-//   k_granular<AR>   the individual TaskEnv methods (facade path)
-//   k_routes<AR>     execute_by_route: a whole preset-route episode per env in one launch
-//   k_generate       synthetic instances (generate_env distributions) with Philox
-//   k_pack_static / k_unpack_static   instance arrays <-> static records
-//   k_sum_steps      reduction of the per-env decision counters
+// Kernels (one thread per env, 32 envs = one tile = one warp; state in tiled struct-of-arrays, see dcm_soa.h):
+//   k_step       dcm_reset / dcm_step: one leader decision per env per launch -- action application, coalition update,
+//                agent update, slot advance, episode accounting + auto-reset, leader choice                (hot path 1/2)
+//   k_obs        observation + mask builder: rows produced per env, transposed through a per-warp shared-memory tile,
+//                written with unit-stride stores straight into the policy's input tensors               (hot path 2/2)
+//   k_granular   the individual TaskEnv methods (facade path)
+//   k_routes     execute_by_route: a whole preset-route episode per env in one launch
+//   k_generate   synthetic instances (generate_env distributions) with Philox
+//   k_pack_static / k_unpack_static / k_export / k_import / k_init / k_sum_steps   plumbing
 //
 // Build: nvcc -std=c++17 -O3 -fmad=false -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared
 #include <cuda_runtime.h>
@@ -17,412 +19,486 @@
 #include <string>
 
 #include "../../include/dcmrta.h"
-#include "dcm_device.cuh"
+#include "dcm_thread.cuh"
 
 using namespace dcm;
 
-#ifndef DCM_WARPS
-#define DCM_WARPS 4           // envs (warps) per CTA
-#endif
+#define STEP_THREADS 64
+#define OBS_THREADS 64
+#define OBS_PITCH 43            // words per env in the staging tile: 40 floats + 8 mask bytes + 1 pad (odd => conflict-free)
+#define OBS_AGENTS_PER_CHUNK 6  // 36 floats
+#define OBS_ROWS_PER_CHUNK 8    // 40 floats + 8 mask bytes
 
 // ---------------------------------------------------------------------------------------------------------------
 // kernel argument blocks
 // ---------------------------------------------------------------------------------------------------------------
 struct EnvArgs {
-    DcmLayout L;
-    int B;
-    unsigned char* dyn;       // [B, dyn_bytes]
-    unsigned char* sta;       // [B, sta_bytes]
+    DcmSoa S;
     double W, vel, max_time;
     u64 seed, first_gid;
     unsigned cflags;
     double gen_max_duration; int gen_random_duration;
 };
 
-struct FusedArgs {
+struct StepArgs {
     int mode;                                  // 0 = step, 1 = reset
     const int* action; const int* followers; int fstride; const int* leader_in; const unsigned char* which; int policy;
-    float* agent_obs; float* task_obs; unsigned char* mask; int* next_leader; float* reward; unsigned char* done; int* used_action;
+    int* next_leader; float* reward; unsigned char* done; int* used_action;
     double* metrics;                           // [B,8] last finished episode
 };
 
+struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask; };
+
 enum GranOp { OP_NEXT_DECISION = 1, OP_UNIQUE_GROUP, OP_SET_CLOCK, OP_GET_CLOCK, OP_TASK_UPDATE, OP_AGENT_UPDATE, OP_APPLY_MEMBERS,
-              OP_BUILD_OBS, OP_CHECK_FINISHED, OP_COMPUTE_METRICS, OP_ENV_FLAGS };
+              OP_CHECK_FINISHED, OP_COMPUTE_METRICS, OP_ENV_FLAGS };
 
 struct GranArgs {
     int op;
     u64* deciders; const u64* deciders_in; double* t; const double* t_in; signed char* group_rank; unsigned char* newly;
     const int* action; const int* members; int mstride; const int* n_members; double* reward;
-    const int* leader; float* agent_obs; float* task_obs; unsigned char* mask; unsigned char* finished; double* metrics;
+    unsigned char* finished; double* metrics; double* task_wait; double* agent_wait;
     unsigned* flags_out;
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// record movement: 16-byte vector copies, unit stride across the warp
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void copy16(void* dst, const void* src, int bytes, int lane) {
-    const int4* s = (const int4*)src; int4* d = (int4*)dst;
-    const int n = bytes >> 4;
-#pragma unroll 4
-    for (int i = lane; i < n; i += 32) d[i] = s[i];
+__device__ __forceinline__ TC make_tc(const EnvArgs& E, int b) {
+    return TC{E.S, (unsigned)b >> 5, (unsigned)b & 31u, E.S.A, E.S.T, E.S.MC, E.W, E.vel, E.max_time};
 }
 
-// on-device instance generation for one env (lane <-> task); Philox ctr = (gid_lo, gid_hi, instance#, 0x80000000 + 2*j + b)
+// on-device instance generation for one env; Philox ctr = (gid_lo, gid_hi, instance#, 0x80000000 + 2*j + b)
 __device__ __forceinline__ double u01(unsigned hi, unsigned lo) {               // 53-bit uniform in [0,1)
     return (double)(((u64)(hi >> 5) << 26) | (u64)(lo >> 6)) * (1.0 / 9007199254740992.0);
 }
-__device__ __forceinline__ void dev_generate(unsigned char* sta, const DcmLayout& L, int lane, u64 seed, u64 gid, unsigned instance,
-                                             double max_duration, int random_duration) {
-    double* tx = (double*)(sta + L.s_tx); double* ty = (double*)(sta + L.s_ty); double* dur = (double*)(sta + L.s_dur);
-    double* depot = (double*)(sta + L.s_depot); unsigned char* req = sta + L.s_req;
+__device__ __noinline__ void t_generate(const TC& c, u64 seed, u64 gid, unsigned instance, double max_duration, int random_duration) {
     const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), g0 = (unsigned)gid, g1 = (unsigned)(gid >> 32);
-    for (int j = lane; j < L.T; j += 32) {
-        uint4 a = philox(g0, g1, instance, 0x80000000u + 2u * j, k0, k1);
-        uint4 b = philox(g0, g1, instance, 0x80000001u + 2u * j, k0, k1);
-        tx[j] = u01(a.x, a.y); ty[j] = u01(a.z, a.w);                           // task_env.py:69
-        req[j] = (unsigned char)(1 + pick(b.x, L.M));                           // :71
-        dur[j] = random_duration ? u01(b.y, b.z) * max_duration : max_duration; // :70
+    for (int j = 0; j < c.T; ++j) {
+        const uint4 a = philox(g0, g1, instance, 0x80000000u + 2u * j, k0, k1);
+        const uint4 b = philox(g0, g1, instance, 0x80000001u + 2u * j, k0, k1);
+        EL(c, s_tx, c.T, j) = u01(a.x, a.y); EL(c, s_ty, c.T, j) = u01(a.z, a.w);          // task_env.py:69
+        EL(c, s_req, c.T, j) = (unsigned char)(1 + pick(b.x, c.s.M));                      // :71
+        EL(c, s_dur, c.T, j) = random_duration ? u01(b.y, b.z) * max_duration : max_duration;   // :70
     }
-    if (lane == 0) {
-        uint4 a = philox(g0, g1, instance, 0xFFFFFFFFu, k0, k1);
-        depot[0] = u01(a.x, a.y); depot[1] = u01(a.z, a.w);                     // :67
-    }
-    __syncwarp();
+    const uint4 a = philox(g0, g1, instance, 0xFFFFFFFFu, k0, k1);
+    EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w);                // :67
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_fused: reset / step
+// k_step: reset / step
 // ---------------------------------------------------------------------------------------------------------------
-template <int AR>
-__device__ __forceinline__ void choose_leader_and_observe(Rec& R, int lane, const Rng& rng, unsigned episode, unsigned n_steps,
-                                                          double now, u64 pending, u64& group, int& leader, unsigned& flags,
-                                                          const int* leader_in, int e, const FusedArgs& f, const DcmLayout& L) {
-    group = dev_current_group<AR>(R, lane, pending);                           // task_env.py:291-298
-    int inj = leader_in ? leader_in[e] : -1;
+__device__ __forceinline__ int choose_leader(const TC& c, const Rng& rng, unsigned episode, unsigned n_steps, u64 pending, u64& group,
+                                             unsigned& flags, const int* leader_in, int b) {
+    group = t_current_group(c, pending);                                      // task_env.py:291-298
+    const int inj = leader_in ? leader_in[b] : -1;
     if (inj >= 0) {
-        if (inj < L.A && ((group >> inj) & 1ull)) leader = inj;
-        else { flags |= ENV_ERR_LEADER; leader = __ffsll((long long)group) - 1; }
-    } else {
-        uint4 b = draw_block(rng, episode, n_steps, 0);
-        leader = kth_bit(group, pick(b.y, __popcll(group)));                   // worker.py:54
+        if (inj < c.A && ((group >> inj) & 1ull)) return inj;
+        flags |= ENV_ERR_LEADER;
+        return __ffsll((long long)group) - 1;
     }
-    dev_build_obs(R, lane, now, leader,
-                  f.agent_obs ? f.agent_obs + (size_t)e * 6 * L.A : nullptr,
-                  f.task_obs ? f.task_obs + (size_t)e * 5 * (L.T + 1) : nullptr,
-                  f.mask ? f.mask + (size_t)e * (L.T + 1) : nullptr);
+    const int n = __popcll(group);
+    if (n == 1) return __ffsll((long long)group) - 1;                         // same value as pick(word, 1) == 0
+    const uint4 blk = draw_block(rng, episode, n_steps, 0);
+    return kth_bit(group, pick(blk.y, n));                                    // worker.py:54
 }
 
-template <int AR>
-__global__ void __launch_bounds__(32 * DCM_WARPS) k_fused(const __grid_constant__ EnvArgs E, const __grid_constant__ FusedArgs F) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * DCM_WARPS + warp;
-    if (e >= E.B) return;
-    const DcmLayout& L = E.L;
-    unsigned char* dyn_s = smem + (size_t)warp * (L.dyn_bytes + L.stage_bytes);
-    unsigned char* g_dyn = E.dyn + (size_t)e * L.dyn_bytes;
-    unsigned char* g_sta = E.sta + (size_t)e * L.sta_bytes;
-    if (F.mode == 1 && F.which && !F.which[e]) return;
-
-    copy16(dyn_s, g_dyn, L.dyn_bytes, lane);
-    __syncwarp();
-    Rec R = make_rec(dyn_s, g_sta, dyn_s + L.dyn_bytes, L, E.W, E.vel, E.max_time);
-    DcmHdr h = *R.hdr;
-    double now = h.now; u64 pending = h.pending, group = h.group;
-    unsigned n_steps = h.n_steps, episode = h.episode, flags = h.flags, instance = h.instance, total = h.total_steps;
-    int leader = h.leader;
-    const Rng rng{E.seed, E.first_gid + (u64)e};
+template <int TW>
+__global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
+    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (b >= E.S.B) return;
+    if (F.mode == 1 && F.which && !F.which[b]) return;
+    const TC c = make_tc(E, b);
+    St<TW> st, st0; ld_state(c, st); st0 = st;
+    double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
+    unsigned n_steps = EL(c, n_steps, 1, 0), episode = EL(c, episode, 1, 0), flags = EL(c, flags, 1, 0);
+    int leader = EL(c, leader, 1, 0);
+    const Rng rng{E.seed, E.first_gid + (u64)b};
     float reward_out = 0.f; unsigned char done_out = 0; int action_out = -1;
     bool dirty = true;
 
-    if (F.mode == 1) {                                                          // ---- dcm_reset
-        dev_clear(R, lane);
+    if (F.mode == 1) {                                                        // ---- dcm_reset
+        t_clear(c, st);
         now = 0.0; pending = 0; group = 0; n_steps = 0; flags = 0; leader = -1;
-        dev_advance<AR>(R, lane, now, pending, flags);
-        if (!(flags & ENV_DONE)) choose_leader_and_observe<AR>(R, lane, rng, episode, n_steps, now, pending, group, leader, flags, F.leader_in, e, F, L);
-    } else if (flags & ENV_DONE) {                                              // ---- finished earlier, no auto-reset
+        t_advance(c, st, now, pending, flags);
+        if (!(flags & ENV_DONE)) leader = choose_leader(c, rng, episode, n_steps, pending, group, flags, F.leader_in, b);
+    } else if (flags & ENV_DONE) {                                            // ---- finished earlier, no auto-reset
         done_out = 1; leader = -1; dirty = false;
-    } else {                                                                    // ---- dcm_step
+    } else {                                                                  // ---- dcm_step
         bool ok = true;
         uint4 b0 = make_uint4(0, 0, 0, 0);
-        if (F.policy != 0 || !F.followers) b0 = draw_block(rng, episode, n_steps, 0);
-        int action = F.policy != 0 ? dev_policy_action(R, lane, leader, F.policy, b0.x) : F.action[e];
-        if (action < 0 || action > L.T) { flags |= ENV_ERR_ACTION; ok = false; }
-        unsigned char* mlist = R.stage + 8 * L.Ap; double* rew = (double*)R.stage;
-        int nm = 1; u64 mm = 1ull << leader;
+        bool have_b0 = false;
+        int action;
+        if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
+        else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
+        else action = F.action[b];
+        if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
+        int want = 0; u64 g = group & ~(1ull << leader);                      // task_env.py:328
+        const int* fp = F.followers ? F.followers + (size_t)b * F.fstride : nullptr;
         if (ok) {
-            const int gsz = __popcll(group);
-            const int vacancy = action == 0 ? gsz : (int)R.status[action - 1];  // task_env.py:327
-            u64 g = group & ~(1ull << leader);                                  // :328
-            if (lane == 0) mlist[0] = (unsigned char)leader;
-            const int* fp = F.followers ? F.followers + (size_t)e * F.fstride : nullptr;
-            if (vacancy > 1) {                                                  // :330
-                const int avail = __popcll(g);
-                const int want = vacancy - 1 < avail ? vacancy - 1 : avail;     // :331
-                if (action == 0) {                                              // Q11: the whole remaining group follows to the depot
-                    while (g) { int fo = __ffsll((long long)g) - 1; if (lane == 0) mlist[nm] = (unsigned char)fo; ++nm; mm |= 1ull << fo; g &= g - 1; }
-                } else if (fp) {                                                // injected followers (trace replay)
-                    for (int k = 0; k < want; ++k) {
-                        int fo = k < F.fstride ? fp[k] : -1;
-                        if (fo < 0 || fo >= L.A || !((g >> fo) & 1ull)) { ok = false; break; }
-                        g &= ~(1ull << fo); mm |= 1ull << fo; if (lane == 0) mlist[nm] = (unsigned char)fo; ++nm;
-                    }
-                    if (ok && want < F.fstride && fp[want] >= 0) ok = false;
-                    if (!ok) flags |= ENV_ERR_FOLLOW;
-                } else {                                                        // :331 uniform without replacement
-                    uint4 b = b0;
-                    for (int k = 0; k < want; ++k) {
-                        const int slot = 2 + k;
-                        if ((slot & 3) == 0) b = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2));
-                        int fo = kth_bit(g, pick(word_of(b, slot & 3), __popcll(g)));
-                        g &= ~(1ull << fo); mm |= 1ull << fo; if (lane == 0) mlist[nm] = (unsigned char)fo; ++nm;
-                    }
+            const int vacancy = action == 0 ? __popcll(group) : (int)EL(c, t_status, c.T, action - 1);   // :327
+            if (vacancy > 1) { const int avail = __popcll(g); want = vacancy - 1 < avail ? vacancy - 1 : avail; }   // :330-331
+            if (fp && action != 0) {                                          // validate injected followers before touching state
+                u64 gg = g;
+                for (int k = 0; k < want && ok; ++k) {
+                    const int fo = k < F.fstride ? fp[k] : -1;
+                    if (fo < 0 || fo >= c.A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
                 }
-            } else if (fp && action != 0 && F.fstride > 0 && fp[0] >= 0) { flags |= ENV_ERR_FOLLOW; ok = false; }
+                if (ok && want < F.fstride && fp[want] >= 0) ok = false;
+                if (!ok) flags |= ENV_ERR_FOLLOW;
+            }
         }
         if (ok) {
-            __syncwarp();
             action_out = action;
-            pending &= ~mm;
-            double r = dev_apply_members(R, lane, now, action, mlist, nm, rew, flags);     // :337-341
-            reward_out = __double2float_rn(r);
-            dev_task_update(R, lane, now, nullptr);                             // worker.py:74
-            dev_agent_update(R, lane, now);                                     // worker.py:76
-            ++n_steps; ++total;
-            if (!pending) dev_advance<AR>(R, lane, now, pending, flags);        // worker.py:85, :45-51
+            // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
+            double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
+            double d, tt; travel(c, EL(c, a_x, c.A, leader), EL(c, a_y, c.A, leader), tx, ty, d, tt);
+            double reward = 0.0; int nm = 1;
+            t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt;
+            pending &= ~(1ull << leader);
+            if (action == 0) {                                                // Q11: the whole remaining group follows to the depot
+                for (; g; g &= g - 1) { const int fo = __ffsll((long long)g) - 1; t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; pending &= ~(1ull << fo); }
+            } else {
+                uint4 blk = b0;
+                for (int k = 0; k < want; ++k) {
+                    int fo;
+                    if (fp) fo = fp[k];                                       // injected (trace replay)
+                    else {                                                    // :331 uniform without replacement
+                        const int slot = 2 + k;
+                        if ((slot & 3) == 0 || !have_b0) { blk = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2)); have_b0 = true; }
+                        fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
+                    }
+                    g &= ~(1ull << fo); pending &= ~(1ull << fo);
+                    t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm;
+                }
+            }
+            reward_out = __double2float_rn(reward / (double)nm);              // :337-341
+            t_task_update(c, st, now, nullptr);                               // worker.py:74
+            t_agent_update(c, st, now, agents_to_update(st));                 // worker.py:76
+            ++n_steps; EL(c, total, 1, 0) = EL(c, total, 1, 0) + 1;
+            if (!pending) t_advance(c, st, now, pending, flags);              // worker.py:85, :45-51
             if (flags & ENV_DONE) {
                 done_out = 1;
-                now = dev_episode_metrics<AR>(R, lane, now, n_steps, F.metrics + (size_t)e * 8);   // worker.py:87, :103-108
+                now = t_episode_metrics(c, st, now, n_steps, F.metrics + (size_t)b * 8, nullptr, nullptr);   // worker.py:87, :103-108
                 ++episode; leader = -1; group = 0;
                 if (E.cflags & DCM_FLAG_AUTO_RESET) {
                     if (E.cflags & DCM_FLAG_REGENERATE) {
-                        ++instance;
-                        dev_generate(g_sta, L, lane, E.seed, rng.gid, instance, E.gen_max_duration, E.gen_random_duration);
+                        const unsigned inst = EL(c, instance, 1, 0) + 1; EL(c, instance, 1, 0) = inst;
+                        t_generate(c, E.seed, rng.gid, inst, E.gen_max_duration, E.gen_random_duration);
                     }
-                    dev_clear(R, lane);
+                    t_clear(c, st);
                     now = 0.0; pending = 0; n_steps = 0; flags = 0;
-                    dev_advance<AR>(R, lane, now, pending, flags);
+                    t_advance(c, st, now, pending, flags);
                 }
             }
-            if (!(flags & ENV_DONE)) choose_leader_and_observe<AR>(R, lane, rng, episode, n_steps, now, pending, group, leader, flags, F.leader_in, e, F, L);
+            if (!(flags & ENV_DONE)) leader = choose_leader(c, rng, episode, n_steps, pending, group, flags, F.leader_in, b);
         }
     }
-    if (lane == 0) {
-        if (F.next_leader) F.next_leader[e] = leader;
-        if (F.reward) F.reward[e] = reward_out;
-        if (F.done) F.done[e] = done_out;
-        if (F.used_action) F.used_action[e] = action_out;
-    }
+    if (F.next_leader) F.next_leader[b] = leader;
+    if (F.reward) F.reward[b] = reward_out;
+    if (F.done) F.done[b] = done_out;
+    if (F.used_action) F.used_action[b] = action_out;
     if (dirty) {
-        if (lane == 0) {
-            h.now = now; h.pending = pending; h.group = group; h.n_steps = n_steps; h.episode = episode; h.leader = leader;
-            h.flags = flags; h.instance = instance; h.total_steps = total;
-            *R.hdr = h;
+        EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
+        EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags;
+        st_state(c, st0, st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_obs: observation + mask for the leader of every env (envs without a leader are skipped)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flush_floats(const float* tile, float* g, size_t row_len, int col0, int n, unsigned tile_id, unsigned lane,
+                                             unsigned valid, int B) {
+    // 32 envs x n floats staged at tile[e*OBS_PITCH + k]  ->  g[(tile_id*32+e)*row_len + col0 + k], unit stride across the warp
+    const unsigned inv = (1048576u + n - 1) / n;
+    for (unsigned q = lane; q < 32u * n; q += 32) {
+        const unsigned e = (q * inv) >> 20, k = q - e * n;
+        const unsigned be = tile_id * 32 + e;
+        if (be < (unsigned)B && ((valid >> e) & 1u)) g[(size_t)be * row_len + col0 + k] = tile[e * OBS_PITCH + k];
+    }
+}
+
+template <int TW>
+__global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O) {
+    __shared__ float smem[(OBS_THREADS / 32) * 32 * OBS_PITCH];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned tile_id = blockIdx.x * (OBS_THREADS / 32) + warp;
+    const int b = (int)(tile_id * 32 + lane);
+    const int B = E.S.B, A = E.S.A, T = E.S.T;
+    if (tile_id * 32 >= (unsigned)B) return;
+    float* tile = smem + warp * 32 * OBS_PITCH;
+    float* mine = tile + lane * OBS_PITCH;
+    const TC c = make_tc(E, b < B ? b : B - 1);
+    int leader = -1;
+    if (b < B) leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0);
+    const bool ok = leader >= 0 && leader < A;
+    const unsigned valid = __ballot_sync(0xffffffffu, ok);
+    if (!valid) return;
+    double now = 0, Lx = 0, Ly = 0;
+    St<TW> st;
+    if (ok) { now = EL(c, now, 1, 0); Lx = EL(c, a_x, A, leader); Ly = EL(c, a_y, A, leader); ld_state(c, st); }
+    // ---- agent rows, 6 agents per chunk
+    for (int c0 = 0; c0 < A; c0 += OBS_AGENTS_PER_CHUNK) {
+        const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
+        if (ok) for (int i = 0; i < na; ++i) obs_agent_row(c, st, now, Lx, Ly, c0 + i, mine + 6 * i);
+        __syncwarp();
+        if (O.agent_obs) flush_floats(tile, O.agent_obs, (size_t)6 * A, 6 * c0, 6 * na, tile_id, lane, valid, B);
+        __syncwarp();
+    }
+    // ---- task rows (row 0 = depot) + mask bytes, 8 rows per chunk
+    bool all_masked = true;
+    for (int r0 = 0; r0 <= T; r0 += OBS_ROWS_PER_CHUNK) {
+        const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
+        unsigned char* mbytes = (unsigned char*)(mine + 40);
+        if (ok) for (int i = 0; i < nr; ++i) {
+            obs_task_row(c, Lx, Ly, r0 + i, mine + 5 * i);
+            const bool open = r0 + i > 0 && tbit<TW>(st.open, r0 + i - 1);      // task_env.py:199
+            mbytes[i] = open ? 0 : 1;
+            all_masked = all_masked && !open;
         }
         __syncwarp();
-        copy16(g_dyn, dyn_s, L.dyn_bytes, lane);
+        if (O.task_obs) flush_floats(tile, O.task_obs, (size_t)5 * (T + 1), 5 * r0, 5 * nr, tile_id, lane, valid, B);
+        if (O.mask) {
+            const unsigned inv = (1048576u + nr - 1) / nr;
+            for (unsigned q = lane; q < 32u * nr; q += 32) {
+                const unsigned e = (q * inv) >> 20, k = q - e * nr;
+                const unsigned be = tile_id * 32 + e;
+                if (be < (unsigned)B && ((valid >> e) & 1u) && (r0 + k) > 0)
+                    O.mask[(size_t)be * (T + 1) + r0 + k] = ((const unsigned char*)(tile + e * OBS_PITCH + 40))[k];
+            }
+        }
+        __syncwarp();
     }
+    if (ok && O.mask) O.mask[(size_t)b * (T + 1)] = all_masked ? 0 : 1;          // worker.py:58-61 depot bit
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_granular: one TaskEnv method per launch
 // ---------------------------------------------------------------------------------------------------------------
-template <int AR>
-__global__ void __launch_bounds__(32 * DCM_WARPS) k_granular(const __grid_constant__ EnvArgs E, const __grid_constant__ GranArgs G) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * DCM_WARPS + warp;
-    if (e >= E.B) return;
-    const DcmLayout& L = E.L;
-    unsigned char* dyn_s = smem + (size_t)warp * (L.dyn_bytes + L.stage_bytes);
-    unsigned char* g_dyn = E.dyn + (size_t)e * L.dyn_bytes;
-    copy16(dyn_s, g_dyn, L.dyn_bytes, lane);
-    __syncwarp();
-    Rec R = make_rec(dyn_s, E.sta + (size_t)e * L.sta_bytes, dyn_s + L.dyn_bytes, L, E.W, E.vel, E.max_time);
-    double now = R.hdr->now;
-    unsigned flags = R.hdr->flags;
-    bool dirty = false;
+template <int TW>
+__global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant__ EnvArgs E, const __grid_constant__ GranArgs G) {
+    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    const double now = EL(c, now, 1, 0);
+    St<TW> st, st0; ld_state(c, st); st0 = st;
     switch (G.op) {
-    case OP_NEXT_DECISION: {
-        double t; u64 d = dev_next_decision<AR>(R, lane, t);
-        if (lane == 0) { G.deciders[e] = d; G.t[e] = t; }
-    } break;
-    case OP_UNIQUE_GROUP:
-        dev_group_ranks<AR>(R, lane, G.deciders_in[e], G.group_rank + (size_t)e * L.A);
-        break;
-    case OP_SET_CLOCK:
-        if (lane == 0) R.hdr->now = G.t_in[e];
-        dirty = true;
-        break;
-    case OP_GET_CLOCK:
-        if (lane == 0) G.t[e] = now;
-        break;
-    case OP_TASK_UPDATE: {
-        unsigned char* nw = G.newly ? G.newly + (size_t)e * L.T : nullptr;
-        if (nw) for (int j = lane; j < L.T; j += 32) nw[j] = 0;
-        __syncwarp();
-        dev_task_update(R, lane, now, nw);
-        dirty = true;
-    } break;
-    case OP_AGENT_UPDATE:
-        dev_agent_update(R, lane, now);
-        dirty = true;
-        break;
-    case OP_APPLY_MEMBERS: {
-        int n = G.n_members[e];
-        int action = G.action[e];
-        if (n > 0) {
-            if (action < 0 || action > L.T || n > L.A) { flags |= ENV_ERR_ACTION; }
-            else {
-                unsigned char* mlist = R.stage + 8 * L.Ap; double* rew = (double*)R.stage;
-                for (int k = lane; k < n; k += 32) mlist[k] = (unsigned char)G.members[(size_t)e * G.mstride + k];
-                __syncwarp();
-                double r = dev_apply_members(R, lane, now, action, mlist, n, rew, flags);
-                if (lane == 0 && G.reward) G.reward[e] = r;
-            }
-            if (lane == 0) R.hdr->flags = flags;
-            dirty = true;
+    case OP_NEXT_DECISION: { double t; const u64 d = t_next_decision(c, t); G.deciders[b] = d; G.t[b] = t; } break;
+    case OP_UNIQUE_GROUP: {
+        signed char* out = G.group_rank + (size_t)b * c.A;
+        for (int i = 0; i < c.A; ++i) out[i] = -1;
+        u64 rest = G.deciders_in[b]; int rank = 0;
+        while (rest) {
+            const u64 g = t_current_group(c, rest);
+            for (u64 m = g; m; m &= m - 1) out[__ffsll((long long)m) - 1] = (signed char)rank;
+            rest &= ~g; ++rank;
         }
     } break;
-    case OP_BUILD_OBS: {
-        int leader = G.leader[e];
-        if (leader >= 0 && leader < L.A)
-            dev_build_obs(R, lane, now, leader,
-                          G.agent_obs ? G.agent_obs + (size_t)e * 6 * L.A : nullptr,
-                          G.task_obs ? G.task_obs + (size_t)e * 5 * (L.T + 1) : nullptr,
-                          G.mask ? G.mask + (size_t)e * (L.T + 1) : nullptr);
+    case OP_SET_CLOCK: EL(c, now, 1, 0) = G.t_in[b]; break;
+    case OP_GET_CLOCK: G.t[b] = now; break;
+    case OP_TASK_UPDATE: {
+        unsigned char* nw = G.newly ? G.newly + (size_t)b * c.T : nullptr;
+        if (nw) for (int j = 0; j < c.T; ++j) nw[j] = 0;
+        t_task_update(c, st, now, nw);
+    } break;
+    case OP_AGENT_UPDATE: t_agent_update(c, st, now, st.route); break;   // full reference loop (max_waiting_time may have changed)
+    case OP_APPLY_MEMBERS: {
+        const int n = G.n_members[b]; const int action = G.action[b];
+        if (n <= 0) break;
+        unsigned flags = EL(c, flags, 1, 0);
+        if (action < 0 || action > c.T || n > c.A) flags |= ENV_ERR_ACTION;
+        else {
+            double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
+            double reward = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const int i = G.members[(size_t)b * G.mstride + k];
+                if (i < 0 || i >= c.A) { flags |= ENV_ERR_ACTION; continue; }
+                double d, tt; travel(c, EL(c, a_x, c.A, i), EL(c, a_y, c.A, i), tx, ty, d, tt);
+                t_agent_step(c, st, now, i, action, tx, ty, d, tt, flags);
+                reward += -tt;                                                // task_env.py:337-339
+            }
+            if (G.reward) G.reward[b] = reward / (double)n;                   // :341
+        }
+        EL(c, flags, 1, 0) = flags;
     } break;
     case OP_CHECK_FINISHED: {
-        double t; u64 d = dev_next_decision<AR>(R, lane, t);
+        double t; const u64 d = t_next_decision(c, t);
         bool fin = false;
-        if (d == 0) { fin = dev_all_returned_and_finished(R, lane); if (lane == 0) R.hdr->now = t; dirty = true; }
-        if (lane == 0) G.finished[e] = fin ? 1 : 0;
+        if (d == 0) { fin = t_all_returned_and_finished(c, st); EL(c, now, 1, 0) = t; }
+        G.finished[b] = fin ? 1 : 0;
     } break;
     case OP_COMPUTE_METRICS: {
-        double t = dev_episode_metrics<AR>(R, lane, now, R.hdr->n_steps, G.metrics + (size_t)e * 8);
-        if (lane == 0) R.hdr->now = t;
-        dirty = true;
+        const double t = t_episode_metrics(c, st, now, EL(c, n_steps, 1, 0), G.metrics + (size_t)b * 8,
+                                           G.task_wait ? G.task_wait + (size_t)b * c.T : nullptr,
+                                           G.agent_wait ? G.agent_wait + (size_t)b * c.A : nullptr);
+        EL(c, now, 1, 0) = t;
     } break;
-    case OP_ENV_FLAGS:
-        if (lane == 0) G.flags_out[e] = flags;
-        break;
+    case OP_ENV_FLAGS: G.flags_out[b] = EL(c, flags, 1, 0); break;
     }
-    if (dirty) { __syncwarp(); copy16(g_dyn, dyn_s, L.dyn_bytes, lane); }
+    st_state(c, st0, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_routes: pre_set_route + execute_by_route (task_env.py:562-599), one whole episode per warp
+// k_routes: pre_set_route + execute_by_route (task_env.py:562-599), one whole episode per thread
 // ---------------------------------------------------------------------------------------------------------------
-template <int AR>
-__global__ void __launch_bounds__(32 * DCM_WARPS) k_routes(const __grid_constant__ EnvArgs E, const int* routes, int rstride, const int* route_len,
-                                                           double* makespan) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * DCM_WARPS + warp;
-    if (e >= E.B) return;
-    const DcmLayout& L = E.L;
-    unsigned char* dyn_s = smem + (size_t)warp * (L.dyn_bytes + L.stage_bytes);
-    unsigned char* g_dyn = E.dyn + (size_t)e * L.dyn_bytes;
-    copy16(dyn_s, g_dyn, L.dyn_bytes, lane);
-    __syncwarp();
-    Rec R = make_rec(dyn_s, E.sta + (size_t)e * L.sta_bytes, dyn_s + L.dyn_bytes, L, 100.0 /* :564 */, E.vel, E.max_time);
-    double now = R.hdr->now; unsigned flags = R.hdr->flags; unsigned n_steps = R.hdr->n_steps;
-    unsigned char* pos = R.stage + 8 * L.Ap + L.Ap;                             // per-agent route cursor... needs A bytes beyond mlist
-    // the cursor lives in the tail of the stage area: stage_bytes >= 8*(Tp+Ap) + 8*Ap + Ap > 8*Ap + 2*Ap
-    for (int i = lane; i < L.A; i += 32) pos[i] = 0;
-    __syncwarp();
-    unsigned char* mlist = R.stage + 8 * L.Ap; double* rew = (double*)R.stage;
+template <int TW>
+__global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__ EnvArgs E, const int* routes, int rstride, const int* route_len,
+                                                         unsigned char* cursor /*[B,A] scratch*/, double* makespan) {
+    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c{E.S, (unsigned)b >> 5, (unsigned)b & 31u, E.S.A, E.S.T, E.S.MC, 100.0 /* :564 */, E.vel, E.max_time};
+    double now = EL(c, now, 1, 0); unsigned flags = EL(c, flags, 1, 0); unsigned n_steps = EL(c, n_steps, 1, 0);
+    unsigned char* pos = cursor + (size_t)b * c.A;
+    for (int i = 0; i < c.A; ++i) pos[i] = 0;
+    St<TW> st, st0; ld_state(c, st); st0 = st;
     bool finished = flags & ENV_FINISHED;
     int guard = 0;
-    while (!finished && now < 200.0 && guard < 100000) {                        // :565
-        double t; u64 dec = dev_next_decision<AR>(R, lane, t);                  // :568
-        now = t;                                                                // :569
-        dev_task_update(R, lane, now, nullptr); dev_agent_update(R, lane, now); // :570-571
-        u64 d = dec;
-        while (d) {                                                             // :572 ascending ids
-            int a = __ffsll((long long)d) - 1; d &= d - 1;
-            int p = pos[a]; int len = route_len[(size_t)e * L.A + a];
-            int act = 0;                                                        // :573-574 empty / exhausted route -> depot
-            if (p < len) { act = routes[((size_t)e * L.A + a) * rstride + p]; }
-            __syncwarp();
-            if (lane == 0) { if (p < len) pos[a] = (unsigned char)(p + 1); mlist[0] = (unsigned char)a; }
-            __syncwarp();
-            if (act < 0 || act > L.T) { flags |= ENV_ERR_ACTION; act = 0; }
-            dev_apply_members(R, lane, now, act, mlist, 1, rew, flags);         // :585 agent_step
-            dev_task_update(R, lane, now, nullptr); dev_agent_update(R, lane, now);   // :586-587
+    while (!finished && now < 200.0 && guard < 100000) {                      // :565
+        double t; const u64 dec = t_next_decision(c, t);                      // :568
+        now = t;                                                              // :569
+        t_task_update(c, st, now, nullptr); t_agent_update(c, st, now, st.route);   // :570-571
+        for (u64 d = dec; d; d &= d - 1) {                                    // :572 ascending ids
+            const int a = __ffsll((long long)d) - 1;
+            const int p = pos[a], len = route_len[(size_t)b * c.A + a];
+            int act = 0;                                                      // :573-574 empty / exhausted route -> depot
+            if (p < len) { act = routes[((size_t)b * c.A + a) * rstride + p]; pos[a] = (unsigned char)(p + 1); }
+            if (act < 0 || act > c.T) { flags |= ENV_ERR_ACTION; act = 0; }
+            double tx, ty; node_xy(c, act == 0 ? DCM_NODE_DEPOT : (unsigned)(act - 1), tx, ty);
+            double dd, tt; travel(c, EL(c, a_x, c.A, a), EL(c, a_y, c.A, a), tx, ty, dd, tt);
+            t_agent_step(c, st, now, a, act, tx, ty, dd, tt, flags);          // :585 agent_step
+            t_task_update(c, st, now, nullptr); t_agent_update(c, st, now, st.route);   // :586-587
             ++n_steps;
         }
-        {                                                                       // :588 check_finished
-            double t2; u64 d2 = dev_next_decision<AR>(R, lane, t2);
-            if (d2 == 0) { now = t2; finished = dev_all_returned_and_finished(R, lane); }
-        }
+        double t2; const u64 d2 = t_next_decision(c, t2);                     // :588 check_finished
+        if (d2 == 0) { now = t2; finished = t_all_returned_and_finished(c, st); }
         ++guard;
     }
     if (finished) flags |= ENV_FINISHED;
     flags |= ENV_DONE;
-    if (lane == 0) {
-        R.hdr->now = now; R.hdr->flags = flags; R.hdr->n_steps = n_steps; R.hdr->leader = -1; R.hdr->pending = 0; R.hdr->group = 0;
-        if (makespan) makespan[e] = now;
-    }
-    __syncwarp();
-    copy16(g_dyn, dyn_s, L.dyn_bytes, lane);
+    EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, n_steps, 1, 0) = n_steps; EL(c, leader, 1, 0) = -1;
+    EL(c, pending, 1, 0) = 0; EL(c, group, 1, 0) = 0;
+    st_state(c, st0, st);
+    if (makespan) makespan[b] = now;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// instance kernels
+// instance / plumbing kernels (thread per env)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_generate(const EnvArgs E, int bump_instance) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= E.B) return;
-    DcmHdr* h = (DcmHdr*)(E.dyn + (size_t)warp * E.L.dyn_bytes + E.L.o_hdr);
-    unsigned inst = h->instance + (bump_instance ? 1u : 0u);
-    dev_generate(E.sta + (size_t)warp * E.L.sta_bytes, E.L, lane, E.seed, E.first_gid + (u64)warp, inst, E.gen_max_duration, E.gen_random_duration);
-    if (lane == 0) h->instance = inst;
+__global__ void k_generate(const __grid_constant__ EnvArgs E, int bump_instance) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    const unsigned inst = EL(c, instance, 1, 0) + (bump_instance ? 1u : 0u);
+    t_generate(c, E.seed, E.first_gid + (u64)b, inst, E.gen_max_duration, E.gen_random_duration);
+    EL(c, instance, 1, 0) = inst;
 }
 
-__global__ void k_pack_static(const EnvArgs E, const double* task_xy, const double* depot_xy, const int* req, const double* dur, int* bad) {
-    const int e = blockIdx.x; const DcmLayout& L = E.L;
-    unsigned char* sta = E.sta + (size_t)e * L.sta_bytes;
-    double* tx = (double*)(sta + L.s_tx); double* ty = (double*)(sta + L.s_ty); double* du = (double*)(sta + L.s_dur);
-    unsigned char* rq = sta + L.s_req;
-    for (int j = threadIdx.x; j < L.Tp; j += blockDim.x) {
-        if (j < L.T) {
-            tx[j] = task_xy[((size_t)e * L.T + j) * 2]; ty[j] = task_xy[((size_t)e * L.T + j) * 2 + 1];
-            du[j] = dur[(size_t)e * L.T + j];
-            int r = req[(size_t)e * L.T + j];
-            if (r < 1 || r > L.M) { atomicExch(bad, 1); r = r < 1 ? 1 : L.M; }
-            rq[j] = (unsigned char)r;
-        } else { tx[j] = 0; ty[j] = 0; du[j] = 0; rq[j] = 0; }
+__global__ void k_pack_static(const __grid_constant__ EnvArgs E, const double* task_xy, const double* depot_xy, const int* req, const double* dur) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    for (int j = 0; j < c.T; ++j) {
+        EL(c, s_tx, c.T, j) = task_xy[((size_t)b * c.T + j) * 2]; EL(c, s_ty, c.T, j) = task_xy[((size_t)b * c.T + j) * 2 + 1];
+        EL(c, s_dur, c.T, j) = dur[(size_t)b * c.T + j];
+        int r = req[(size_t)b * c.T + j]; r = r < 1 ? 1 : (r > c.s.M ? c.s.M : r);
+        EL(c, s_req, c.T, j) = (unsigned char)r;
     }
-    if (threadIdx.x == 0) { double* d = (double*)(sta + L.s_depot); d[0] = depot_xy[2 * (size_t)e]; d[1] = depot_xy[2 * (size_t)e + 1]; }
+    EL(c, s_dep, 2, 0) = depot_xy[2 * (size_t)b]; EL(c, s_dep, 2, 1) = depot_xy[2 * (size_t)b + 1];
 }
 
-__global__ void k_unpack_static(const EnvArgs E, double* task_xy, double* depot_xy, int* req, double* dur) {
-    const int e = blockIdx.x; const DcmLayout& L = E.L;
-    const unsigned char* sta = E.sta + (size_t)e * L.sta_bytes;
-    const double* tx = (const double*)(sta + L.s_tx); const double* ty = (const double*)(sta + L.s_ty); const double* du = (const double*)(sta + L.s_dur);
-    const unsigned char* rq = sta + L.s_req;
-    for (int j = threadIdx.x; j < L.T; j += blockDim.x) {
-        if (task_xy) { task_xy[((size_t)e * L.T + j) * 2] = tx[j]; task_xy[((size_t)e * L.T + j) * 2 + 1] = ty[j]; }
-        if (dur) dur[(size_t)e * L.T + j] = du[j];
-        if (req) req[(size_t)e * L.T + j] = rq[j];
+__global__ void k_unpack_static(const __grid_constant__ EnvArgs E, double* task_xy, double* depot_xy, int* req, double* dur) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    for (int j = 0; j < c.T; ++j) {
+        if (task_xy) { task_xy[((size_t)b * c.T + j) * 2] = EL(c, s_tx, c.T, j); task_xy[((size_t)b * c.T + j) * 2 + 1] = EL(c, s_ty, c.T, j); }
+        if (dur) dur[(size_t)b * c.T + j] = EL(c, s_dur, c.T, j);
+        if (req) req[(size_t)b * c.T + j] = EL(c, s_req, c.T, j);
     }
-    if (threadIdx.x == 0 && depot_xy) { const double* d = (const double*)(sta + L.s_depot); depot_xy[2 * (size_t)e] = d[0]; depot_xy[2 * (size_t)e + 1] = d[1]; }
+    if (depot_xy) { depot_xy[2 * (size_t)b] = EL(c, s_dep, 2, 0); depot_xy[2 * (size_t)b + 1] = EL(c, s_dep, 2, 1); }
 }
 
-__global__ void k_init_dyn(const EnvArgs E) {          // zero records, mark every env as "done" until dcm_reset
-    const int e = blockIdx.x; const DcmLayout& L = E.L;
-    unsigned char* dyn = E.dyn + (size_t)e * L.dyn_bytes;
-    for (int i = threadIdx.x; i < L.dyn_bytes; i += blockDim.x) dyn[i] = 0;
-    __syncthreads();
-    if (threadIdx.x == 0) { DcmHdr* h = (DcmHdr*)(dyn + L.o_hdr); h->flags = ENV_DONE; h->leader = -1; }
+__global__ void k_init(const __grid_constant__ EnvArgs E) {                   // every env is "done" until dcm_reset
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= E.S.NT * 32) return;
+    const TC c = make_tc(E, b);
+    EL(c, flags, 1, 0) = ENV_DONE; EL(c, leader, 1, 0) = -1;
 }
 
-__global__ void k_sum_steps(const EnvArgs E, unsigned long long* out) {
+// tiled SoA <-> per-env record of dcm_layout.h (export / import / checkpoint format)
+template <int TW>
+__global__ void k_export(const __grid_constant__ EnvArgs E, const DcmLayout L, unsigned char* dst) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    St<TW> st; ld_state(c, st);
+    unsigned char* r = dst + (size_t)b * L.dyn_bytes;
+    const int T = c.T, A = c.A, Tp = L.Tp, R = c.MC * T;
+    for (int s = 0; s < c.MC; ++s) for (int j = 0; j < T; ++j) {
+        ((double*)(r + L.o_arr))[s * Tp + j] = EL(c, t_arr, R, s * T + j); (r + L.o_mem)[s * Tp + j] = EL(c, t_mem, R, s * T + j);
+    }
+    for (int j = 0; j < T; ++j) {
+        const bool fe = tbit<TW>(st.feas, j);
+        ((double*)(r + L.o_tstart))[j] = fe ? EL(c, t_start, T, j) : 0.0; ((unsigned short*)(r + L.o_tnab))[j] = EL(c, t_nab, T, j);
+        (r + L.o_nmem)[j] = tbit<TW>(st.ne, j) ? EL(c, t_nmem, T, j) : 0; ((signed char*)(r + L.o_status))[j] = EL(c, t_status, T, j);
+        (r + L.o_tflags)[j] = (unsigned char)((fe ? DCM_TF_FEAS : 0u) | (tbit<TW>(st.fin, j) ? DCM_TF_FIN : 0u) | (tbit<TW>(st.stale, j) ? DCM_TF_STALE : 0u));
+    }
+    for (int i = 0; i < A; ++i) {
+        ((double*)(r + L.o_alast))[i] = EL(c, a_last, A, i); ((double*)(r + L.o_and))[i] = EL(c, a_nd, A, i); ((double*)(r + L.o_adist))[i] = EL(c, a_dist, A, i);
+        ((unsigned short*)(r + L.o_anab))[i] = EL(c, a_nab, A, i); (r + L.o_anode)[i] = EL(c, a_node, A, i);
+        const u64 bit = 1ull << i;
+        (r + L.o_aflags)[i] = (unsigned char)(((st.route & bit) ? DCM_AF_ROUTE : 0u) | ((st.assigned & bit) ? DCM_AF_ASSIGNED : 0u) | ((st.returned & bit) ? DCM_AF_RETURNED : 0u) |
+                                              ((st.member & bit) ? DCM_AF_MEMBER : 0u) | ((st.touched & bit) ? DCM_AF_TOUCHED : 0u) | ((st.watch & bit) ? DCM_AF_WATCH : 0u));
+    }
+    DcmHdr h;
+    h.now = EL(c, now, 1, 0); h.pending = EL(c, pending, 1, 0); h.group = EL(c, group, 1, 0); h.n_steps = EL(c, n_steps, 1, 0);
+    h.episode = EL(c, episode, 1, 0); h.leader = EL(c, leader, 1, 0); h.flags = EL(c, flags, 1, 0); h.instance = EL(c, instance, 1, 0);
+    h.total_steps = EL(c, total, 1, 0);
+    *(DcmHdr*)(r + L.o_hdr) = h;
+}
+
+template <int TW>
+__global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, const unsigned char* src) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    St<TW> st, st0; ld_state(c, st0);
+#pragma unroll
+    for (int w = 0; w < TW; ++w) { st.feas[w] = st.fin[w] = st.ne[w] = st.open[w] = st.stale[w] = 0; }
+    st.route = st.assigned = st.returned = st.member = st.depot = st.touched = st.watch = 0;
+    const unsigned char* r = src + (size_t)b * L.dyn_bytes;
+    const int T = c.T, A = c.A, Tp = L.Tp, R = c.MC * T;
+    for (int s = 0; s < c.MC; ++s) for (int j = 0; j < T; ++j) {
+        EL(c, t_arr, R, s * T + j) = ((const double*)(r + L.o_arr))[s * Tp + j]; EL(c, t_mem, R, s * T + j) = (r + L.o_mem)[s * Tp + j];
+    }
+    for (int j = 0; j < T; ++j) {
+        EL(c, t_start, T, j) = ((const double*)(r + L.o_tstart))[j]; EL(c, t_nab, T, j) = ((const unsigned short*)(r + L.o_tnab))[j];
+        const int n = (r + L.o_nmem)[j]; const int stt = ((const signed char*)(r + L.o_status))[j]; const unsigned tf = (r + L.o_tflags)[j];
+        EL(c, t_nmem, T, j) = (unsigned char)n; EL(c, t_status, T, j) = (signed char)stt;
+        tset<TW>(st.feas, j, tf & DCM_TF_FEAS); tset<TW>(st.fin, j, tf & DCM_TF_FIN); tset<TW>(st.stale, j, tf & DCM_TF_STALE);
+        tset<TW>(st.ne, j, n > 0); tset<TW>(st.open, j, !(tf & DCM_TF_FEAS) && stt > 0);
+    }
+    for (int i = 0; i < A; ++i) {
+        EL(c, a_last, A, i) = ((const double*)(r + L.o_alast))[i]; EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i]; EL(c, a_dist, A, i) = ((const double*)(r + L.o_adist))[i];
+        const unsigned node = (r + L.o_anode)[i]; const unsigned af = (r + L.o_aflags)[i]; const u64 bit = 1ull << i;
+        EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; EL(c, a_node, A, i) = (unsigned char)node;
+        double x, y; node_xy(c, node, x, y); EL(c, a_x, A, i) = x; EL(c, a_y, A, i) = y;
+        if (af & DCM_AF_ROUTE) st.route |= bit;
+        if (af & DCM_AF_ASSIGNED) st.assigned |= bit;
+        if (af & DCM_AF_RETURNED) st.returned |= bit;
+        if (af & DCM_AF_MEMBER) st.member |= bit;
+        if (af & DCM_AF_TOUCHED) st.touched |= bit;
+        if (af & DCM_AF_WATCH) st.watch |= bit;
+        if ((af & DCM_AF_ROUTE) && node == DCM_NODE_DEPOT) st.depot |= bit;
+    }
+    st_state(c, st0, st);
+    const DcmHdr h = *(const DcmHdr*)(r + L.o_hdr);
+    EL(c, now, 1, 0) = h.now; EL(c, pending, 1, 0) = h.pending; EL(c, group, 1, 0) = h.group; EL(c, n_steps, 1, 0) = h.n_steps;
+    EL(c, episode, 1, 0) = h.episode; EL(c, leader, 1, 0) = h.leader; EL(c, flags, 1, 0) = h.flags; EL(c, instance, 1, 0) = h.instance;
+    EL(c, total, 1, 0) = h.total_steps;
+}
+
+__global__ void k_sum_steps(const __grid_constant__ EnvArgs E, unsigned long long* out) {
     unsigned long long acc = 0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E.B; e += gridDim.x * blockDim.x)
-        acc += ((const DcmHdr*)(E.dyn + (size_t)e * E.L.dyn_bytes + E.L.o_hdr))->total_steps;
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < E.S.B; b += gridDim.x * blockDim.x) { const TC c = make_tc(E, b); acc += EL(c, total, 1, 0); }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
@@ -436,36 +512,37 @@ static int fail_cuda(cudaError_t e, const char* where) {
     g_err = buf; return DCM_ERR_CUDA;
 }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail_cuda(_e, #call); } while (0)
+// kernels are instantiated for 1, 2 and 4 mask words (T <= 64 / 128 / 254)
+#define LAUNCH_TW(v, kern, grid, block, stream, ...) do { \
+    if ((v)->E.S.TW == 1) kern<1><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
+    else if ((v)->E.S.TW == 2) kern<2><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
+    else kern<4><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); } while (0)
 
 struct dcm_env {
-    int device; EnvArgs E; bool have_instances;
+    int device; EnvArgs E; DcmLayout L; bool have_instances;
+    unsigned char* arena; size_t arena_bytes;
     double* metrics;                 // [B,8]
     unsigned long long* d_counter;   // scratch for reductions
-    int* d_bad;
+    unsigned char* d_cursor;         // [B,A] route cursors
+    unsigned char* d_record;         // [B,dyn_bytes] export staging
     // dcm_step_host staging
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
     cudaStream_t hstream;
     uint64_t launches;
-    size_t smem_bytes;
 };
 
 struct DeviceGuard {
-    int prev; bool ok;
-    explicit DeviceGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess; }
-    ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
+    int prev, target; bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), target(dev) { ok = cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess); }
+    ~DeviceGuard() { if (ok && prev != target) cudaSetDevice(prev); }
 };
 
-static int grid_for(const dcm_env* v) { return (v->E.B + DCM_WARPS - 1) / DCM_WARPS; }
-
-template <typename K> static int set_smem(K kernel, size_t bytes) {
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return DCM_OK;
-}
+static int grid_env(const dcm_env* v, int threads) { return (v->E.S.B + threads - 1) / threads; }
 
 extern "C" {
 
 const char* dcm_last_error(void) { return g_err.c_str(); }
-const char* dcm_version(void) { return "dcmrta_b200 0.1 (sm_100a)"; }
+const char* dcm_version(void) { return "dcmrta_b200 0.3 (sm_100a, thread-per-env, tiled SoA + bitmask summaries)"; }
 
 int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t flags) {
     if (!out) return fail(DCM_ERR_ARG, "dcm_create: out is NULL");
@@ -481,28 +558,47 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!v) return fail(DCM_ERR_NOMEM, "dcm_create: host allocation failed");
     memset(v, 0, sizeof *v);
     v->device = device;
-    v->E.L = dcm_make_layout(A, T, M);
-    v->E.B = B; v->E.W = 10.0; v->E.vel = 0.2; v->E.max_time = 100.0; v->E.seed = 0; v->E.first_gid = 0; v->E.cflags = flags;
+    v->L = dcm_make_layout(A, T, M);
+    DcmSoa& S = v->E.S;
+    S.B = B; S.NT = (B + 31) / 32; S.A = A; S.T = T; S.M = M; S.MC = M; S.TW = T <= 64 ? 1 : (T <= 128 ? 2 : 4);
+    v->E.W = 10.0; v->E.vel = 0.2; v->E.max_time = 100.0; v->E.seed = 0; v->E.first_gid = 0; v->E.cflags = flags;
     v->E.gen_max_duration = 5.0; v->E.gen_random_duration = 0;
-    v->smem_bytes = (size_t)DCM_WARPS * (v->E.L.dyn_bytes + v->E.L.stage_bytes);
-    if (v->smem_bytes > 227 * 1024) { delete v; return fail(DCM_ERR_SHAPE, "dcm_create: per-CTA shared memory exceeds 227 KB for this shape"); }
-    const DcmLayout& L = v->E.L;
-    cudaError_t e = cudaSuccess;
-    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    alloc((void**)&v->E.dyn, (size_t)B * L.dyn_bytes);
-    alloc((void**)&v->E.sta, (size_t)B * L.sta_bytes);
-    alloc((void**)&v->metrics, (size_t)B * 8 * sizeof(double));
-    alloc((void**)&v->d_counter, sizeof(unsigned long long));
-    alloc((void**)&v->d_bad, sizeof(int));
+    // carve one arena; every array is [NT][K][32], 256-byte aligned
+    const int NT = S.NT, R = M * T, TW = S.TW;
+    size_t off = 0;
+    auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(NT, K, elem) + 255) / 256 * 256; return o; };
+    const size_t o_t_arr = carve(R, 8), o_t_start = carve(T, 8), o_a_last = carve(A, 8), o_a_nd = carve(A, 8), o_a_dist = carve(A, 8),
+                 o_now = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8), o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8),
+                 o_s_dep = carve(2, 8), o_w_agent = carve(A, 8), o_a_x = carve(A, 8), o_a_y = carve(A, 8),
+                 o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_stale = carve(TW, 8),
+                 o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
+                 o_am_touched = carve(1, 8), o_am_watch = carve(1, 8),
+                 o_n_steps = carve(1, 4), o_episode = carve(1, 4), o_flags = carve(1, 4), o_instance = carve(1, 4), o_total = carve(1, 4), o_leader = carve(1, 4),
+                 o_t_nab = carve(T, 2), o_a_nab = carve(A, 2),
+                 o_t_mem = carve(R, 1), o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(A, 1),
+                 o_s_req = carve(T, 1);
+    v->arena_bytes = off;
+    cudaError_t e = cudaMalloc((void**)&v->arena, off);
+    if (e == cudaSuccess) e = cudaMemset(v->arena, 0, off);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->metrics, (size_t)B * 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(v->metrics, 0, (size_t)B * 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_counter, sizeof(unsigned long long));
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
-    int rc;
-    if ((rc = set_smem(k_fused<1>, v->smem_bytes)) || (rc = set_smem(k_fused<2>, v->smem_bytes)) ||
-        (rc = set_smem(k_granular<1>, v->smem_bytes)) || (rc = set_smem(k_granular<2>, v->smem_bytes)) ||
-        (rc = set_smem(k_routes<1>, v->smem_bytes)) || (rc = set_smem(k_routes<2>, v->smem_bytes))) { dcm_destroy(v); return rc; }
-    k_init_dyn<<<B, 128>>>(v->E);
-    e = cudaMemset(v->metrics, 0, (size_t)B * 8 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemset(v->E.sta, 0, (size_t)B * L.sta_bytes);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    unsigned char* a = v->arena;
+    S.t_arr = (double*)(a + o_t_arr); S.t_start = (double*)(a + o_t_start); S.a_last = (double*)(a + o_a_last); S.a_nd = (double*)(a + o_a_nd);
+    S.a_dist = (double*)(a + o_a_dist); S.now = (double*)(a + o_now); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
+    S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dep = (double*)(a + o_s_dep);
+    S.w_agent = (double*)(a + o_w_agent); S.a_x = (double*)(a + o_a_x); S.a_y = (double*)(a + o_a_y);
+    S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_stale = (u64*)(a + o_m_stale);
+    S.am_route = (u64*)(a + o_am_route); S.am_assigned = (u64*)(a + o_am_assigned); S.am_returned = (u64*)(a + o_am_returned); S.am_member = (u64*)(a + o_am_member);
+    S.am_depot = (u64*)(a + o_am_depot); S.am_touched = (u64*)(a + o_am_touched); S.am_watch = (u64*)(a + o_am_watch);
+    S.n_steps = (unsigned*)(a + o_n_steps); S.episode = (unsigned*)(a + o_episode); S.flags = (unsigned*)(a + o_flags);
+    S.instance = (unsigned*)(a + o_instance); S.total = (unsigned*)(a + o_total); S.leader = (int*)(a + o_leader);
+    S.t_nab = (unsigned short*)(a + o_t_nab); S.a_nab = (unsigned short*)(a + o_a_nab);
+    S.t_mem = a + o_t_mem; S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status);
+    S.a_node = a + o_a_node; S.s_req = a + o_s_req;
+    k_init<<<(S.NT * 32 + 127) / 128, 128>>>(v->E);
+    e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dcm_destroy(v); return fail_cuda(e, "dcm_create init"); }
     v->launches = 1;
     *out = v;
@@ -512,7 +608,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
 int dcm_destroy(dcm_env* v) {
     if (!v) return DCM_OK;
     DeviceGuard g(v->device);
-    cudaFree(v->E.dyn); cudaFree(v->E.sta); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_bad);
+    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_cursor); cudaFree(v->d_record);
     cudaFree(v->d_action); cudaFree(v->d_agent); cudaFree(v->d_task); cudaFree(v->d_mask); cudaFree(v->d_leader); cudaFree(v->d_reward); cudaFree(v->d_done);
     if (v->hstream) cudaStreamDestroy(v->hstream);
     delete v;
@@ -535,9 +631,7 @@ int dcm_seed(dcm_env* v, uint64_t seed, uint64_t first_gid) {
 int dcm_load_instances(dcm_env* v, const double* task_xy, const double* depot_xy, const int32_t* req, const double* dur, void* stream) {
     if (!v || !task_xy || !depot_xy || !req || !dur) return fail(DCM_ERR_ARG, "dcm_load_instances: NULL argument");
     DeviceGuard g(v->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(v->d_bad, 0, sizeof(int), s));
-    k_pack_static<<<v->E.B, 64, 0, s>>>(v->E, task_xy, depot_xy, req, dur, v->d_bad);
+    k_pack_static<<<grid_env(v, 128), 128, 0, (cudaStream_t)stream>>>(v->E, task_xy, depot_xy, req, dur);
     CK(cudaGetLastError());
     v->launches++; v->have_instances = true;
     return DCM_OK;
@@ -546,8 +640,8 @@ int dcm_load_instances(dcm_env* v, const double* task_xy, const double* depot_xy
 int dcm_load_instances_host(dcm_env* v, const double* task_xy, const double* depot_xy, const int32_t* req, const double* dur) {
     if (!v || !task_xy || !depot_xy || !req || !dur) return fail(DCM_ERR_ARG, "dcm_load_instances_host: NULL argument");
     DeviceGuard g(v->device);
-    const size_t B = v->E.B, T = v->E.L.T;
-    for (size_t k = 0; k < B * T; ++k) if (req[k] < 1 || req[k] > v->E.L.M) return fail(DCM_ERR_ARG, "dcm_load_instances_host: requirement outside [1, M]");
+    const size_t B = v->E.S.B, T = v->E.S.T;
+    for (size_t k = 0; k < B * T; ++k) if (req[k] < 1 || req[k] > v->E.S.M) return fail(DCM_ERR_ARG, "dcm_load_instances_host: requirement outside [1, M]");
     double *dxy = nullptr, *ddep = nullptr, *ddur = nullptr; int* dreq = nullptr;
     cudaError_t e = cudaMalloc(&dxy, B * T * 2 * 8);
     if (e == cudaSuccess) e = cudaMalloc(&ddep, B * 2 * 8);
@@ -568,8 +662,7 @@ int dcm_generate(dcm_env* v, double max_duration, int random_duration, void* str
     if (!v) return fail(DCM_ERR_ARG, "dcm_generate: env is NULL");
     DeviceGuard g(v->device);
     v->E.gen_max_duration = max_duration; v->E.gen_random_duration = random_duration;
-    const int threads = 128, warps = threads / 32;
-    k_generate<<<(v->E.B + warps - 1) / warps, threads, 0, (cudaStream_t)stream>>>(v->E, v->have_instances ? 1 : 0);
+    k_generate<<<grid_env(v, 128), 128, 0, (cudaStream_t)stream>>>(v->E, v->have_instances ? 1 : 0);
     CK(cudaGetLastError());
     v->launches++; v->have_instances = true;
     return DCM_OK;
@@ -579,19 +672,27 @@ int dcm_get_instances(dcm_env* v, double* task_xy, double* depot_xy, int32_t* re
     if (!v) return fail(DCM_ERR_ARG, "dcm_get_instances: env is NULL");
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_get_instances: no instances installed");
     DeviceGuard g(v->device);
-    k_unpack_static<<<v->E.B, 64, 0, (cudaStream_t)stream>>>(v->E, task_xy, depot_xy, req, dur);
+    k_unpack_static<<<grid_env(v, 128), 128, 0, (cudaStream_t)stream>>>(v->E, task_xy, depot_xy, req, dur);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
 }
 
-static int launch_fused(dcm_env* v, const FusedArgs& F, void* stream) {
-    DeviceGuard g(v->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (v->E.L.A <= 32) k_fused<1><<<grid_for(v), 32 * DCM_WARPS, v->smem_bytes, s>>>(v->E, F);
-    else k_fused<2><<<grid_for(v), 32 * DCM_WARPS, v->smem_bytes, s>>>(v->E, F);
+static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
+    const int tiles_per_block = OBS_THREADS / 32;
+    LAUNCH_TW(v, k_obs, (v->E.S.NT + tiles_per_block - 1) / tiles_per_block, OBS_THREADS, s, v->E, O);
     CK(cudaGetLastError());
     v->launches++;
+    return DCM_OK;
+}
+
+static int launch_step(dcm_env* v, const StepArgs& F, const ObsArgs& O, void* stream) {
+    DeviceGuard g(v->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
+    CK(cudaGetLastError());
+    v->launches++;
+    if (O.agent_obs || O.task_obs || O.mask) return launch_obs(v, O, s);
     return DCM_OK;
 }
 
@@ -599,10 +700,10 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
               int32_t* next_leader, void* stream) {
     if (!v) return fail(DCM_ERR_ARG, "dcm_reset: env is NULL");
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_reset: load or generate instances first");
-    FusedArgs F; memset(&F, 0, sizeof F);
-    F.mode = 1; F.which = which; F.leader_in = leader_in;
-    F.agent_obs = agent_obs; F.task_obs = task_obs; F.mask = mask; F.next_leader = next_leader; F.metrics = v->metrics;
-    return launch_fused(v, F, stream);
+    StepArgs F; memset(&F, 0, sizeof F);
+    F.mode = 1; F.which = which; F.leader_in = leader_in; F.next_leader = next_leader; F.metrics = v->metrics;
+    ObsArgs O{nullptr, agent_obs, task_obs, mask};
+    return launch_step(v, F, O, stream);
 }
 
 int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fstride, const int32_t* next_leader_in, int policy,
@@ -612,16 +713,16 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     if (policy < 0 || policy > 2) return fail(DCM_ERR_ARG, "dcm_step: unknown policy");
     if (policy == DCM_POLICY_EXTERNAL && !action) return fail(DCM_ERR_ARG, "dcm_step: action is NULL with the external policy");
     if (followers && fstride < 0) return fail(DCM_ERR_ARG, "dcm_step: negative follower stride");
-    FusedArgs F; memset(&F, 0, sizeof F);
+    StepArgs F; memset(&F, 0, sizeof F);
     F.mode = 0; F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
-    F.agent_obs = agent_obs; F.task_obs = task_obs; F.mask = mask; F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action;
-    F.metrics = v->metrics;
-    return launch_fused(v, F, stream);
+    F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action; F.metrics = v->metrics;
+    ObsArgs O{nullptr, agent_obs, task_obs, mask};
+    return launch_step(v, F, O, stream);
 }
 
 static int ensure_host_staging(dcm_env* v) {
     if (v->hstream) return DCM_OK;
-    const size_t B = v->E.B, A = v->E.L.A, T = v->E.L.T;
+    const size_t B = v->E.S.B, A = v->E.S.A, T = v->E.S.T;
     CK(cudaMalloc(&v->d_action, B * 4)); CK(cudaMalloc(&v->d_agent, B * A * 6 * 4)); CK(cudaMalloc(&v->d_task, B * (T + 1) * 5 * 4));
     CK(cudaMalloc(&v->d_mask, B * (T + 1))); CK(cudaMalloc(&v->d_leader, B * 4)); CK(cudaMalloc(&v->d_reward, B * 4)); CK(cudaMalloc(&v->d_done, B));
     CK(cudaStreamCreateWithFlags(&v->hstream, cudaStreamNonBlocking));
@@ -635,7 +736,7 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
     DeviceGuard g(v->device);
     int rc = ensure_host_staging(v);
     if (rc) return rc;
-    const size_t B = v->E.B, A = v->E.L.A, T = v->E.L.T;
+    const size_t B = v->E.S.B, A = v->E.S.A, T = v->E.S.T;
     cudaStream_t s = v->hstream;
     if (action) CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
     rc = dcm_step(v, v->d_action, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
@@ -653,16 +754,14 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
 int dcm_episode_metrics(dcm_env* v, double* out, void* stream) {
     if (!v || !out) return fail(DCM_ERR_ARG, "dcm_episode_metrics: NULL argument");
     DeviceGuard g(v->device);
-    CK(cudaMemcpyAsync(out, v->metrics, (size_t)v->E.B * 8 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(out, v->metrics, (size_t)v->E.S.B * 8 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DCM_OK;
 }
 
 static int launch_gran(dcm_env* v, const GranArgs& G, void* stream) {
     if (!v->have_instances) return fail(DCM_ERR_STATE, "granular op: load or generate instances first");
     DeviceGuard g(v->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (v->E.L.A <= 32) k_granular<1><<<grid_for(v), 32 * DCM_WARPS, v->smem_bytes, s>>>(v->E, G);
-    else k_granular<2><<<grid_for(v), 32 * DCM_WARPS, v->smem_bytes, s>>>(v->E, G);
+    LAUNCH_TW(v, k_granular, grid_env(v, STEP_THREADS), STEP_THREADS, (cudaStream_t)stream, v->E, G);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
@@ -695,14 +794,18 @@ int dcm_apply_members(dcm_env* v, const int32_t* action, const int32_t* members,
     return launch_gran(v, G, stream);
 }
 int dcm_build_obs(dcm_env* v, const int32_t* leader, float* agent_obs, float* task_obs, uint8_t* mask, void* stream) {
-    GRAN_BEGIN("dcm_build_obs", leader); G.op = OP_BUILD_OBS; G.leader = leader; G.agent_obs = agent_obs; G.task_obs = task_obs; G.mask = mask;
-    return launch_gran(v, G, stream);
+    if (!v || !leader) return fail(DCM_ERR_ARG, "dcm_build_obs: NULL argument");
+    if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_build_obs: load or generate instances first");
+    DeviceGuard g(v->device);
+    ObsArgs O{leader, agent_obs, task_obs, mask};
+    return launch_obs(v, O, (cudaStream_t)stream);
 }
 int dcm_check_finished(dcm_env* v, uint8_t* finished, void* stream) {
     GRAN_BEGIN("dcm_check_finished", finished); G.op = OP_CHECK_FINISHED; G.finished = finished; return launch_gran(v, G, stream);
 }
-int dcm_compute_metrics(dcm_env* v, double* out, void* stream) {
-    GRAN_BEGIN("dcm_compute_metrics", out); G.op = OP_COMPUTE_METRICS; G.metrics = out; return launch_gran(v, G, stream);
+int dcm_compute_metrics(dcm_env* v, double* out, double* task_wait, double* agent_wait, void* stream) {
+    GRAN_BEGIN("dcm_compute_metrics", out); G.op = OP_COMPUTE_METRICS; G.metrics = out; G.task_wait = task_wait; G.agent_wait = agent_wait;
+    return launch_gran(v, G, stream);
 }
 int dcm_env_flags(dcm_env* v, uint32_t* flags, void* stream) {
     GRAN_BEGIN("dcm_env_flags", flags); G.op = OP_ENV_FLAGS; G.flags_out = flags; return launch_gran(v, G, stream);
@@ -713,37 +816,49 @@ int dcm_execute_by_route(dcm_env* v, const int32_t* routes, int rstride, const i
     if (rstride > 255) return fail(DCM_ERR_SHAPE, "dcm_execute_by_route: routes longer than 255 are not supported");
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_execute_by_route: load instances first");
     DeviceGuard g(v->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (v->E.L.A <= 32) k_routes<1><<<grid_for(v), 32 * DCM_WARPS, v->smem_bytes, s>>>(v->E, routes, rstride, route_len, makespan);
-    else k_routes<2><<<grid_for(v), 32 * DCM_WARPS, v->smem_bytes, s>>>(v->E, routes, rstride, route_len, makespan);
+    if (!v->d_cursor) CK(cudaMalloc(&v->d_cursor, (size_t)v->E.S.B * v->E.S.A));
+    LAUNCH_TW(v, k_routes, grid_env(v, STEP_THREADS), STEP_THREADS, (cudaStream_t)stream, v->E, routes, rstride, route_len, v->d_cursor, makespan);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
 }
 
-size_t dcm_record_bytes(const dcm_env* v) { return v ? (size_t)v->E.L.dyn_bytes : 0; }
+size_t dcm_record_bytes(const dcm_env* v) { return v ? (size_t)v->L.dyn_bytes : 0; }
 
 int dcm_export_state(dcm_env* v, void* dst, size_t bytes, void* stream) {
     if (!v || !dst) return fail(DCM_ERR_ARG, "dcm_export_state: NULL argument");
-    if (bytes < (size_t)v->E.B * v->E.L.dyn_bytes) return fail(DCM_ERR_ARG, "dcm_export_state: buffer too small");
+    const size_t need = (size_t)v->E.S.B * v->L.dyn_bytes;
+    if (bytes < need) return fail(DCM_ERR_ARG, "dcm_export_state: buffer too small");
     DeviceGuard g(v->device);
-    CK(cudaMemcpyAsync(dst, v->E.dyn, (size_t)v->E.B * v->E.L.dyn_bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    if (!v->d_record) { CK(cudaMalloc(&v->d_record, need)); }
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(v->d_record, 0, need, s));
+    LAUNCH_TW(v, k_export, grid_env(v, 128), 128, s, v->E, v->L, v->d_record);
+    CK(cudaGetLastError());
+    v->launches++;
+    CK(cudaMemcpyAsync(dst, v->d_record, need, cudaMemcpyDefault, s));
     return DCM_OK;
 }
 int dcm_import_state(dcm_env* v, const void* src, size_t bytes, void* stream) {
     if (!v || !src) return fail(DCM_ERR_ARG, "dcm_import_state: NULL argument");
-    if (bytes != (size_t)v->E.B * v->E.L.dyn_bytes) return fail(DCM_ERR_ARG, "dcm_import_state: size mismatch");
+    const size_t need = (size_t)v->E.S.B * v->L.dyn_bytes;
+    if (bytes != need) return fail(DCM_ERR_ARG, "dcm_import_state: size mismatch");
     DeviceGuard g(v->device);
-    CK(cudaMemcpyAsync(v->E.dyn, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    if (!v->d_record) { CK(cudaMalloc(&v->d_record, need)); }
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(v->d_record, src, need, cudaMemcpyDefault, s));
+    LAUNCH_TW(v, k_import, grid_env(v, 128), 128, s, v->E, v->L, v->d_record);
+    CK(cudaGetLastError());
+    v->launches++;
     return DCM_OK;
 }
 
 int dcm_layout(const dcm_env* v, int32_t* out, int n) {
     if (!v || !out) return 0;
-    const DcmLayout& L = v->E.L;
+    const DcmLayout& L = v->L;
     const int vals[] = {L.A, L.T, L.M, L.MC, L.Tp, L.Ap, L.o_arr, L.o_tstart, L.o_alast, L.o_and, L.o_adist, L.o_hdr, L.o_tnab, L.o_anab,
                         L.o_mem, L.o_nmem, L.o_status, L.o_tflags, L.o_anode, L.o_aflags, L.dyn_bytes,
-                        L.s_tx, L.s_ty, L.s_dur, L.s_depot, L.s_req, L.sta_bytes, L.stage_bytes, DCM_WARPS};
+                        L.s_tx, L.s_ty, L.s_dur, L.s_depot, L.s_req, L.sta_bytes, L.stage_bytes, 32};
     const int cnt = (int)(sizeof vals / sizeof vals[0]);
     for (int i = 0; i < n && i < cnt; ++i) out[i] = vals[i];
     return cnt < n ? cnt : n;
@@ -764,7 +879,7 @@ int dcm_total_steps(dcm_env* v, uint64_t* out) {
 
 size_t dcm_algorithmic_bytes_per_step(const dcm_env* v) {
     if (!v) return 0;
-    const size_t A = v->E.L.A, T = v->E.L.T, M = v->E.L.M, w = 8;
+    const size_t A = v->E.S.A, T = v->E.S.T, M = v->E.S.M, w = 8;
     const size_t s_static = 2 * w * T + 2 * w + T + w * T;
     const size_t s_dyn = T * (M * (1 + w) + 2 * w + 5) + A * (3 * w + 4) + 40;
     const size_t s_obs = 4 * 6 * A + 4 * 5 * (T + 1) + (T + 1);

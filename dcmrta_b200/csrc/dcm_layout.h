@@ -20,9 +20,13 @@
 
 #define DCM_TF_FEAS 1u       // task flags
 #define DCM_TF_FIN 2u
+#define DCM_TF_STALE 4u      // bookkeeping: members removed after status was computed (Q3)
 #define DCM_AF_ROUTE 1u      // agent flags: len(route) > 0
 #define DCM_AF_ASSIGNED 2u
 #define DCM_AF_RETURNED 4u
+#define DCM_AF_MEMBER 8u     // bookkeeping bits (not reference state): member of the task it stands at,
+#define DCM_AF_TOUCHED 16u   // next agent_update must recompute it,
+#define DCM_AF_WATCH 32u     // waiting for now >= time_start
 
 struct DcmHdr {              // 48 bytes
     double now;                      // current_time

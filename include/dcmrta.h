@@ -146,8 +146,9 @@ int dcm_apply_members(dcm_env* env, const int32_t* action_d, const int32_t* memb
 int dcm_build_obs(dcm_env* env, const int32_t* leader_d, float* agent_obs_d, float* task_obs_d, uint8_t* mask_d, void* stream);
 /* check_finished (task_env.py:366-373), including its side effect on the clock: finished_d [B] u8 */
 int dcm_check_finished(dcm_env* env, uint8_t* finished_d, void* stream);
-/* get_episode_reward + metrics computed NOW for every env (same row layout as dcm_episode_metrics) */
-int dcm_compute_metrics(dcm_env* env, double* out_d, void* stream);
+/* get_episode_reward + metrics computed NOW for every env (same row layout as dcm_episode_metrics); optionally also the
+ * per-element sums calculate_waiting_time leaves in the dicts: task_wait_d [B,T], agent_wait_d [B,A] f64 (or NULL) */
+int dcm_compute_metrics(dcm_env* env, double* out_d, double* task_wait_d, double* agent_wait_d, void* stream);
 /* pre_set_route + execute_by_route (task_env.py:562-599): routes_d [B,A,rstride] i32 actions (0 = depot), route_len_d [B,A];
  * runs every env to completion in one launch with max_waiting_time = 100 and the 200 clock cap; makespan_d [B] f64 */
 int dcm_execute_by_route(dcm_env* env, const int32_t* routes_d, int rstride, const int32_t* route_len_d,
