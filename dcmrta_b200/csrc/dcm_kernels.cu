@@ -41,10 +41,8 @@ struct EnvArgs {
 };
 
 struct StepArgs {
-    int mode;                                  // 0 = step, 1 = reset
-    const int* action; const int* followers; int fstride; const int* leader_in; const unsigned char* which; int policy;
+    const int* action; const int* followers; int fstride; const int* leader_in; int policy;
     int* next_leader; float* reward; unsigned char* done; int* used_action;
-    double* metrics;                           // [B,8] last finished episode
 };
 
 struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask; };
@@ -81,8 +79,20 @@ __device__ __noinline__ void t_generate(const TC& c, u64 seed, u64 gid, unsigned
     EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w);                // :67
 }
 
+__device__ __forceinline__ void w_generate(const TC& c, unsigned lane, u64 seed, u64 gid, unsigned instance, double max_duration, int random_duration) {
+    const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), g0 = (unsigned)gid, g1 = (unsigned)(gid >> 32);
+    for (int j = lane; j < c.T; j += 32) {                                    // same streams as t_generate, lanes over tasks
+        const uint4 a = philox(g0, g1, instance, 0x80000000u + 2u * j, k0, k1);
+        const uint4 b = philox(g0, g1, instance, 0x80000001u + 2u * j, k0, k1);
+        EL(c, s_tx, c.T, j) = u01(a.x, a.y); EL(c, s_ty, c.T, j) = u01(a.z, a.w);
+        EL(c, s_req, c.T, j) = (unsigned char)(1 + pick(b.x, c.s.M));
+        EL(c, s_dur, c.T, j) = random_duration ? u01(b.y, b.z) * max_duration : max_duration;
+    }
+    if (lane == 0) { const uint4 a = philox(g0, g1, instance, 0xFFFFFFFFu, k0, k1); EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w); }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// k_step: reset / step
+// k_step: one leader decision per env
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int choose_leader(const TC& c, const Rng& rng, unsigned episode, unsigned n_steps, u64 pending, u64& group,
                                              unsigned& flags, const int* leader_in, int b) {
@@ -103,106 +113,242 @@ template <int TW>
 __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
-    if (F.mode == 1 && F.which && !F.which[b]) return;
     const TC c = make_tc(E, b);
+    unsigned flags = EL(c, flags, 1, 0);
+    if (flags & ENV_DONE) {                                                   // finished earlier and not restarted: untouched
+        if (F.next_leader) F.next_leader[b] = -1;
+        if (F.reward) F.reward[b] = 0.f;
+        if (F.done) F.done[b] = 1;
+        if (F.used_action) F.used_action[b] = -1;
+        return;
+    }
     St<TW> st, st0; ld_state(c, st); st0 = st;
     double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
-    unsigned n_steps = EL(c, n_steps, 1, 0), episode = EL(c, episode, 1, 0), flags = EL(c, flags, 1, 0);
+    unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0);
     int leader = EL(c, leader, 1, 0);
     const Rng rng{E.seed, E.first_gid + (u64)b};
-    float reward_out = 0.f; unsigned char done_out = 0; int action_out = -1;
-    bool dirty = true;
+    float reward_out = 0.f; int action_out = -1;
 
-    if (F.mode == 1) {                                                        // ---- dcm_reset
-        t_clear(c, st);
-        now = 0.0; pending = 0; group = 0; n_steps = 0; flags = 0; leader = -1;
-        t_advance(c, st, now, pending, flags);
-        if (!(flags & ENV_DONE)) leader = choose_leader(c, rng, episode, n_steps, pending, group, flags, F.leader_in, b);
-    } else if (flags & ENV_DONE) {                                            // ---- finished earlier, no auto-reset
-        done_out = 1; leader = -1; dirty = false;
-    } else {                                                                  // ---- dcm_step
-        bool ok = true;
-        uint4 b0 = make_uint4(0, 0, 0, 0);
-        bool have_b0 = false;
-        int action;
-        if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
-        else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
-        else action = F.action[b];
-        if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
-        int want = 0; u64 g = group & ~(1ull << leader);                      // task_env.py:328
-        const int* fp = F.followers ? F.followers + (size_t)b * F.fstride : nullptr;
-        if (ok) {
-            const int vacancy = action == 0 ? __popcll(group) : (int)EL(c, t_status, c.T, action - 1);   // :327
-            if (vacancy > 1) { const int avail = __popcll(g); want = vacancy - 1 < avail ? vacancy - 1 : avail; }   // :330-331
-            if (fp && action != 0) {                                          // validate injected followers before touching state
-                u64 gg = g;
-                for (int k = 0; k < want && ok; ++k) {
-                    const int fo = k < F.fstride ? fp[k] : -1;
-                    if (fo < 0 || fo >= c.A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
+    bool ok = true;
+    uint4 b0 = make_uint4(0, 0, 0, 0);
+    bool have_b0 = false;
+    int action;
+    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
+    else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
+    else action = F.action[b];
+    if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
+    int want = 0; u64 g = group & ~(1ull << leader);                          // task_env.py:328
+    const int* fp = F.followers ? F.followers + (size_t)b * F.fstride : nullptr;
+    if (ok) {
+        const int vacancy = action == 0 ? __popcll(group) : (int)EL(c, t_status, c.T, action - 1);   // :327
+        if (vacancy > 1) { const int avail = __popcll(g); want = vacancy - 1 < avail ? vacancy - 1 : avail; }   // :330-331
+        if (fp && action != 0) {                                              // validate injected followers before touching state
+            u64 gg = g;
+            for (int k = 0; k < want && ok; ++k) {
+                const int fo = k < F.fstride ? fp[k] : -1;
+                if (fo < 0 || fo >= c.A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
+            }
+            if (ok && want < F.fstride && fp[want] >= 0) ok = false;
+            if (!ok) flags |= ENV_ERR_FOLLOW;
+        }
+    }
+    if (ok) {
+        action_out = action;
+        // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
+        double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
+        double d, tt; travel(c, EL(c, a_x, c.A, leader), EL(c, a_y, c.A, leader), tx, ty, d, tt);
+        double reward = 0.0; int nm = 1;
+        t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt;
+        pending &= ~(1ull << leader);
+        if (action == 0) {                                                    // Q11: the whole remaining group follows to the depot
+            for (; g; g &= g - 1) { const int fo = ctz64(g); t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; pending &= ~(1ull << fo); }
+        } else {
+            uint4 blk = b0;
+            for (int k = 0; k < want; ++k) {
+                int fo;
+                if (fp) fo = fp[k];                                           // injected (trace replay)
+                else {                                                        // :331 uniform without replacement
+                    const int slot = 2 + k;
+                    if ((slot & 3) == 0 || !have_b0) { blk = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2)); have_b0 = true; }
+                    fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
                 }
-                if (ok && want < F.fstride && fp[want] >= 0) ok = false;
-                if (!ok) flags |= ENV_ERR_FOLLOW;
+                g &= ~(1ull << fo); pending &= ~(1ull << fo);
+                t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm;
             }
         }
-        if (ok) {
-            action_out = action;
-            // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
-            double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
-            double d, tt; travel(c, EL(c, a_x, c.A, leader), EL(c, a_y, c.A, leader), tx, ty, d, tt);
-            double reward = 0.0; int nm = 1;
-            t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt;
-            pending &= ~(1ull << leader);
-            if (action == 0) {                                                // Q11: the whole remaining group follows to the depot
-                for (; g; g &= g - 1) { const int fo = __ffsll((long long)g) - 1; t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; pending &= ~(1ull << fo); }
-            } else {
-                uint4 blk = b0;
-                for (int k = 0; k < want; ++k) {
-                    int fo;
-                    if (fp) fo = fp[k];                                       // injected (trace replay)
-                    else {                                                    // :331 uniform without replacement
-                        const int slot = 2 + k;
-                        if ((slot & 3) == 0 || !have_b0) { blk = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2)); have_b0 = true; }
-                        fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
-                    }
-                    g &= ~(1ull << fo); pending &= ~(1ull << fo);
-                    t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm;
-                }
-            }
-            reward_out = __double2float_rn(reward / (double)nm);              // :337-341
-            t_task_update(c, st, now, nullptr);                               // worker.py:74
-            t_agent_update(c, st, now, agents_to_update(st));                 // worker.py:76
-            ++n_steps; EL(c, total, 1, 0) = EL(c, total, 1, 0) + 1;
-            if (!pending) t_advance(c, st, now, pending, flags);              // worker.py:85, :45-51
-            if (flags & ENV_DONE) {
-                done_out = 1;
-                now = t_episode_metrics(c, st, now, n_steps, F.metrics + (size_t)b * 8, nullptr, nullptr);   // worker.py:87, :103-108
-                ++episode; leader = -1; group = 0;
-                if (E.cflags & DCM_FLAG_AUTO_RESET) {
-                    if (E.cflags & DCM_FLAG_REGENERATE) {
-                        const unsigned inst = EL(c, instance, 1, 0) + 1; EL(c, instance, 1, 0) = inst;
-                        t_generate(c, E.seed, rng.gid, inst, E.gen_max_duration, E.gen_random_duration);
-                    }
-                    t_clear(c, st);
-                    now = 0.0; pending = 0; n_steps = 0; flags = 0;
-                    t_advance(c, st, now, pending, flags);
-                }
-            }
-            if (!(flags & ENV_DONE)) leader = choose_leader(c, rng, episode, n_steps, pending, group, flags, F.leader_in, b);
-        }
+        reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
+        t_task_update(c, st, now, nullptr);                                   // worker.py:74
+        t_agent_update(c, st, now, agents_to_update(st));                     // worker.py:76
+        ++n_steps; EL(c, total, 1, 0) = EL(c, total, 1, 0) + 1;
+        if (!pending) t_advance(c, st, now, pending, flags);                  // worker.py:85, :45-51
+        if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
+        else leader = choose_leader(c, rng, episode, n_steps, pending, group, flags, F.leader_in, b);
     }
     if (F.next_leader) F.next_leader[b] = leader;
     if (F.reward) F.reward[b] = reward_out;
-    if (F.done) F.done[b] = done_out;
+    if (F.done) F.done[b] = (flags & ENV_DONE) ? 1 : 0;
     if (F.used_action) F.used_action[b] = action_out;
-    if (dirty) {
-        EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
-        EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags;
-        st_state(c, st0, st);
+    EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
+    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags;
+    st_state(c, st0, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_episode: episode accounting (worker.py:87, :103-108) and restart (clear_decisions + first slot + first leader) for
+// the envs that need it -- about 1 env in 125 per step -- done WARP-COOPERATIVELY (lanes over tasks / agents) by the
+// warp that owns the tile, so that this rare, long path stays off the critical path of k_step.
+//   mode 0: envs that k_step just finished (DONE and not yet ACCOUNTED); restart only with DCM_FLAG_AUTO_RESET
+//   mode 1: dcm_reset (every env, or those selected by `which`)
+// ---------------------------------------------------------------------------------------------------------------
+#define EPI_WARPS 4
+struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int* next_leader; double* metrics; };
+
+__device__ __forceinline__ double wmax(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; } return v; }
+__device__ __forceinline__ double wmin(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; } return v; }
+
+// out[8]: reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions.  Returns the final clock.
+template <int TW>
+__device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, double* scr) {
+    const int T = c.T, A = c.A, R = c.MC * c.T;
+    double* s_task = scr; double* s_ts = scr + T; double* s_agent = scr + 2 * T; double* s_dist = scr + 2 * T + A;
+    for (int j = lane; j < T; j += 32) {                                      // task['sum_waiting_time'] :349-357
+        const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
+        double v = w_ab;
+        const bool feas = tbit<TW>(st.feas, j);
+        if (tbit<TW>(st.ne, j)) {
+            const int n = EL(c, t_nmem, T, j);
+            double mx = EL(c, t_arr, R, j);
+            for (int s = 1; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); mx = a > mx ? a : mx; }
+            double acc = 0.0;                                                 // np.sum of < 8 terms is sequential
+            for (int s = 0; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); acc += feas ? (mx - a) : (now - a); }
+            v = acc + w_ab;
+        }
+        s_task[j] = v;
+        s_ts[j] = feas ? EL(c, t_start, T, j) : 0.0;
+    }
+    // agent sums in the reference order (tasks ascending, members in list order :358-362): the owner lanes of a task's
+    // slots broadcast (member, term) and the lane that maps to the member accumulates
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < TW; ++w) for (u64 mm = st.ne[w]; mm; mm &= mm - 1) {
+        const int j = 64 * w + ctz64(mm);
+        const int n = EL(c, t_nmem, T, j);
+        const bool feas = (st.feas[w] >> (j & 63)) & 1ull;
+        double a = -CUDART_INF; unsigned m = 0;
+        if ((int)lane < n) { a = EL(c, t_arr, R, lane * T + j); m = EL(c, t_mem, R, lane * T + j); }
+        const double mx = wmax(a);
+        double add;
+        if (feas) add = mx - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }
+        for (int s = 0; s < n; ++s) {
+            const unsigned ms = __shfl_sync(0xffffffffu, m, s); const double as = __shfl_sync(0xffffffffu, add, s);
+            if (lane == (ms & 31u)) { if (ms < 32u) acc0 += as; else acc1 += as; }
+        }
+    }
+    for (int r = 0; r < 2; ++r) {                                             // + W per abandoned_agent entry (:363-364; added last, ~1e-16 rel.)
+        const int i = lane + 32 * r;
+        if (i < A) {
+            double acc = r ? acc1 : acc0;
+            for (int k = 0; k < (int)EL(c, a_nab, A, i); ++k) acc += c.W;
+            s_agent[i] = acc; s_dist[i] = EL(c, a_dist, A, i);
+        }
+    }
+    // :422 check_finished side effect on the clock
+    double mn = CUDART_INF, la = 0.0;
+    for (int i = lane; i < A; i += 32) { const double nd = EL(c, a_nd, A, i); if (nd < mn) mn = nd; const double l2 = EL(c, a_last, A, i); la = l2 > la ? l2 : la; }
+    mn = wmin(mn); la = wmax(la);
+    if (mn == CUDART_INF) now = la;
+    int nfin = 0;
+#pragma unroll
+    for (int w = 0; w < TW; ++w) nfin += __popcll(st.fin[w]);
+    __syncwarp();
+    if (lane == 0) {
+        out[0] = -now;                                                        // :424
+        out[1] = (double)nfin / (double)T;                                    // worker.py:103
+        out[2] = now;                                                         // :104
+        out[3] = np_sum([&](int j) { return s_ts[j]; }, T) / (double)T;       // :105 nanmean(time_start)
+        out[4] = np_sum([&](int i) { return s_agent[i]; }, A) / (double)A;    // :106
+        out[5] = np_sum([&](int i) { return s_dist[i]; }, A);                 // :107
+        out[6] = np_sum([&](int j) { return s_task[j]; }, T) / (double)T;     // :108
+        out[7] = (double)n_steps;
+    }
+    __syncwarp();
+    return now;
+}
+
+template <int TW>
+__global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
+    __shared__ double scratch[EPI_WARPS][2 * DCM_MAX_TASKS + 2 * DCM_MAX_AGENTS];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned tile = blockIdx.x * EPI_WARPS + warp;
+    if (tile >= (unsigned)E.S.NT) return;
+    const int B = E.S.B, A = E.S.A, T = E.S.T;
+    const int b = (int)(tile * 32 + lane);
+    bool need = false;
+    if (b < B) {
+        if (P.mode == 1) need = !P.which || P.which[b];
+        else { const unsigned f = E.S.flags[b]; need = (f & ENV_DONE) && !(f & ENV_ACCOUNTED); }   // K == 1: tiled index == linear index
+    }
+    for (unsigned todo = __ballot_sync(0xffffffffu, need); todo; todo &= todo - 1) {
+        const int be = (int)(tile * 32 + (__ffs(todo) - 1));
+        const TC c = make_tc(E, be);
+        St<TW> st; ld_state(c, st);
+        unsigned flags = EL(c, flags, 1, 0), episode = EL(c, episode, 1, 0);
+        const u64 gid = E.first_gid + (u64)be;
+        if (P.mode == 0) {
+            const double now = w_episode_metrics(c, st, lane, EL(c, now, 1, 0), EL(c, n_steps, 1, 0), P.metrics + (size_t)be * 8, scratch[warp]);
+            ++episode; flags |= ENV_ACCOUNTED;
+            if (!(E.cflags & DCM_FLAG_AUTO_RESET)) {
+                if (lane == 0) { EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, episode, 1, 0) = episode; }
+                continue;
+            }
+            if (E.cflags & DCM_FLAG_REGENERATE) {
+                const unsigned inst = EL(c, instance, 1, 0) + 1;
+                __syncwarp();
+                if (lane == 0) EL(c, instance, 1, 0) = inst;
+                w_generate(c, lane, E.seed, gid, inst, E.gen_max_duration, E.gen_random_duration);
+                __syncwarp();
+            }
+        }
+        // ---- clear_decisions (task_env.py:129-140), lanes over tasks / agents
+        for (int j = lane; j < T; j += 32) {
+            EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)EL(c, s_req, T, j); EL(c, t_start, T, j) = 0.0; EL(c, t_nab, T, j) = 0;
+        }
+        const double dx = EL(c, s_dep, 2, 0), dy = EL(c, s_dep, 2, 1);
+        for (int i = lane; i < A; i += 32) {
+            EL(c, a_last, A, i) = 0.0; EL(c, a_nd, A, i) = 0.0; EL(c, a_dist, A, i) = 0.0;
+            EL(c, a_node, A, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0; EL(c, a_x, A, i) = dx; EL(c, a_y, A, i) = dy;
+        }
+        // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
+        const u64 all = A >= 64 ? ~0ull : ((1ull << A) - 1);
+        unsigned nflags = 0; u64 pending = all, group = all; int leader;
+        if (!(0.0 < E.max_time)) { nflags = ENV_DONE | ENV_ACCOUNTED; pending = 0; group = 0; leader = -1; }
+        else {
+            const int inj = P.leader_in ? P.leader_in[be] : -1;
+            if (inj >= 0) { if (inj < A) leader = inj; else { nflags |= ENV_ERR_LEADER; leader = 0; } }
+            else if (A == 1) leader = 0;
+            else { const Rng rng{E.seed, gid}; leader = kth_bit(all, pick(draw_block(rng, episode, 0, 0).y, A)); }   // worker.py:54
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < TW; ++w) {
+                EL(c, m_feas, TW, w) = 0; EL(c, m_fin, TW, w) = 0; EL(c, m_ne, TW, w) = 0; EL(c, m_stale, TW, w) = 0;
+                EL(c, m_open, TW, w) = all_tasks<TW>(T, w);
+            }
+            EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
+            EL(c, am_depot, 1, 0) = 0; EL(c, am_touched, 1, 0) = 0; EL(c, am_watch, 1, 0) = 0;
+            EL(c, now, 1, 0) = 0.0; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = 0;
+            EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = nflags;
+            if (P.next_leader) P.next_leader[be] = leader;
+        }
+        __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_obs: observation + mask for the leader of every env (envs without a leader are skipped)
+// k_obs: observation + mask for the leader of every env (envs without a leader are skipped).  One warp per
+// (tile of 32 envs, chunk of rows): lane <-> env produces the chunk's rows into a shared-memory tile with an odd pitch
+// (conflict-free), then the warp streams the 32 x n floats out with unit-stride stores.  blockIdx.y = chunk:
+// [0, NA) agent chunks of 6 rows, [NA, NA + NR) task chunks of 8 rows (+ their mask bytes).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void flush_floats(const float* tile, float* g, size_t row_len, int col0, int n, unsigned tile_id, unsigned lane,
                                              unsigned valid, int B) {
@@ -231,42 +377,54 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
     const bool ok = leader >= 0 && leader < A;
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
-    double now = 0, Lx = 0, Ly = 0;
-    St<TW> st;
-    if (ok) { now = EL(c, now, 1, 0); Lx = EL(c, a_x, A, leader); Ly = EL(c, a_y, A, leader); ld_state(c, st); }
-    // ---- agent rows, 6 agents per chunk
-    for (int c0 = 0; c0 < A; c0 += OBS_AGENTS_PER_CHUNK) {
+    double Lx = 0, Ly = 0;
+    if (ok) { Lx = EL(c, a_x, A, leader); Ly = EL(c, a_y, A, leader); }
+    const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK;
+    const int chunk = blockIdx.y;
+    if (chunk < NA) {                                                         // ---- agent rows
+        if (!O.agent_obs) return;
+        const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
         const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
-        if (ok) for (int i = 0; i < na; ++i) obs_agent_row(c, st, now, Lx, Ly, c0 + i, mine + 6 * i);
-        __syncwarp();
-        if (O.agent_obs) flush_floats(tile, O.agent_obs, (size_t)6 * A, 6 * c0, 6 * na, tile_id, lane, valid, B);
-        __syncwarp();
-    }
-    // ---- task rows (row 0 = depot) + mask bytes, 8 rows per chunk
-    bool all_masked = true;
-    for (int r0 = 0; r0 <= T; r0 += OBS_ROWS_PER_CHUNK) {
-        const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
-        unsigned char* mbytes = (unsigned char*)(mine + 40);
-        if (ok) for (int i = 0; i < nr; ++i) {
-            obs_task_row(c, Lx, Ly, r0 + i, mine + 5 * i);
-            const bool open = r0 + i > 0 && tbit<TW>(st.open, r0 + i - 1);      // task_env.py:199
-            mbytes[i] = open ? 0 : 1;
-            all_masked = all_masked && !open;
+        if (ok) {
+            St<TW> st;
+#pragma unroll
+            for (int w = 0; w < TW; ++w) st.feas[w] = EL(c, m_feas, TW, w);
+            st.route = EL(c, am_route, 1, 0); st.depot = EL(c, am_depot, 1, 0); st.assigned = EL(c, am_assigned, 1, 0);
+            const double now = EL(c, now, 1, 0);
+#pragma unroll
+            for (int i = 0; i < OBS_AGENTS_PER_CHUNK; ++i) if (i < na) obs_agent_row(c, st, now, Lx, Ly, c0 + i, mine + 6 * i);
         }
         __syncwarp();
-        if (O.task_obs) flush_floats(tile, O.task_obs, (size_t)5 * (T + 1), 5 * r0, 5 * nr, tile_id, lane, valid, B);
-        if (O.mask) {
-            const unsigned inv = (1048576u + nr - 1) / nr;
-            for (unsigned q = lane; q < 32u * nr; q += 32) {
-                const unsigned e = (q * inv) >> 20, k = q - e * nr;
-                const unsigned be = tile_id * 32 + e;
-                if (be < (unsigned)B && ((valid >> e) & 1u) && (r0 + k) > 0)
-                    O.mask[(size_t)be * (T + 1) + r0 + k] = ((const unsigned char*)(tile + e * OBS_PITCH + 40))[k];
-            }
-        }
-        __syncwarp();
+        flush_floats(tile, O.agent_obs, (size_t)6 * A, 6 * c0, 6 * na, tile_id, lane, valid, B);
+        return;
     }
-    if (ok && O.mask) O.mask[(size_t)b * (T + 1)] = all_masked ? 0 : 1;          // worker.py:58-61 depot bit
+    // ---- task rows (row 0 = depot) + mask bytes
+    const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
+    const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
+    unsigned char* mbytes = (unsigned char*)(mine + 40);
+    if (ok) {
+        u64 open[TW]; bool any_open = false;
+#pragma unroll
+        for (int w = 0; w < TW; ++w) { open[w] = EL(c, m_open, TW, w); any_open = any_open || open[w] != 0; }
+#pragma unroll
+        for (int i = 0; i < OBS_ROWS_PER_CHUNK; ++i) if (i < nr) {
+            if (O.task_obs) obs_task_row(c, Lx, Ly, r0 + i, mine + 5 * i);
+            const bool is_open = r0 + i > 0 && tbit<TW>(open, r0 + i - 1);    // task_env.py:199
+            mbytes[i] = is_open ? 0 : 1;
+        }
+        if (r0 == 0) mbytes[0] = any_open ? 1 : 0;                            // worker.py:58-61 depot bit: allowed only when nothing is open
+    }
+    __syncwarp();
+    if (O.task_obs) flush_floats(tile, O.task_obs, (size_t)5 * (T + 1), 5 * r0, 5 * nr, tile_id, lane, valid, B);
+    if (O.mask) {
+        const unsigned inv = (1048576u + nr - 1) / nr;
+        for (unsigned q = lane; q < 32u * nr; q += 32) {
+            const unsigned e = (q * inv) >> 20, k = q - e * nr;
+            const unsigned be = tile_id * 32 + e;
+            if (be < (unsigned)B && ((valid >> e) & 1u))
+                O.mask[(size_t)be * (T + 1) + r0 + k] = ((const unsigned char*)(tile + e * OBS_PITCH + 40))[k];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -371,7 +529,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__
         ++guard;
     }
     if (finished) flags |= ENV_FINISHED;
-    flags |= ENV_DONE;
+    flags |= ENV_DONE | ENV_ACCOUNTED;          // metrics are fetched explicitly with dcm_compute_metrics (baselines/CTAS-D.py:80-94)
     EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, n_steps, 1, 0) = n_steps; EL(c, leader, 1, 0) = -1;
     EL(c, pending, 1, 0) = 0; EL(c, group, 1, 0) = 0;
     st_state(c, st0, st);
@@ -419,7 +577,7 @@ __global__ void k_init(const __grid_constant__ EnvArgs E) {                   //
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= E.S.NT * 32) return;
     const TC c = make_tc(E, b);
-    EL(c, flags, 1, 0) = ENV_DONE; EL(c, leader, 1, 0) = -1;
+    EL(c, flags, 1, 0) = ENV_DONE | ENV_ACCOUNTED; EL(c, leader, 1, 0) = -1;
 }
 
 // tiled SoA <-> per-env record of dcm_layout.h (export / import / checkpoint format)
@@ -680,19 +838,18 @@ int dcm_get_instances(dcm_env* v, double* task_xy, double* depot_xy, int32_t* re
 
 static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
     const int tiles_per_block = OBS_THREADS / 32;
-    LAUNCH_TW(v, k_obs, (v->E.S.NT + tiles_per_block - 1) / tiles_per_block, OBS_THREADS, s, v->E, O);
+    const int NA = (v->E.S.A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (v->E.S.T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
+    const dim3 grid((v->E.S.NT + tiles_per_block - 1) / tiles_per_block, NA + NR);
+    LAUNCH_TW(v, k_obs, grid, OBS_THREADS, s, v->E, O);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
 }
 
-static int launch_step(dcm_env* v, const StepArgs& F, const ObsArgs& O, void* stream) {
-    DeviceGuard g(v->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
+static int launch_episode(dcm_env* v, const EpiArgs& P, cudaStream_t s) {
+    LAUNCH_TW(v, k_episode, (v->E.S.NT + EPI_WARPS - 1) / EPI_WARPS, 32 * EPI_WARPS, s, v->E, P);
     CK(cudaGetLastError());
     v->launches++;
-    if (O.agent_obs || O.task_obs || O.mask) return launch_obs(v, O, s);
     return DCM_OK;
 }
 
@@ -700,10 +857,14 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
               int32_t* next_leader, void* stream) {
     if (!v) return fail(DCM_ERR_ARG, "dcm_reset: env is NULL");
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_reset: load or generate instances first");
-    StepArgs F; memset(&F, 0, sizeof F);
-    F.mode = 1; F.which = which; F.leader_in = leader_in; F.next_leader = next_leader; F.metrics = v->metrics;
+    DeviceGuard g(v->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    EpiArgs P{1, which, leader_in, next_leader, v->metrics};
+    int rc = launch_episode(v, P, s);
+    if (rc) return rc;
     ObsArgs O{nullptr, agent_obs, task_obs, mask};
-    return launch_step(v, F, O, stream);
+    if (agent_obs || task_obs || mask) return launch_obs(v, O, s);
+    return DCM_OK;
 }
 
 int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fstride, const int32_t* next_leader_in, int policy,
@@ -713,11 +874,22 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     if (policy < 0 || policy > 2) return fail(DCM_ERR_ARG, "dcm_step: unknown policy");
     if (policy == DCM_POLICY_EXTERNAL && !action) return fail(DCM_ERR_ARG, "dcm_step: action is NULL with the external policy");
     if (followers && fstride < 0) return fail(DCM_ERR_ARG, "dcm_step: negative follower stride");
+    DeviceGuard g(v->device);
+    cudaStream_t s = (cudaStream_t)stream;
     StepArgs F; memset(&F, 0, sizeof F);
-    F.mode = 0; F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
-    F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action; F.metrics = v->metrics;
+    F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
+    F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action;
+    LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
+    CK(cudaGetLastError());
+    v->launches++;
+    // episode accounting (+ restart with DCM_FLAG_AUTO_RESET) of the envs that just finished; the injected leader of a
+    // restarted env is the same next_leader_in entry
+    EpiArgs P{0, nullptr, next_leader_in, next_leader, v->metrics};
+    int rc = launch_episode(v, P, s);
+    if (rc) return rc;
     ObsArgs O{nullptr, agent_obs, task_obs, mask};
-    return launch_step(v, F, O, stream);
+    if (agent_obs || task_obs || mask) return launch_obs(v, O, s);
+    return DCM_OK;
 }
 
 static int ensure_host_staging(dcm_env* v) {

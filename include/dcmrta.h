@@ -61,6 +61,7 @@ enum dcm_status {
 #define DCM_ENV_ERR_ACTION   32u  /* action outside [0, T] */
 #define DCM_ENV_ERR_FOLLOW   64u  /* injected followers are not what step() could have drawn (task_env.py:331) */
 #define DCM_ENV_ERR_LEADER  128u  /* injected leader is not in the current group (worker.py:54) */
+#define DCM_ENV_ACCOUNTED   256u  /* the finished episode's metrics have been computed (dcm_episode_metrics has them) */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */
 
