@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ E
         action_out = action;
         // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
         double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
-        double d, tt; travel(c, EL(c, a_x, c.A, leader), EL(c, a_y, c.A, leader), tx, ty, d, tt);
+        double d, tt; travel(c, AREC(c, leader, AR_X), AREC(c, leader, AR_Y), tx, ty, d, tt);
         double reward = 0.0; int nm = 1;
         t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt;
         pending &= ~(1ull << leader);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ E
         }
         reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
         t_task_update(c, st, now, nullptr);                                   // worker.py:74
-        t_agent_update(c, st, now, agents_to_update(st));                     // worker.py:76
+        t_agent_update(c, st, now, st.touched);                               // worker.py:76
         ++n_steps; EL(c, total, 1, 0) = EL(c, total, 1, 0) + 1;
         if (!pending) t_advance(c, st, now, pending, flags);                  // worker.py:85, :45-51
         if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
@@ -206,55 +206,58 @@ struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int
 __device__ __forceinline__ double wmax(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; } return v; }
 __device__ __forceinline__ double wmin(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; } return v; }
 
+struct EpiScratch {
+    double sa[32][DCM_MAX_M];        // arrivals of the slots of the 32 tasks of a batch
+    double smx[32];                  // latest arrival per task
+    double s_task[DCM_MAX_TASKS + 2], s_ts[DCM_MAX_TASKS + 2], s_agent[DCM_MAX_AGENTS], s_dist[DCM_MAX_AGENTS];
+    unsigned char sm[32][DCM_MAX_M]; // member ids
+    unsigned char sn[32];            // member count | feasible << 7
+};
+
 // out[8]: reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions.  Returns the final clock.
+// Warp-cooperative: tasks are staged 32 at a time (lane <-> task, all slot loads in flight at once), then the agent sums are
+// accumulated in the reference order (tasks ascending, members in list order, :358-362) from shared memory.
 template <int TW>
-__device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, double* scr) {
-    const int T = c.T, A = c.A, R = c.MC * c.T;
-    double* s_task = scr; double* s_ts = scr + T; double* s_agent = scr + 2 * T; double* s_dist = scr + 2 * T + A;
-    for (int j = lane; j < T; j += 32) {                                      // task['sum_waiting_time'] :349-357
-        const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
-        double v = w_ab;
-        const bool feas = tbit<TW>(st.feas, j);
-        if (tbit<TW>(st.ne, j)) {
-            const int n = EL(c, t_nmem, T, j);
-            double mx = EL(c, t_arr, R, j);
-            for (int s = 1; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); mx = a > mx ? a : mx; }
-            double acc = 0.0;                                                 // np.sum of < 8 terms is sequential
-            for (int s = 0; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); acc += feas ? (mx - a) : (now - a); }
-            v = acc + w_ab;
-        }
-        s_task[j] = v;
-        s_ts[j] = feas ? EL(c, t_start, T, j) : 0.0;
-    }
-    // agent sums in the reference order (tasks ascending, members in list order :358-362): the owner lanes of a task's
-    // slots broadcast (member, term) and the lane that maps to the member accumulates
+__device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, EpiScratch& S) {
+    const int T = c.T, A = c.A;
     double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-    for (int w = 0; w < TW; ++w) for (u64 mm = st.ne[w]; mm; mm &= mm - 1) {
-        const int j = 64 * w + ctz64(mm);
-        const int n = EL(c, t_nmem, T, j);
-        const bool feas = (st.feas[w] >> (j & 63)) & 1ull;
-        double a = -CUDART_INF; unsigned m = 0;
-        if ((int)lane < n) { a = EL(c, t_arr, R, lane * T + j); m = EL(c, t_mem, R, lane * T + j); }
-        const double mx = wmax(a);
-        double add;
-        if (feas) add = mx - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }
-        for (int s = 0; s < n; ++s) {
-            const unsigned ms = __shfl_sync(0xffffffffu, m, s); const double as = __shfl_sync(0xffffffffu, add, s);
-            if (lane == (ms & 31u)) { if (ms < 32u) acc0 += as; else acc1 += as; }
+    for (int j0 = 0; j0 < T; j0 += 32) {
+        const int j = j0 + (int)lane;
+        int n = 0; bool feas = false; double mx = 0.0;
+        if (j < T) { feas = tbit<TW>(st.feas, j); if (tbit<TW>(st.ne, j)) n = EL(c, t_nmem, T, j); }
+        for (int s = 0; s < n; ++s) { const double a = SARR(c, j, s); S.sa[lane][s] = a; S.sm[lane][s] = SMEM(c, j, s); mx = (s == 0 || a > mx) ? a : mx; }
+        S.sn[lane] = (unsigned char)(n | (feas ? 0x80 : 0)); S.smx[lane] = mx;
+        if (j < T) {                                                          // task['sum_waiting_time'] :349-357
+            const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
+            double v = w_ab;
+            if (n) { double acc = 0.0; for (int s = 0; s < n; ++s) { const double a = S.sa[lane][s]; acc += feas ? (mx - a) : (now - a); } v = acc + w_ab; }
+            S.s_task[j] = v;
+            S.s_ts[j] = feas ? TINFO(c, j, 0) : 0.0;
         }
+        __syncwarp();
+        const int nt = T - j0 < 32 ? T - j0 : 32;
+        for (int t = 0; t < nt; ++t) {
+            const int cnt = S.sn[t] & 0x7f; const bool ft = S.sn[t] & 0x80; const double mxt = S.smx[t];
+            for (int s = 0; s < cnt; ++s) {
+                const unsigned m = S.sm[t][s]; const double a = S.sa[t][s];
+                double add;
+                if (ft) add = mxt - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }     // :360 / :362
+                if (lane == (m & 31u)) { if (m < 32u) acc0 += add; else acc1 += add; }
+            }
+        }
+        __syncwarp();
     }
     for (int r = 0; r < 2; ++r) {                                             // + W per abandoned_agent entry (:363-364; added last, ~1e-16 rel.)
         const int i = lane + 32 * r;
         if (i < A) {
             double acc = r ? acc1 : acc0;
             for (int k = 0; k < (int)EL(c, a_nab, A, i); ++k) acc += c.W;
-            s_agent[i] = acc; s_dist[i] = EL(c, a_dist, A, i);
+            S.s_agent[i] = acc; S.s_dist[i] = AREC(c, i, AR_DIST);
         }
     }
     // :422 check_finished side effect on the clock
     double mn = CUDART_INF, la = 0.0;
-    for (int i = lane; i < A; i += 32) { const double nd = EL(c, a_nd, A, i); if (nd < mn) mn = nd; const double l2 = EL(c, a_last, A, i); la = l2 > la ? l2 : la; }
+    for (int i = lane; i < A; i += 32) { const double nd = EL(c, a_nd, A, i); if (nd < mn) mn = nd; const double l2 = AREC(c, i, AR_LAST); la = l2 > la ? l2 : la; }
     mn = wmin(mn); la = wmax(la);
     if (mn == CUDART_INF) now = la;
     int nfin = 0;
@@ -265,22 +268,22 @@ __device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& s
         out[0] = -now;                                                        // :424
         out[1] = (double)nfin / (double)T;                                    // worker.py:103
         out[2] = now;                                                         // :104
-        out[3] = np_sum([&](int j) { return s_ts[j]; }, T) / (double)T;       // :105 nanmean(time_start)
-        out[4] = np_sum([&](int i) { return s_agent[i]; }, A) / (double)A;    // :106
-        out[5] = np_sum([&](int i) { return s_dist[i]; }, A);                 // :107
-        out[6] = np_sum([&](int j) { return s_task[j]; }, T) / (double)T;     // :108
+        out[3] = np_sum([&](int j) { return S.s_ts[j]; }, T) / (double)T;     // :105 nanmean(time_start)
+        out[4] = np_sum([&](int i) { return S.s_agent[i]; }, A) / (double)A;  // :106
+        out[5] = np_sum([&](int i) { return S.s_dist[i]; }, A);               // :107
+        out[6] = np_sum([&](int j) { return S.s_task[j]; }, T) / (double)T;   // :108
         out[7] = (double)n_steps;
     }
     __syncwarp();
     return now;
 }
 
+// one block per tile; the block's warps share the tile's envs that need work (warp w takes the w-th, (w+4)-th, ... of them)
 template <int TW>
 __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
-    __shared__ double scratch[EPI_WARPS][2 * DCM_MAX_TASKS + 2 * DCM_MAX_AGENTS];
+    __shared__ EpiScratch scratch[EPI_WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned tile = blockIdx.x * EPI_WARPS + warp;
-    if (tile >= (unsigned)E.S.NT) return;
+    const unsigned tile = blockIdx.x;
     const int B = E.S.B, A = E.S.A, T = E.S.T;
     const int b = (int)(tile * 32 + lane);
     bool need = false;
@@ -288,7 +291,9 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
         if (P.mode == 1) need = !P.which || P.which[b];
         else { const unsigned f = E.S.flags[b]; need = (f & ENV_DONE) && !(f & ENV_ACCOUNTED); }   // K == 1: tiled index == linear index
     }
-    for (unsigned todo = __ballot_sync(0xffffffffu, need); todo; todo &= todo - 1) {
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    for (unsigned k = 0; todo; todo &= todo - 1, ++k) {
+        if ((k % EPI_WARPS) != warp) continue;
         const int be = (int)(tile * 32 + (__ffs(todo) - 1));
         const TC c = make_tc(E, be);
         St<TW> st; ld_state(c, st);
@@ -310,13 +315,11 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
             }
         }
         // ---- clear_decisions (task_env.py:129-140), lanes over tasks / agents
-        for (int j = lane; j < T; j += 32) {
-            EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)EL(c, s_req, T, j); EL(c, t_start, T, j) = 0.0; EL(c, t_nab, T, j) = 0;
-        }
+        for (int j = lane; j < T; j += 32) { EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)EL(c, s_req, T, j); EL(c, t_nab, T, j) = 0; }
         const double dx = EL(c, s_dep, 2, 0), dy = EL(c, s_dep, 2, 1);
         for (int i = lane; i < A; i += 32) {
-            EL(c, a_last, A, i) = 0.0; EL(c, a_nd, A, i) = 0.0; EL(c, a_dist, A, i) = 0.0;
-            EL(c, a_node, A, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0; EL(c, a_x, A, i) = dx; EL(c, a_y, A, i) = dy;
+            AREC(c, i, AR_LAST) = 0.0; AREC(c, i, AR_X) = dx; AREC(c, i, AR_Y) = dy; AREC(c, i, AR_DIST) = 0.0;
+            EL(c, a_nd, A, i) = 0.0; EL(c, a_node, A, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
         }
         // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
         const u64 all = A >= 64 ? ~0ull : ((1ull << A) - 1);
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
         if (lane == 0) {
 #pragma unroll
             for (int w = 0; w < TW; ++w) {
-                EL(c, m_feas, TW, w) = 0; EL(c, m_fin, TW, w) = 0; EL(c, m_ne, TW, w) = 0; EL(c, m_stale, TW, w) = 0;
+                EL(c, m_feas, TW, w) = 0; EL(c, m_fin, TW, w) = 0; EL(c, m_ne, TW, w) = 0; EL(c, m_dirty, TW, w) = 0;
                 EL(c, m_open, TW, w) = all_tasks<TW>(T, w);
             }
             EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
     double Lx = 0, Ly = 0;
-    if (ok) { Lx = EL(c, a_x, A, leader); Ly = EL(c, a_y, A, leader); }
+    if (ok) { Lx = AREC(c, leader, AR_X); Ly = AREC(c, leader, AR_Y); }
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK;
     const int chunk = blockIdx.y;
     if (chunk < NA) {                                                         // ---- agent rows
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant
             for (int k = 0; k < n; ++k) {
                 const int i = G.members[(size_t)b * G.mstride + k];
                 if (i < 0 || i >= c.A) { flags |= ENV_ERR_ACTION; continue; }
-                double d, tt; travel(c, EL(c, a_x, c.A, i), EL(c, a_y, c.A, i), tx, ty, d, tt);
+                double d, tt; travel(c, AREC(c, i, AR_X), AREC(c, i, AR_Y), tx, ty, d, tt);
                 t_agent_step(c, st, now, i, action, tx, ty, d, tt, flags);
                 reward += -tt;                                                // task_env.py:337-339
             }
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__
             if (p < len) { act = routes[((size_t)b * c.A + a) * rstride + p]; pos[a] = (unsigned char)(p + 1); }
             if (act < 0 || act > c.T) { flags |= ENV_ERR_ACTION; act = 0; }
             double tx, ty; node_xy(c, act == 0 ? DCM_NODE_DEPOT : (unsigned)(act - 1), tx, ty);
-            double dd, tt; travel(c, EL(c, a_x, c.A, a), EL(c, a_y, c.A, a), tx, ty, dd, tt);
+            double dd, tt; travel(c, AREC(c, a, AR_X), AREC(c, a, AR_Y), tx, ty, dd, tt);
             t_agent_step(c, st, now, a, act, tx, ty, dd, tt, flags);          // :585 agent_step
             t_task_update(c, st, now, nullptr); t_agent_update(c, st, now, st.route);   // :586-587
             ++n_steps;
@@ -588,18 +591,16 @@ __global__ void k_export(const __grid_constant__ EnvArgs E, const DcmLayout L, u
     const TC c = make_tc(E, b);
     St<TW> st; ld_state(c, st);
     unsigned char* r = dst + (size_t)b * L.dyn_bytes;
-    const int T = c.T, A = c.A, Tp = L.Tp, R = c.MC * T;
-    for (int s = 0; s < c.MC; ++s) for (int j = 0; j < T; ++j) {
-        ((double*)(r + L.o_arr))[s * Tp + j] = EL(c, t_arr, R, s * T + j); (r + L.o_mem)[s * Tp + j] = EL(c, t_mem, R, s * T + j);
-    }
+    const int T = c.T, A = c.A, Tp = L.Tp;
     for (int j = 0; j < T; ++j) {
-        const bool fe = tbit<TW>(st.feas, j);
-        ((double*)(r + L.o_tstart))[j] = fe ? EL(c, t_start, T, j) : 0.0; ((unsigned short*)(r + L.o_tnab))[j] = EL(c, t_nab, T, j);
-        (r + L.o_nmem)[j] = tbit<TW>(st.ne, j) ? EL(c, t_nmem, T, j) : 0; ((signed char*)(r + L.o_status))[j] = EL(c, t_status, T, j);
-        (r + L.o_tflags)[j] = (unsigned char)((fe ? DCM_TF_FEAS : 0u) | (tbit<TW>(st.fin, j) ? DCM_TF_FIN : 0u) | (tbit<TW>(st.stale, j) ? DCM_TF_STALE : 0u));
+        const bool fe = tbit<TW>(st.feas, j); const int n = tbit<TW>(st.ne, j) ? (int)EL(c, t_nmem, T, j) : 0;
+        for (int s = 0; s < n; ++s) { ((double*)(r + L.o_arr))[s * Tp + j] = SARR(c, j, s); (r + L.o_mem)[s * Tp + j] = SMEM(c, j, s); }
+        ((double*)(r + L.o_tstart))[j] = fe ? TINFO(c, j, 0) : 0.0; ((unsigned short*)(r + L.o_tnab))[j] = EL(c, t_nab, T, j);
+        (r + L.o_nmem)[j] = (unsigned char)n; ((signed char*)(r + L.o_status))[j] = EL(c, t_status, T, j);
+        (r + L.o_tflags)[j] = (unsigned char)((fe ? DCM_TF_FEAS : 0u) | (tbit<TW>(st.fin, j) ? DCM_TF_FIN : 0u) | (tbit<TW>(st.dirty, j) ? DCM_TF_STALE : 0u));
     }
     for (int i = 0; i < A; ++i) {
-        ((double*)(r + L.o_alast))[i] = EL(c, a_last, A, i); ((double*)(r + L.o_and))[i] = EL(c, a_nd, A, i); ((double*)(r + L.o_adist))[i] = EL(c, a_dist, A, i);
+        ((double*)(r + L.o_alast))[i] = AREC(c, i, AR_LAST); ((double*)(r + L.o_and))[i] = EL(c, a_nd, A, i); ((double*)(r + L.o_adist))[i] = AREC(c, i, AR_DIST);
         ((unsigned short*)(r + L.o_anab))[i] = EL(c, a_nab, A, i); (r + L.o_anode)[i] = EL(c, a_node, A, i);
         const u64 bit = 1ull << i;
         (r + L.o_aflags)[i] = (unsigned char)(((st.route & bit) ? DCM_AF_ROUTE : 0u) | ((st.assigned & bit) ? DCM_AF_ASSIGNED : 0u) | ((st.returned & bit) ? DCM_AF_RETURNED : 0u) |
@@ -619,31 +620,36 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
     const TC c = make_tc(E, b);
     St<TW> st, st0; ld_state(c, st0);
 #pragma unroll
-    for (int w = 0; w < TW; ++w) { st.feas[w] = st.fin[w] = st.ne[w] = st.open[w] = st.stale[w] = 0; }
+    for (int w = 0; w < TW; ++w) { st.feas[w] = st.fin[w] = st.ne[w] = st.open[w] = st.dirty[w] = 0; }
     st.route = st.assigned = st.returned = st.member = st.depot = st.touched = st.watch = 0;
     const unsigned char* r = src + (size_t)b * L.dyn_bytes;
-    const int T = c.T, A = c.A, Tp = L.Tp, R = c.MC * T;
-    for (int s = 0; s < c.MC; ++s) for (int j = 0; j < T; ++j) {
-        EL(c, t_arr, R, s * T + j) = ((const double*)(r + L.o_arr))[s * Tp + j]; EL(c, t_mem, R, s * T + j) = (r + L.o_mem)[s * Tp + j];
-    }
+    const int T = c.T, A = c.A, Tp = L.Tp;
     for (int j = 0; j < T; ++j) {
-        EL(c, t_start, T, j) = ((const double*)(r + L.o_tstart))[j]; EL(c, t_nab, T, j) = ((const unsigned short*)(r + L.o_tnab))[j];
         const int n = (r + L.o_nmem)[j]; const int stt = ((const signed char*)(r + L.o_status))[j]; const unsigned tf = (r + L.o_tflags)[j];
+        double amin = CUDART_INF;
+        for (int s = 0; s < n && s < c.MC; ++s) {
+            const double a = ((const double*)(r + L.o_arr))[s * Tp + j];
+            SARR(c, j, s) = a; SMEM(c, j, s) = (r + L.o_mem)[s * Tp + j]; amin = a < amin ? a : amin;
+        }
+        const double ts = ((const double*)(r + L.o_tstart))[j];
+        if (tf & DCM_TF_FEAS) { TINFO(c, j, 0) = ts; TINFO(c, j, 1) = ts + EL(c, s_dur, T, j); } else TINFO(c, j, 0) = amin;
+        EL(c, t_nab, T, j) = ((const unsigned short*)(r + L.o_tnab))[j];
         EL(c, t_nmem, T, j) = (unsigned char)n; EL(c, t_status, T, j) = (signed char)stt;
-        tset<TW>(st.feas, j, tf & DCM_TF_FEAS); tset<TW>(st.fin, j, tf & DCM_TF_FIN); tset<TW>(st.stale, j, tf & DCM_TF_STALE);
+        tset<TW>(st.feas, j, tf & DCM_TF_FEAS); tset<TW>(st.fin, j, tf & DCM_TF_FIN); tset<TW>(st.dirty, j, tf & DCM_TF_STALE);
         tset<TW>(st.ne, j, n > 0); tset<TW>(st.open, j, !(tf & DCM_TF_FEAS) && stt > 0);
     }
     for (int i = 0; i < A; ++i) {
-        EL(c, a_last, A, i) = ((const double*)(r + L.o_alast))[i]; EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i]; EL(c, a_dist, A, i) = ((const double*)(r + L.o_adist))[i];
         const unsigned node = (r + L.o_anode)[i]; const unsigned af = (r + L.o_aflags)[i]; const u64 bit = 1ull << i;
+        double x, y; node_xy(c, node, x, y);
+        AREC(c, i, AR_LAST) = ((const double*)(r + L.o_alast))[i]; AREC(c, i, AR_X) = x; AREC(c, i, AR_Y) = y; AREC(c, i, AR_DIST) = ((const double*)(r + L.o_adist))[i];
+        EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i];
         EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; EL(c, a_node, A, i) = (unsigned char)node;
-        double x, y; node_xy(c, node, x, y); EL(c, a_x, A, i) = x; EL(c, a_y, A, i) = y;
         if (af & DCM_AF_ROUTE) st.route |= bit;
         if (af & DCM_AF_ASSIGNED) st.assigned |= bit;
         if (af & DCM_AF_RETURNED) st.returned |= bit;
         if (af & DCM_AF_MEMBER) st.member |= bit;
         if (af & DCM_AF_TOUCHED) st.touched |= bit;
-        if (af & DCM_AF_WATCH) st.watch |= bit;
+        if ((af & DCM_AF_WATCH) && node != DCM_NODE_DEPOT) { st.watch |= bit; EL(c, a_ts, A, i) = ((const double*)(r + L.o_tstart))[node]; }
         if ((af & DCM_AF_ROUTE) && node == DCM_NODE_DEPOT) st.depot |= bit;
     }
     st_state(c, st0, st);
@@ -700,7 +706,7 @@ static int grid_env(const dcm_env* v, int threads) { return (v->E.S.B + threads 
 extern "C" {
 
 const char* dcm_last_error(void) { return g_err.c_str(); }
-const char* dcm_version(void) { return "dcmrta_b200 0.3 (sm_100a, thread-per-env, tiled SoA + bitmask summaries)"; }
+const char* dcm_version(void) { return "dcmrta_b200 0.4 (sm_100a, thread-per-env, tiled state + bitmask summaries)"; }
 
 int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t flags) {
     if (!out) return fail(DCM_ERR_ARG, "dcm_create: out is NULL");
@@ -722,19 +728,19 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     v->E.W = 10.0; v->E.vel = 0.2; v->E.max_time = 100.0; v->E.seed = 0; v->E.first_gid = 0; v->E.cflags = flags;
     v->E.gen_max_duration = 5.0; v->E.gen_random_duration = 0;
     // carve one arena; every array is [NT][K][32], 256-byte aligned
-    const int NT = S.NT, R = M * T, TW = S.TW;
+    const int NT = S.NT, TW = S.TW;
     size_t off = 0;
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(NT, K, elem) + 255) / 256 * 256; return o; };
-    const size_t o_t_arr = carve(R, 8), o_t_start = carve(T, 8), o_a_last = carve(A, 8), o_a_nd = carve(A, 8), o_a_dist = carve(A, 8),
-                 o_now = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8), o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8),
-                 o_s_dep = carve(2, 8), o_w_agent = carve(A, 8), o_a_x = carve(A, 8), o_a_y = carve(A, 8),
-                 o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_stale = carve(TW, 8),
+    const int MCB = M <= 8 ? 8 : 16; S.MCB = MCB;
+    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32),
+                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
+                 o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
+                 o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
                  o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
                  o_am_touched = carve(1, 8), o_am_watch = carve(1, 8),
                  o_n_steps = carve(1, 4), o_episode = carve(1, 4), o_flags = carve(1, 4), o_instance = carve(1, 4), o_total = carve(1, 4), o_leader = carve(1, 4),
                  o_t_nab = carve(T, 2), o_a_nab = carve(A, 2),
-                 o_t_mem = carve(R, 1), o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(A, 1),
-                 o_s_req = carve(T, 1);
+                 o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(A, 1), o_s_req = carve(T, 1);
     v->arena_bytes = off;
     cudaError_t e = cudaMalloc((void**)&v->arena, off);
     if (e == cudaSuccess) e = cudaMemset(v->arena, 0, off);
@@ -743,18 +749,16 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_counter, sizeof(unsigned long long));
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
-    S.t_arr = (double*)(a + o_t_arr); S.t_start = (double*)(a + o_t_start); S.a_last = (double*)(a + o_a_last); S.a_nd = (double*)(a + o_a_nd);
-    S.a_dist = (double*)(a + o_a_dist); S.now = (double*)(a + o_now); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
-    S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dep = (double*)(a + o_s_dep);
-    S.w_agent = (double*)(a + o_w_agent); S.a_x = (double*)(a + o_a_x); S.a_y = (double*)(a + o_a_y);
-    S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_stale = (u64*)(a + o_m_stale);
+    S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec);
+    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
+    S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
+    S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_dirty = (u64*)(a + o_m_dirty);
     S.am_route = (u64*)(a + o_am_route); S.am_assigned = (u64*)(a + o_am_assigned); S.am_returned = (u64*)(a + o_am_returned); S.am_member = (u64*)(a + o_am_member);
     S.am_depot = (u64*)(a + o_am_depot); S.am_touched = (u64*)(a + o_am_touched); S.am_watch = (u64*)(a + o_am_watch);
     S.n_steps = (unsigned*)(a + o_n_steps); S.episode = (unsigned*)(a + o_episode); S.flags = (unsigned*)(a + o_flags);
     S.instance = (unsigned*)(a + o_instance); S.total = (unsigned*)(a + o_total); S.leader = (int*)(a + o_leader);
     S.t_nab = (unsigned short*)(a + o_t_nab); S.a_nab = (unsigned short*)(a + o_a_nab);
-    S.t_mem = a + o_t_mem; S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status);
-    S.a_node = a + o_a_node; S.s_req = a + o_s_req;
+    S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status); S.a_node = a + o_a_node; S.s_req = a + o_s_req;
     k_init<<<(S.NT * 32 + 127) / 128, 128>>>(v->E);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dcm_destroy(v); return fail_cuda(e, "dcm_create init"); }
@@ -847,7 +851,7 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 }
 
 static int launch_episode(dcm_env* v, const EpiArgs& P, cudaStream_t s) {
-    LAUNCH_TW(v, k_episode, (v->E.S.NT + EPI_WARPS - 1) / EPI_WARPS, 32 * EPI_WARPS, s, v->E, P);
+    LAUNCH_TW(v, k_episode, v->E.S.NT, 32 * EPI_WARPS, s, v->E, P);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;

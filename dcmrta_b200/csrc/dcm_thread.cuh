@@ -1,9 +1,8 @@
-// dcm_thread.cuh -- thread-per-env device functions of the TaskEnv step for sm_100a (v3: bitmask summaries).
+// dcm_thread.cuh -- thread-per-env device functions of the TaskEnv step for sm_100a (v4).
 //
-// One thread simulates one env; the 32 envs of a tile are simulated by the 32 lanes of one warp, so every access to
-// the tiled struct-of-arrays state (dcm_soa.h) is a unit-stride warp access.  The boolean state of an env (which
-// tasks are feasible / finished / non-empty / open, which agents have a route / are assigned / returned / members /
-// at the depot) lives in 64-bit masks held in registers (struct St); loops run over set bits only.
+// One thread simulates one env; the 32 envs of a tile are simulated by the 32 lanes of one warp.  The boolean state of
+// an env lives in 64-bit masks held in registers (struct St); loops run over set bits only; load-only passes are kept
+// free of stores so that the compiler can batch their loads (the kernel is latency-bound, not bandwidth-bound).
 //
 // All event-clock arithmetic is fp64 in the exact operation order of the reference; the file
 // is compiled with -fmad=false and the one fused multiply-add the reference performs (inside np.linalg.norm) is
@@ -30,12 +29,19 @@ struct TC {
     double W, vel, max_time;
 };
 
-// element (row k) of this thread's env in an array with K rows per tile
+// row-major arrays: element (row k) of this thread's env in an array with K rows per tile
 #define EL(c, arr, K, k) ((c).s.arr[(((c).tile * (unsigned)(K) + (unsigned)(k)) << 5) + (c).l])
+// lane-contiguous arrays
+#define LANE_ROW(c, K, k) ((size_t)((((c).tile * (unsigned)(K) + (unsigned)(k)) << 5) + (c).l))
+#define SARR(c, j, sl) ((c).s.t_slot_arr[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
+#define SMEM(c, j, sl) ((c).s.t_slot_mem[LANE_ROW(c, (c).T, j) * (unsigned)(c).s.MCB + (unsigned)(sl)])   // member id of slot s
+#define TINFO(c, j, k) ((c).s.t_info[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
+#define AREC(c, i, f) ((c).s.a_rec[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // 0 last arrival, 1 x, 2 y, 3 travel_dist
+enum { AR_LAST = 0, AR_X = 1, AR_Y = 2, AR_DIST = 3 };
 
 // register-resident boolean state of one env
 template <int TW> struct St {
-    u64 feas[TW], fin[TW], ne[TW], open[TW], stale[TW];
+    u64 feas[TW], fin[TW], ne[TW], open[TW], dirty[TW];
     u64 route, assigned, returned, member, depot, touched, watch;
 };
 
@@ -49,10 +55,7 @@ template <int TW> __device__ __forceinline__ u64 all_tasks(int T, int w) {
     const int r = T - 64 * w;
     return r >= 64 ? ~0ull : (r <= 0 ? 0ull : ((1ull << r) - 1));
 }
-#define TBIT(arr, j) (((arr)[(j) >> 6] >> ((j) & 63)) & 1ull)
-#define TSET(arr, j) ((arr)[(j) >> 6] |= 1ull << ((j) & 63))
-#define TCLR(arr, j) ((arr)[(j) >> 6] &= ~(1ull << ((j) & 63)))
-// with TW == 1 the word index is a compile-time 0; for TW > 1 the arrays are indexed dynamically only on rare paths
+// with TW == 1 the word index is a compile-time 0; for TW > 1 the word is selected without dynamic register indexing
 template <int TW> __device__ __forceinline__ bool tbit(const u64 (&a)[TW], int j) {
     if (TW == 1) return (a[0] >> j) & 1ull;
     u64 w = a[0];
@@ -70,7 +73,7 @@ template <int TW> __device__ __forceinline__ void ld_state(const TC& c, St<TW>& 
 #pragma unroll
     for (int w = 0; w < TW; ++w) {
         st.feas[w] = EL(c, m_feas, TW, w); st.fin[w] = EL(c, m_fin, TW, w); st.ne[w] = EL(c, m_ne, TW, w);
-        st.open[w] = EL(c, m_open, TW, w); st.stale[w] = EL(c, m_stale, TW, w);
+        st.open[w] = EL(c, m_open, TW, w); st.dirty[w] = EL(c, m_dirty, TW, w);
     }
     st.route = EL(c, am_route, 1, 0); st.assigned = EL(c, am_assigned, 1, 0); st.returned = EL(c, am_returned, 1, 0);
     st.member = EL(c, am_member, 1, 0); st.depot = EL(c, am_depot, 1, 0); st.touched = EL(c, am_touched, 1, 0);
@@ -83,7 +86,7 @@ template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St
         if (o.fin[w] != st.fin[w]) EL(c, m_fin, TW, w) = st.fin[w];
         if (o.ne[w] != st.ne[w]) EL(c, m_ne, TW, w) = st.ne[w];
         if (o.open[w] != st.open[w]) EL(c, m_open, TW, w) = st.open[w];
-        if (o.stale[w] != st.stale[w]) EL(c, m_stale, TW, w) = st.stale[w];
+        if (o.dirty[w] != st.dirty[w]) EL(c, m_dirty, TW, w) = st.dirty[w];
     }
     if (o.route != st.route) EL(c, am_route, 1, 0) = st.route;
     if (o.assigned != st.assigned) EL(c, am_assigned, 1, 0) = st.assigned;
@@ -121,130 +124,131 @@ __device__ __forceinline__ void node_xy(const TC& c, unsigned node, double& x, d
 __device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double by) { return ax < bx || (ax == bx && ay < by); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// clear_decisions (task_env.py:129-140)
-// ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __noinline__ void t_clear(const TC& c, St<TW>& st) {
-    for (int j = 0; j < c.T; ++j) {
-        EL(c, t_nmem, c.T, j) = 0; EL(c, t_status, c.T, j) = (signed char)EL(c, s_req, c.T, j);
-        EL(c, t_start, c.T, j) = 0.0; EL(c, t_nab, c.T, j) = 0;
-    }
-    const double dx = EL(c, s_dep, 2, 0), dy = EL(c, s_dep, 2, 1);
-    for (int i = 0; i < c.A; ++i) {
-        EL(c, a_last, c.A, i) = 0.0; EL(c, a_nd, c.A, i) = 0.0; EL(c, a_dist, c.A, i) = 0.0;
-        EL(c, a_node, c.A, i) = DCM_NODE_DEPOT; EL(c, a_nab, c.A, i) = 0; EL(c, a_x, c.A, i) = dx; EL(c, a_y, c.A, i) = dy;
-    }
-#pragma unroll
-    for (int w = 0; w < TW; ++w) { st.feas[w] = 0; st.fin[w] = 0; st.ne[w] = 0; st.stale[w] = 0; st.open[w] = all_tasks<TW>(c.T, w); }
-    st.route = st.assigned = st.returned = st.member = st.depot = st.touched = st.watch = 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // task_update (task_env.py:245-281).  newly: optional per-env [T] u8 (plain row-major global) of ids that became feasible.
-// Visits only (a) non-feasible tasks that have members, (b) non-feasible empty tasks whose stored status is stale,
-// (c) feasible tasks that have not finished; every other task is left exactly as the reference would leave it.
+//
+// The reference recomputes every non-feasible task on every call.  What can actually change for such a task is:
+//   - its member count changed since the last call (join or removal)      -> `dirty` bit: recompute status, :252-265;
+//   - a waiting member reaches fl(now - arrival) >= max_waiting_time      -> :266-271.  fl() is monotone, so the member
+//     with the EARLIEST arrival (amin, kept per task) passes the test first: if it does not, nobody does.
+// A non-dirty task with members therefore costs one load and one compare; everything else is evaluated exactly as written
+// in the reference, including Q2 (skip after removal) and Q3 (status not refreshed after removals).
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW> __device__ __forceinline__ void abandon(const TC& c, St<TW>& st, unsigned m, int j) {
     EL(c, a_nab, c.A, m) = (unsigned short)(EL(c, a_nab, c.A, m) + 1);
     if (EL(c, a_node, c.A, m) == (unsigned)j) st.member &= ~(1ull << m);      // it no longer belongs to the task it stands at
 }
 
-// stale-status refresh at the START of a task_update: tasks emptied by removals in an EARLIER call get status = requirements
-// (:252 with len(members) == 0); tasks made stale by the current call are refreshed by the next one, exactly like the reference
-template <int TW> __device__ __forceinline__ void t_refresh_stale(const TC& c, St<TW>& st) {
-#pragma unroll
-    for (int w = 0; w < TW; ++w) {
-        for (u64 mm = st.stale[w] & ~st.feas[w] & ~st.ne[w]; mm; mm &= mm - 1) {
-            const int j = 64 * w + ctz64(mm);
-            EL(c, t_status, c.T, j) = (signed char)EL(c, s_req, c.T, j);      // :252 with len(members) == 0
-            st.open[w] |= mm & (0 - mm);                                      // requirements >= 1
+template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly) {
+    const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
+    const int n = EL(c, t_nmem, T, j);                                        // :250
+    const int stt = (int)EL(c, s_req, T, j) - n;                              // :252 (not refreshed after removals: Q3)
+    if (stt != (int)EL(c, t_status, T, j)) EL(c, t_status, T, j) = (signed char)stt;
+    u64 open = stt > 0 ? bit : 0, feas = 0, ne = bit, dirty = 0;
+    if (stt <= 0) {                                                           // :254
+        double mx = SARR(c, j, 0), mn = mx;
+        for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; mn = a < mn ? a : mn; }
+        if (mx - mn <= c.W) {                                                 // :255
+            TINFO(c, j, 0) = mx; TINFO(c, j, 1) = mx + EL(c, s_dur, T, j);    // :256-257 time_start, time_finish
+            feas = bit; open = 0;                                             // :258
+            if (newly) newly[j] = 1;
+            for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
+                const unsigned m = SMEM(c, j, s);
+                if (EL(c, a_node, c.A, m) == (unsigned)j) st.touched |= 1ull << m;
+            }
+        } else {                                                              // :260-265 (iterates a copy: no skipping, Q4)
+            const double thr = mx - c.W;
+            int wv = 0, nab = 0; double amin = CUDART_INF;
+            for (int s = 0; s < n; ++s) {
+                const double a = SARR(c, j, s); const unsigned m = SMEM(c, j, s);
+                if (a <= thr) { ++nab; abandon(c, st, m, j); }
+                else { if (wv != s) { SARR(c, j, wv) = a; SMEM(c, j, wv) = (unsigned char)m; } ++wv; amin = a < amin ? a : amin; }
+            }
+            EL(c, t_nmem, T, j) = (unsigned char)wv; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
+            TINFO(c, j, 0) = amin;
+            if (wv == 0) ne = 0;
+            dirty = bit;
         }
-        st.stale[w] &= st.ne[w] & ~st.feas[w];                                // non-empty stale tasks are recomputed in (a)
+    } else {                                                                  // :266-271 (mutates while iterating: Q2)
+        int i = 0, nn = n, nab = 0;
+        while (i < nn) {
+            const double a = SARR(c, j, i);
+            if (now - a >= c.W) {                                             // :269 (Q1: false when fl(arr+W) rounded down)
+                abandon(c, st, SMEM(c, j, i), j);
+                for (int k = i; k < nn - 1; ++k) { SARR(c, j, k) = SARR(c, j, k + 1); SMEM(c, j, k) = SMEM(c, j, k + 1); }
+                --nn; ++nab;                                                  // the element that moved into slot i is skipped
+            }
+            ++i;
+        }
+        if (nab) {
+            EL(c, t_nmem, T, j) = (unsigned char)nn; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
+            double amin = CUDART_INF;
+            for (int s = 0; s < nn; ++s) { const double a = SARR(c, j, s); amin = a < amin ? a : amin; }
+            TINFO(c, j, 0) = amin;
+            if (nn == 0) ne = 0;
+            dirty = bit;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TW; ++k) if (TW == 1 || k == w) {
+        st.open[k] = (st.open[k] & ~bit) | open; st.feas[k] |= feas; st.ne[k] = (st.ne[k] & ~bit) | ne; st.dirty[k] = (st.dirty[k] & ~bit) | dirty;
     }
 }
 
 template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly) {
-    const int T = c.T, R = c.MC * c.T;
-    t_refresh_stale(c, st);
+    const int T = c.T;
+    // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished
+    u64 hot[TW], done[TW];
 #pragma unroll
     for (int w = 0; w < TW; ++w) {
-        // (a) non-feasible tasks with members                                               :249-271
-        for (u64 mm = ~st.feas[w] & st.ne[w]; mm; mm &= mm - 1) {
-            const int j = 64 * w + ctz64(mm); const u64 bit = mm & (0 - mm);
-            const int n = EL(c, t_nmem, T, j);                                // :250
-            const int stt = (int)EL(c, s_req, T, j) - n;                      // :252 (not refreshed after removals: Q3)
-            if (stt != (int)EL(c, t_status, T, j)) EL(c, t_status, T, j) = (signed char)stt;
-            st.open[w] = stt > 0 ? (st.open[w] | bit) : (st.open[w] & ~bit);
-            st.stale[w] &= ~bit;
-            if (stt <= 0) {                                                   // :254
-                double mx = EL(c, t_arr, R, j), mn = mx;
-                for (int s = 1; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); mx = a > mx ? a : mx; mn = a < mn ? a : mn; }
-                if (mx - mn <= c.W) {                                         // :255
-                    EL(c, t_start, T, j) = mx;                                // :256 (time_finish = fl(mx + time), :257)
-                    st.feas[w] |= bit; st.open[w] &= ~bit;                    // :258
-                    if (newly) newly[j] = 1;
-                    for (int s = 0; s < n; ++s) {                             // members standing here get next_decision = time_finish
-                        const unsigned m = EL(c, t_mem, R, s * T + j);
-                        if (EL(c, a_node, c.A, m) == (unsigned)j) st.touched |= 1ull << m;
-                    }
-                } else {                                                      // :260-265 (iterates a copy: no skipping, Q4)
-                    const double thr = mx - c.W;
-                    int wv = 0, nab = 0;
-                    for (int s = 0; s < n; ++s) {
-                        const double a = EL(c, t_arr, R, s * T + j); const unsigned m = EL(c, t_mem, R, s * T + j);
-                        if (a <= thr) { ++nab; abandon(c, st, m, j); }
-                        else { if (wv != s) { EL(c, t_arr, R, wv * T + j) = a; EL(c, t_mem, R, wv * T + j) = (unsigned char)m; } ++wv; }
-                    }
-                    EL(c, t_nmem, T, j) = (unsigned char)wv; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
-                    if (wv == 0) st.ne[w] &= ~bit;
-                    st.stale[w] |= bit;
-                }
-            } else {                                                          // :266-271 (mutates while iterating: Q2)
-                int i = 0, nn = n, nab = 0;
-                while (i < nn) {
-                    const double a = EL(c, t_arr, R, i * T + j);
-                    if (now - a >= c.W) {                                     // :269 (Q1: false when fl(arr+W) rounded down)
-                        abandon(c, st, EL(c, t_mem, R, i * T + j), j);
-                        for (int k = i; k < nn - 1; ++k) {
-                            EL(c, t_arr, R, k * T + j) = EL(c, t_arr, R, (k + 1) * T + j);
-                            EL(c, t_mem, R, k * T + j) = EL(c, t_mem, R, (k + 1) * T + j);
-                        }
-                        --nn; ++nab;                                          // the element that moved into slot i is skipped
-                    }
-                    ++i;
-                }
-                if (nab) {
-                    EL(c, t_nmem, T, j) = (unsigned char)nn; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
-                    if (nn == 0) st.ne[w] &= ~bit;
-                    st.stale[w] |= bit;
-                }
-            }
-        }
-    }
-    // (c) feasible, not finished                                                            :272-274
-#pragma unroll
-    for (int w = 0; w < TW; ++w) {
-        for (u64 mm = st.feas[w] & ~st.fin[w]; mm; mm &= mm - 1) {
+        hot[w] = st.dirty[w] & ~st.feas[w] & st.ne[w]; done[w] = 0;
+        for (u64 mm = ~st.feas[w] & st.ne[w] & ~st.dirty[w]; mm; mm &= mm - 1) {       // waiting coalitions: earliest arrival only
             const int j = 64 * w + ctz64(mm);
-            if (now >= EL(c, t_start, T, j) + EL(c, s_dur, T, j)) st.fin[w] |= mm & (0 - mm);
+            if (now - TINFO(c, j, 0) >= c.W) hot[w] |= mm & (0 - mm);
+        }
+        for (u64 mm = st.feas[w] & ~st.fin[w]; mm; mm &= mm - 1) {                     // :272-274
+            const int j = 64 * w + ctz64(mm);
+            if (now >= TINFO(c, j, 1)) done[w] |= mm & (0 - mm);
         }
     }
+    // ---- tasks that lost their last member in an EARLIER call: status = requirements (:252 with no members); tasks whose
+    //      count changed but that are feasible are not recomputed by the reference (:249)
+#pragma unroll
+    for (int w = 0; w < TW; ++w) {
+        for (u64 mm = st.dirty[w] & ~st.feas[w] & ~st.ne[w]; mm; mm &= mm - 1) {
+            const int j = 64 * w + ctz64(mm);
+            EL(c, t_status, T, j) = (signed char)EL(c, s_req, T, j);
+            st.open[w] |= mm & (0 - mm);                                      // requirements >= 1
+        }
+        st.dirty[w] &= ~st.feas[w] & st.ne[w];
+        st.fin[w] |= done[w];
+    }
+    // ---- full evaluation (rare: the task that was just joined, a coalition whose earliest member gives up)
+#pragma unroll
+    for (int w = 0; w < TW; ++w)
+        for (u64 mm = hot[w]; mm; mm &= mm - 1) t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly);
     bool allf = true;
 #pragma unroll
     for (int w = 0; w < TW; ++w) allf = allf && st.feas[w] == all_tasks<TW>(T, w);
     if (allf) {                                                               // :277-280 depot members
         for (u64 mm = st.depot & st.route & ~st.returned; mm; mm &= mm - 1) {
             const int i = ctz64(mm);
-            if (now >= EL(c, a_last, c.A, i)) st.returned |= 1ull << i;
+            if (now >= AREC(c, i, AR_LAST)) st.returned |= 1ull << i;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// agent_update (task_env.py:207-243, reactive_planning False), restricted to `which` (a superset of the agents whose
-// next_decision / assigned can differ from what is stored; pass st.route for the full reference loop).
+// agent_update (task_env.py:207-243, reactive_planning False).
+//   full:  agents in `which` are recomputed exactly as the reference does (pass st.route for its whole loop);
+//   watch: members of a feasible task that are not assigned yet only need `now >= time_start` re-checked (:232-233).
+// For every other agent the reference recomputes exactly what is already stored (see DESIGN.md "restricted update").
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which) {
-    const int T = c.T, A = c.A;
+    const int A = c.A;
+    for (u64 mm = st.watch & ~which; mm; mm &= mm - 1) {                      // load-only pass
+        const int i = ctz64(mm);
+        if (now >= EL(c, a_ts, A, i)) { st.assigned |= 1ull << i; st.watch &= ~(1ull << i); }
+    }
     for (u64 mm = which & st.route; mm; mm &= mm - 1) {                       // :209
         const int i = ctz64(mm); const u64 bit = 1ull << i;
         double nd;
@@ -253,24 +257,19 @@ template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St
         else {
             const unsigned k = EL(c, a_node, A, i);
             if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) {             // :229-230
-                const double ts = EL(c, t_start, T, k);
-                nd = ts + EL(c, s_dur, T, k);                                 // :231 time_finish
+                const double ts = TINFO(c, k, 0);
+                nd = TINFO(c, k, 1);                                          // :231 time_finish
                 if (now >= ts) st.assigned |= bit;                            // :232-233 (otherwise unchanged: Q5)
-                else if (!(st.assigned & bit)) st.watch |= bit;               // re-check when the clock reaches time_start
+                else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = ts; }
             } else {
-                nd = EL(c, a_last, A, i) + c.W;                               // :235 / :238
+                nd = AREC(c, i, AR_LAST) + c.W;                               // :235 / :238
                 st.assigned &= ~bit;
             }
         }
-        const double old = EL(c, a_nd, A, i);
-        if (__double_as_longlong(old) != __double_as_longlong(nd)) EL(c, a_nd, A, i) = nd;
+        EL(c, a_nd, A, i) = nd;
     }
     st.touched = 0;
 }
-// agents whose stored next_decision / assigned may be out of date: those that moved or whose task just became
-// feasible (touched), and members of a feasible task still waiting for `now >= time_start` to become assigned (watch).
-// For every other agent the reference's agent_update recomputes exactly what is already stored.
-template <int TW> __device__ __forceinline__ u64 agents_to_update(const St<TW>& st) { return st.touched | st.watch; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // next_decision (task_env.py:283-289): earliest next_decision over the agents, deciders by exact equality (one pass)
@@ -278,7 +277,7 @@ template <int TW> __device__ __forceinline__ u64 agents_to_update(const St<TW>& 
 __device__ __forceinline__ u64 t_next_decision(const TC& c, double& t_out) {
     const int A = c.A;
     double mn = CUDART_INF; u64 mask = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < A; ++i) {
         const double nd = EL(c, a_nd, A, i);
         if (nd < mn) { mn = nd; mask = 1ull << i; }                           // NaN compares false
@@ -286,7 +285,7 @@ __device__ __forceinline__ u64 t_next_decision(const TC& c, double& t_out) {
     }
     if (mask == 0) {                                                          // :285-286 everybody is NaN
         double la = 0.0;
-        for (int i = 0; i < A; ++i) { const double a = EL(c, a_last, A, i); la = a > la ? a : la; }
+        for (int i = 0; i < A; ++i) { const double a = AREC(c, i, AR_LAST); la = a > la ? a : la; }
         t_out = la; return 0;
     }
     t_out = mn;
@@ -309,11 +308,12 @@ template <int TW> __device__ __forceinline__ bool t_all_returned_and_finished(co
 __device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending) {
     if ((pending & (pending - 1)) == 0) return pending;                       // zero or one decider
     double bx = CUDART_INF, by = CUDART_INF; u64 g = 0;
-    for (u64 m = pending; m; m &= m - 1) {
-        const int i = ctz64(m);
-        const double x = EL(c, a_x, c.A, i), y = EL(c, a_y, c.A, i);
-        if (lex_less(x, y, bx, by)) { bx = x; by = y; g = 1ull << i; }
-        else if (x == bx && y == by) g |= 1ull << i;
+    for (u64 m = pending; m;) {                                               // two agents per trip: four loads in flight
+        const int i0 = ctz64(m); m &= m - 1;
+        const int i1 = m ? ctz64(m) : i0; m &= m - 1;
+        const double x0 = AREC(c, i0, AR_X), y0 = AREC(c, i0, AR_Y), x1 = AREC(c, i1, AR_X), y1 = AREC(c, i1, AR_Y);
+        if (lex_less(x0, y0, bx, by)) { bx = x0; by = y0; g = 1ull << i0; } else if (x0 == bx && y0 == by) g |= 1ull << i0;
+        if (lex_less(x1, y1, bx, by)) { bx = x1; by = y1; g = 1ull << i1; } else if (x1 == bx && y1 == by) g |= 1ull << i1;
     }
     return g;
 }
@@ -329,25 +329,29 @@ __device__ __forceinline__ void travel(const TC& c, double ax, double ay, double
 }
 template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<TW>& st, double now, int i, int action, double tx, double ty,
                                                               double d, double tt, unsigned& flags) {
-    const int A = c.A, T = c.T, R = c.MC * c.T;
+    const int A = c.A, T = c.T;
     const u64 bit = 1ull << i;
-    EL(c, a_dist, A, i) = EL(c, a_dist, A, i) + d;                            // :317
     const double arrival = now + tt;                                          // :318
-    EL(c, a_last, A, i) = arrival;
+    AREC(c, i, AR_DIST) = AREC(c, i, AR_DIST) + d;                            // :317
+    AREC(c, i, AR_LAST) = arrival; AREC(c, i, AR_X) = tx; AREC(c, i, AR_Y) = ty;   // :318, :320
     EL(c, a_node, A, i) = (unsigned char)(action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1));   // :314
-    EL(c, a_x, A, i) = tx; EL(c, a_y, A, i) = ty;                             // :320
     st.route |= bit; st.touched |= bit;
     if (action == 0) { st.depot |= bit; st.member &= ~bit; return; }
     st.depot &= ~bit;
     const int j = action - 1;                                                 // :321-322
-    const int n = tbit<TW>(st.ne, j) ? (int)EL(c, t_nmem, T, j) : 0;
+    const bool nonempty = tbit<TW>(st.ne, j);
+    const int n = nonempty ? (int)EL(c, t_nmem, T, j) : 0;
     int pos = -1;
-    for (int s = 0; s < n; ++s) if (EL(c, t_mem, R, s * T + j) == (unsigned)i) pos = s;
-    if (pos >= 0) { EL(c, t_arr, R, pos * T + j) = arrival; st.member |= bit; }   // re-visit by a current member (Q8): last arrival wins
-    else if (n < c.MC) {
-        EL(c, t_mem, R, n * T + j) = (unsigned char)i; EL(c, t_arr, R, n * T + j) = arrival;
+    for (int s = 0; s < n; ++s) if (SMEM(c, j, s) == (unsigned)i) pos = s;
+    const bool feas = tbit<TW>(st.feas, j);
+    if (pos >= 0) {                                                           // re-visit by a current member (Q8): last arrival wins
+        SARR(c, j, pos) = arrival; st.member |= bit;
+        if (!feas) { double amin = CUDART_INF; for (int s = 0; s < n; ++s) { const double a = SARR(c, j, s); amin = a < amin ? a : amin; } TINFO(c, j, 0) = amin; }
+    } else if (n < c.MC) {
+        SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
         EL(c, t_nmem, T, j) = (unsigned char)(n + 1);
-        tset<TW>(st.ne, j, true);
+        if (!feas) { const double amin = n ? TINFO(c, j, 0) : CUDART_INF; if (arrival < amin) TINFO(c, j, 0) = arrival; }
+        tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true);
         st.member |= bit;
     } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }
 }
@@ -361,7 +365,7 @@ template <int TW> __device__ __forceinline__ int t_policy_action(const TC& c, co
     for (int w = 0; w < TW; ++w) n_open += __popcll(st.open[w]);
     if (n_open == 0) return 0;                                                // only the depot is unmasked
     if (policy == 2) {                                                        // greedy nearest (fp64 squared distance, lowest id on ties)
-        const double Lx = EL(c, a_x, c.A, leader), Ly = EL(c, a_y, c.A, leader);
+        const double Lx = AREC(c, leader, AR_X), Ly = AREC(c, leader, AR_Y);
         double bd = CUDART_INF; int bj = -1;
 #pragma unroll
         for (int w = 0; w < TW; ++w) for (u64 mm = st.open[w]; mm; mm &= mm - 1) {
@@ -403,22 +407,22 @@ template <class F> __device__ __forceinline__ double np_sum(F val, int n) {     
     return np_sum_le128(val, 0, n2) + np_sum_le128(val, n2, n - n2);
 }
 
-// out[8] (plain global): reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions.
-// Optional per-element outputs: task_wait [T], agent_wait [A] (plain global rows of this env).  Returns the final clock
-// (the trailing check_finished of :422 may move it).
+// Thread-per-env version (granular dcm_compute_metrics).  out[8] (plain global): reward, success_rate, makespan, time_cost,
+// waiting_time, travel_dist, efficiency, decisions.  Optional per-element outputs: task_wait [T], agent_wait [A].
+// Returns the final clock (the trailing check_finished of :422 may move it).
 template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, const St<TW>& st, double now, unsigned n_steps, double* out,
                                                                    double* task_wait, double* agent_wait) {
-    const int T = c.T, A = c.A, R = c.MC * c.T;
+    const int T = c.T, A = c.A;
     for (int i = 0; i < A; ++i) EL(c, w_agent, A, i) = 0.0;                   // :345-346
     auto task_sum = [&](int j) -> double {                                    // task['sum_waiting_time'] :349-357
         const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
         if (!tbit<TW>(st.ne, j)) return w_ab;
         const int n = EL(c, t_nmem, T, j);
-        double mx = EL(c, t_arr, R, j);
-        for (int s = 1; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); mx = a > mx ? a : mx; }
+        double mx = SARR(c, j, 0);
+        for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; }
         const bool feas = tbit<TW>(st.feas, j);
         double acc = 0.0;                                                     // np.sum of < 8 terms is sequential
-        for (int s = 0; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); acc += feas ? (mx - a) : (now - a); }
+        for (int s = 0; s < n; ++s) { const double a = SARR(c, j, s); acc += feas ? (mx - a) : (now - a); }
         return acc + w_ab;
     };
     // per-agent sums: tasks in id order, members in list order (:358-362); the W * abandon entries are added at the end
@@ -427,11 +431,11 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
     for (int w = 0; w < TW; ++w) for (u64 mm = st.ne[w]; mm; mm &= mm - 1) {
         const int j = 64 * w + ctz64(mm);
         const int n = EL(c, t_nmem, T, j);
-        double mx = EL(c, t_arr, R, j);
-        for (int s = 1; s < n; ++s) { const double a = EL(c, t_arr, R, s * T + j); mx = a > mx ? a : mx; }
+        double mx = SARR(c, j, 0);
+        for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; }
         const bool feas = (st.feas[w] >> (j & 63)) & 1ull;
         for (int s = 0; s < n; ++s) {
-            const double a = EL(c, t_arr, R, s * T + j); const unsigned m = EL(c, t_mem, R, s * T + j);
+            const double a = SARR(c, j, s); const unsigned m = SMEM(c, j, s);
             double add;
             if (feas) add = mx - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }
             EL(c, w_agent, A, m) = EL(c, w_agent, A, m) + add;
@@ -453,9 +457,9 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
     out[0] = -now;                                                            // :424
     out[1] = (double)nfin / (double)T;                                        // worker.py:103
     out[2] = now;                                                             // :104
-    out[3] = np_sum([&](int j) { return tbit<TW>(st.feas, j) ? EL(c, t_start, T, j) : 0.0; }, T) / (double)T;   // :105 nanmean(time_start)
+    out[3] = np_sum([&](int j) { return tbit<TW>(st.feas, j) ? TINFO(c, j, 0) : 0.0; }, T) / (double)T;   // :105 nanmean(time_start)
     out[4] = np_sum([&](int i) { return EL(c, w_agent, A, i); }, A) / (double)A;     // :106
-    out[5] = np_sum([&](int i) { return EL(c, a_dist, A, i); }, A);                  // :107
+    out[5] = np_sum([&](int i) { return AREC(c, i, AR_DIST); }, A);                  // :107
     out[6] = np_sum(task_sum, T) / (double)T;                                        // :108
     out[7] = (double)n_steps;
     return now;
@@ -475,7 +479,7 @@ template <int TW> __device__ __forceinline__ void t_advance(const TC& c, St<TW>&
         if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; return; }     // worker.py:45
         pending = dec; now = t;                                               // worker.py:47-49
         t_task_update(c, st, now, nullptr);                                   // :50
-        t_agent_update(c, st, now, agents_to_update(st));                     // :51
+        t_agent_update(c, st, now, st.touched);                               // :51
         if (pending) return;
         // Nobody could decide.  One such slot is normal (it marks agents as returned); a second in a row means the
         // state can no longer change and the reference `while` (worker.py:45) would spin forever: stop and flag it.
@@ -491,14 +495,16 @@ template <int TW> __device__ __forceinline__ void t_advance(const TC& c, St<TW>&
 template <int TW> __device__ __forceinline__ void obs_agent_row(const TC& c, const St<TW>& st, double now, double Lx, double Ly, int i, float* r) {
     const u64 bit = 1ull << i;
     double travel_t = 0.0, wait = 0.0, remain = 0.0;
-    const double ax = EL(c, a_x, c.A, i), ay = EL(c, a_y, c.A, i);
+    const double ax = AREC(c, i, AR_X), ay = AREC(c, i, AR_Y);
     if ((st.route & bit) && !(st.depot & bit)) {                              // :168
         const unsigned k = EL(c, a_node, c.A, i);
-        const double arr = EL(c, a_last, c.A, i);
-        const double ts = tbit<TW>(st.feas, (int)k) ? EL(c, t_start, c.T, k) : 0.0;
+        const double arr = AREC(c, i, AR_LAST);
+        const bool feas = tbit<TW>(st.feas, (int)k);
+        const double ts = feas ? TINFO(c, k, 0) : 0.0;                        // time_start is 0 until the task is feasible (Q6)
+        const double tf = feas ? TINFO(c, k, 1) : 0.0 + EL(c, s_dur, c.T, k); // fl(time_start + time)
         const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;             // :169
-        if (now <= ts) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }                      // :170
-        if (now >= ts) { const double q = ts + EL(c, s_dur, c.T, k) - now; remain = q < 0.0 ? 0.0 : q; } // :171
+        if (now <= ts) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }   // :170
+        if (now >= ts) { const double q = tf - now; remain = q < 0.0 ? 0.0 : q; }     // :171
     }
     r[0] = __double2float_rn(travel_t); r[1] = __double2float_rn(remain); r[2] = __double2float_rn(wait);   // :176-177
     r[3] = __double2float_rn(Lx - ax); r[4] = __double2float_rn(Ly - ay); r[5] = (st.assigned & bit) ? 1.0f : 0.0f;

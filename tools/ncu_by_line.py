@@ -26,7 +26,8 @@ for l in dis[start + 1:]:
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(out))
 # first kernel only
-hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+kidx = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern.split("ILi")[0].lstrip("_Z0123456789") in r[1]]
+hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address" and (not kidx or i > kidx[0]))
 hdr = rows[hdr_i]
 ci = {n: hdr.index(n) for n in ("Address", "Source", "Instructions Executed", "# Samples", "Thread Instructions Executed", "stall_no_inst", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_branch_resolving")}
 base = None
@@ -60,7 +61,7 @@ def func_table(path):
     except OSError:
         pass
     return tab
-tabs = {f: func_table(os.path.join("dcmrta_b200/csrc", f)) for f in ("dcm_device.cuh", "dcm_kernels.cu")}
+tabs = {f: func_table(os.path.join("dcmrta_b200/csrc", f)) for f in ("dcm_thread.cuh", "dcm_kernels.cu")}
 fagg = collections.defaultdict(collections.Counter)
 for (f, ln), c in agg.items():
     name = f
