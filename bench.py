@@ -216,8 +216,13 @@ def run_ours(args):
     launches1 = env.launch_count()
     w0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
+    prof_at = int(os.environ.get("DCM_PROFILE_AT", "-1"))        # ncu --profile-from-start off: capture a few steady-state steps
+    for k in range(args.steps):
+        if k == prof_at:
+            torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStart()
         env.step(policy=args.policy)
+        if k == prof_at + 1:
+            torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
     ev1.record()
     torch.cuda.synchronize()
     w1 = time.time()

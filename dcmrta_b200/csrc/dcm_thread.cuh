@@ -36,8 +36,10 @@ struct TC {
 #define SARR(c, j, sl) ((c).s.t_slot_arr[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
 #define SMEM(c, j, sl) ((c).s.t_slot_mem[LANE_ROW(c, (c).T, j) * (unsigned)(c).s.MCB + (unsigned)(sl)])   // member id of slot s
 #define TINFO(c, j, k) ((c).s.t_info[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
-#define AREC(c, i, f) ((c).s.a_rec[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // 0 last arrival, 1 x, 2 y, 3 travel_dist
-enum { AR_LAST = 0, AR_X = 1, AR_Y = 2, AR_DIST = 3 };
+#define AREC(c, i, f) ((c).s.a_rec[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // {x, y, last arrival, travel_dist}
+enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
+#define AREC2(c, i, h) (((double2*)(c).s.a_rec)[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
+#define TINFO2(c, j) (((double2*)(c).s.t_info)[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
 
 // register-resident boolean state of one env
 template <int TW> struct St {
@@ -51,6 +53,17 @@ __device__ __forceinline__ int kth_bit(u64 m, int k) {            // position of
     return ctz64(m);
 }
 __device__ __forceinline__ int pick(unsigned word, int n) { return (int)__umulhi(word, (unsigned)n); }
+// Visit the set bits of m four at a time: the four loads are issued before any result is consumed (absent bits alias the
+// first one), so a set of n items costs ceil(n/4) memory round trips instead of n.  The step kernel is latency-bound.
+template <class V, class L, class U> __device__ __forceinline__ void for_bits4(u64 m, int base, L load, U use) {
+    while (m) {
+        const u64 b0 = m & (0 - m); m ^= b0; const u64 b1 = m & (0 - m); m ^= b1;
+        const u64 b2 = m & (0 - m); m ^= b2; const u64 b3 = m & (0 - m); m ^= b3;
+        const int j0 = base + ctz64(b0), j1 = b1 ? base + ctz64(b1) : j0, j2 = b2 ? base + ctz64(b2) : j0, j3 = b3 ? base + ctz64(b3) : j0;
+        const V v0 = load(j0), v1 = load(j1), v2 = load(j2), v3 = load(j3);
+        use(b0, j0, v0); if (b1) use(b1, j1, v1); if (b2) use(b2, j2, v2); if (b3) use(b3, j3, v3);
+    }
+}
 template <int TW> __device__ __forceinline__ u64 all_tasks(int T, int w) {
     const int r = T - 64 * w;
     return r >= 64 ? ~0ull : (r <= 0 ? 0ull : ((1ull << r) - 1));
@@ -201,14 +214,12 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 #pragma unroll
     for (int w = 0; w < TW; ++w) {
         hot[w] = st.dirty[w] & ~st.feas[w] & st.ne[w]; done[w] = 0;
-        for (u64 mm = ~st.feas[w] & st.ne[w] & ~st.dirty[w]; mm; mm &= mm - 1) {       // waiting coalitions: earliest arrival only
-            const int j = 64 * w + ctz64(mm);
-            if (now - TINFO(c, j, 0) >= c.W) hot[w] |= mm & (0 - mm);
-        }
-        for (u64 mm = st.feas[w] & ~st.fin[w]; mm; mm &= mm - 1) {                     // :272-274
-            const int j = 64 * w + ctz64(mm);
-            if (now >= TINFO(c, j, 1)) done[w] |= mm & (0 - mm);
-        }
+        u64 h = 0, dn = 0;
+        for_bits4<double>(~st.feas[w] & st.ne[w] & ~st.dirty[w], 64 * w,                // waiting coalitions: earliest arrival only
+                          [&](int j) { return TINFO(c, j, 0); }, [&](u64 bit, int, double amin) { if (now - amin >= c.W) h |= bit; });
+        for_bits4<double>(st.feas[w] & ~st.fin[w], 64 * w,                              // :272-274
+                          [&](int j) { return TINFO(c, j, 1); }, [&](u64 bit, int, double tf) { if (now >= tf) dn |= bit; });
+        hot[w] |= h; done[w] = dn;
     }
     // ---- tasks that lost their last member in an EARLIER call: status = requirements (:252 with no members); tasks whose
     //      count changed but that are feasible are not recomputed by the reference (:249)
@@ -230,10 +241,10 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 #pragma unroll
     for (int w = 0; w < TW; ++w) allf = allf && st.feas[w] == all_tasks<TW>(T, w);
     if (allf) {                                                               // :277-280 depot members
-        for (u64 mm = st.depot & st.route & ~st.returned; mm; mm &= mm - 1) {
-            const int i = ctz64(mm);
-            if (now >= AREC(c, i, AR_LAST)) st.returned |= 1ull << i;
-        }
+        u64 ret = 0;
+        for_bits4<double>(st.depot & st.route & ~st.returned, 0, [&](int i) { return AREC(c, i, AR_LAST); },
+                          [&](u64 bit, int, double last) { if (now >= last) ret |= bit; });
+        st.returned |= ret;
     }
 }
 
@@ -245,28 +256,35 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which) {
     const int A = c.A;
-    for (u64 mm = st.watch & ~which; mm; mm &= mm - 1) {                      // load-only pass
-        const int i = ctz64(mm);
-        if (now >= EL(c, a_ts, A, i)) { st.assigned |= 1ull << i; st.watch &= ~(1ull << i); }
+    {                                                                         // watch: load-only pass
+        u64 asg = 0;
+        for_bits4<double>(st.watch & ~which, 0, [&](int i) { return EL(c, a_ts, A, i); }, [&](u64 bit, int, double ts) { if (now >= ts) asg |= bit; });
+        st.assigned |= asg; st.watch &= ~asg;
     }
-    for (u64 mm = which & st.route; mm; mm &= mm - 1) {                       // :209
-        const int i = ctz64(mm); const u64 bit = 1ull << i;
-        double nd;
-        st.watch &= ~bit;
-        if (st.depot & bit) nd = CUDART_NAN;                                  // :212, :226
-        else {
-            const unsigned k = EL(c, a_node, A, i);
-            if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) {             // :229-230
-                const double ts = TINFO(c, k, 0);
-                nd = TINFO(c, k, 1);                                          // :231 time_finish
-                if (now >= ts) st.assigned |= bit;                            // :232-233 (otherwise unchanged: Q5)
-                else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = ts; }
+    // full recomputation, four agents per trip: level 1 = their nodes, level 2 = task info + last arrival, then the stores
+    for (u64 m = which & st.route; m;) {                                      // :209
+        const u64 b0 = m & (0 - m); m ^= b0; const u64 b1 = m & (0 - m); m ^= b1;
+        const u64 b2 = m & (0 - m); m ^= b2; const u64 b3 = m & (0 - m); m ^= b3;
+        const int i0 = ctz64(b0), i1 = b1 ? ctz64(b1) : i0, i2 = b2 ? ctz64(b2) : i0, i3 = b3 ? ctz64(b3) : i0;
+        const unsigned n0 = EL(c, a_node, A, i0), n1 = EL(c, a_node, A, i1), n2 = EL(c, a_node, A, i2), n3 = EL(c, a_node, A, i3);
+        const unsigned k0 = n0 == DCM_NODE_DEPOT ? 0u : n0, k1 = n1 == DCM_NODE_DEPOT ? 0u : n1, k2 = n2 == DCM_NODE_DEPOT ? 0u : n2, k3 = n3 == DCM_NODE_DEPOT ? 0u : n3;
+        const double2 t0 = TINFO2(c, k0), t1 = TINFO2(c, k1), t2 = TINFO2(c, k2), t3 = TINFO2(c, k3);
+        const double l0 = AREC(c, i0, AR_LAST), l1 = AREC(c, i1, AR_LAST), l2 = AREC(c, i2, AR_LAST), l3 = AREC(c, i3, AR_LAST);
+        auto one = [&](u64 bit, int i, unsigned k, double2 tinfo, double last) {
+            double nd;
+            st.watch &= ~bit;
+            if (st.depot & bit) nd = CUDART_NAN;                              // :212, :226
+            else if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) {        // :229-230
+                nd = tinfo.y;                                                 // :231 time_finish
+                if (now >= tinfo.x) st.assigned |= bit;                       // :232-233 (otherwise unchanged: Q5)
+                else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = tinfo.x; }
             } else {
-                nd = AREC(c, i, AR_LAST) + c.W;                               // :235 / :238
+                nd = last + c.W;                                              // :235 / :238
                 st.assigned &= ~bit;
             }
-        }
-        EL(c, a_nd, A, i) = nd;
+            EL(c, a_nd, A, i) = nd;
+        };
+        one(b0, i0, k0, t0, l0); if (b1) one(b1, i1, k1, t1, l1); if (b2) one(b2, i2, k2, t2, l2); if (b3) one(b3, i3, k3, t3, l3);
     }
     st.touched = 0;
 }
@@ -308,13 +326,9 @@ template <int TW> __device__ __forceinline__ bool t_all_returned_and_finished(co
 __device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending) {
     if ((pending & (pending - 1)) == 0) return pending;                       // zero or one decider
     double bx = CUDART_INF, by = CUDART_INF; u64 g = 0;
-    for (u64 m = pending; m;) {                                               // two agents per trip: four loads in flight
-        const int i0 = ctz64(m); m &= m - 1;
-        const int i1 = m ? ctz64(m) : i0; m &= m - 1;
-        const double x0 = AREC(c, i0, AR_X), y0 = AREC(c, i0, AR_Y), x1 = AREC(c, i1, AR_X), y1 = AREC(c, i1, AR_Y);
-        if (lex_less(x0, y0, bx, by)) { bx = x0; by = y0; g = 1ull << i0; } else if (x0 == bx && y0 == by) g |= 1ull << i0;
-        if (lex_less(x1, y1, bx, by)) { bx = x1; by = y1; g = 1ull << i1; } else if (x1 == bx && y1 == by) g |= 1ull << i1;
-    }
+    for_bits4<double2>(pending, 0, [&](int i) { return AREC2(c, i, 0); }, [&](u64 bit, int, double2 p) {
+        if (lex_less(p.x, p.y, bx, by)) { bx = p.x; by = p.y; g = bit; } else if (p.x == bx && p.y == by) g |= bit;
+    });
     return g;
 }
 
@@ -331,26 +345,33 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
                                                               double d, double tt, unsigned& flags) {
     const int A = c.A, T = c.T;
     const u64 bit = 1ull << i;
+    const int j = action - 1;
+    const bool to_task = action != 0, feas = to_task && tbit<TW>(st.feas, j), nonempty = to_task && tbit<TW>(st.ne, j);
+    // ---- every load first (nothing below can be hoisted above a byte store by the compiler)
+    const double2 ld = AREC2(c, i, 1);                                        // {last arrival, travel_dist}
+    int n = 0; u64 ids0 = 0, ids1 = 0; double amin = CUDART_INF;
+    if (nonempty) {
+        n = EL(c, t_nmem, T, j);
+        const u64* idw = (const u64*)&SMEM(c, j, 0);
+        ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1];
+        amin = TINFO(c, j, 0);
+    }
     const double arrival = now + tt;                                          // :318
-    AREC(c, i, AR_DIST) = AREC(c, i, AR_DIST) + d;                            // :317
-    AREC(c, i, AR_LAST) = arrival; AREC(c, i, AR_X) = tx; AREC(c, i, AR_Y) = ty;   // :318, :320
-    EL(c, a_node, A, i) = (unsigned char)(action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1));   // :314
+    AREC2(c, i, 1) = make_double2(arrival, ld.y + d);                         // :317-318
+    AREC2(c, i, 0) = make_double2(tx, ty);                                    // :320
+    EL(c, a_node, A, i) = (unsigned char)(to_task ? (unsigned)j : DCM_NODE_DEPOT);   // :314
     st.route |= bit; st.touched |= bit;
-    if (action == 0) { st.depot |= bit; st.member &= ~bit; return; }
+    if (!to_task) { st.depot |= bit; st.member &= ~bit; return; }
     st.depot &= ~bit;
-    const int j = action - 1;                                                 // :321-322
-    const bool nonempty = tbit<TW>(st.ne, j);
-    const int n = nonempty ? (int)EL(c, t_nmem, T, j) : 0;
-    int pos = -1;
-    for (int s = 0; s < n; ++s) if (SMEM(c, j, s) == (unsigned)i) pos = s;
-    const bool feas = tbit<TW>(st.feas, j);
+    int pos = -1;                                                             // :321-322
+    for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
     if (pos >= 0) {                                                           // re-visit by a current member (Q8): last arrival wins
         SARR(c, j, pos) = arrival; st.member |= bit;
-        if (!feas) { double amin = CUDART_INF; for (int s = 0; s < n; ++s) { const double a = SARR(c, j, s); amin = a < amin ? a : amin; } TINFO(c, j, 0) = amin; }
+        if (!feas) { double am = CUDART_INF; for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); am = a < am ? a : am; } TINFO(c, j, 0) = am; }
     } else if (n < c.MC) {
         SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
         EL(c, t_nmem, T, j) = (unsigned char)(n + 1);
-        if (!feas) { const double amin = n ? TINFO(c, j, 0) : CUDART_INF; if (arrival < amin) TINFO(c, j, 0) = arrival; }
+        if (!feas && (n == 0 || arrival < amin)) TINFO(c, j, 0) = arrival;
         tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true);
         st.member |= bit;
     } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }
