@@ -25,9 +25,9 @@ using namespace dcm;
 
 #define STEP_THREADS 64
 #define OBS_THREADS 64
-#define OBS_PITCH 43            // words per env in the staging tile: 40 floats + 8 mask bytes + 1 pad (odd => conflict-free)
-#define OBS_AGENTS_PER_CHUNK 6  // 36 floats
-#define OBS_ROWS_PER_CHUNK 8    // 40 floats + 8 mask bytes
+#define OBS_PITCH 65            // words per env in the staging tile: 60 floats + 12 mask bytes + pad (odd => conflict-free)
+#define OBS_AGENTS_PER_CHUNK 10 // 60 floats
+#define OBS_ROWS_PER_CHUNK 12   // 60 floats + 12 mask bytes
 
 // ---------------------------------------------------------------------------------------------------------------
 // kernel argument blocks
@@ -225,7 +225,16 @@ __device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& s
         const int j = j0 + (int)lane;
         int n = 0; bool feas = false; double mx = 0.0;
         if (j < T) { feas = tbit<TW>(st.feas, j); if (tbit<TW>(st.ne, j)) n = EL(c, t_nmem, T, j); }
-        for (int s = 0; s < n; ++s) { const double a = SARR(c, j, s); S.sa[lane][s] = a; S.sm[lane][s] = SMEM(c, j, s); mx = (s == 0 || a > mx) ? a : mx; }
+        u64 ids0 = 0, ids1 = 0;
+        if (n) { const u64* idw = (const u64*)&SMEM(c, j, 0); ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1]; }
+        for (int s0 = 0; s0 < n; s0 += 4) {                                   // four arrivals in flight
+            const double a0 = SARR(c, j, s0), a1 = SARR(c, j, s0 + 1 < n ? s0 + 1 : s0), a2 = SARR(c, j, s0 + 2 < n ? s0 + 2 : s0), a3 = SARR(c, j, s0 + 3 < n ? s0 + 3 : s0);
+            S.sa[lane][s0] = a0; mx = (s0 == 0 || a0 > mx) ? a0 : mx;
+            if (s0 + 1 < n) { S.sa[lane][s0 + 1] = a1; mx = a1 > mx ? a1 : mx; }
+            if (s0 + 2 < n) { S.sa[lane][s0 + 2] = a2; mx = a2 > mx ? a2 : mx; }
+            if (s0 + 3 < n) { S.sa[lane][s0 + 3] = a3; mx = a3 > mx ? a3 : mx; }
+        }
+        for (int sl = 0; sl < n; ++sl) S.sm[lane][sl] = (unsigned char)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu);
         S.sn[lane] = (unsigned char)(n | (feas ? 0x80 : 0)); S.smx[lane] = mx;
         if (j < T) {                                                          // task['sum_waiting_time'] :349-357
             const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
@@ -349,18 +358,20 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_obs: observation + mask for the leader of every env (envs without a leader are skipped).  One warp per
-// (tile of 32 envs, chunk of rows): lane <-> env produces the chunk's rows into a shared-memory tile with an odd pitch
-// (conflict-free), then the warp streams the 32 x n floats out with unit-stride stores.  blockIdx.y = chunk:
-// [0, NA) agent chunks of 6 rows, [NA, NA + NR) task chunks of 8 rows (+ their mask bytes).
+// (tile of 32 envs, chunk of rows): lane <-> env produces the chunk's rows -- loads batched five / six rows at a time --
+// into a shared-memory tile with an odd pitch (conflict-free), then the warp walks the 32 envs and streams each env's
+// 60 contiguous floats (and its mask bytes) out with unit-stride stores.  blockIdx.y = chunk: [0, NA) agent chunks of 10
+// rows, [NA, NA + NR) task chunks of 12 rows.  mask (task_env.py:192-200 + worker.py:58-61), agent rows (:165-180),
+// task rows (:182-190), cast to fp32 (worker.py:62,64).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flush_floats(const float* tile, float* g, size_t row_len, int col0, int n, unsigned tile_id, unsigned lane,
-                                             unsigned valid, int B) {
-    // 32 envs x n floats staged at tile[e*OBS_PITCH + k]  ->  g[(tile_id*32+e)*row_len + col0 + k], unit stride across the warp
-    const unsigned inv = (1048576u + n - 1) / n;
-    for (unsigned q = lane; q < 32u * n; q += 32) {
-        const unsigned e = (q * inv) >> 20, k = q - e * n;
-        const unsigned be = tile_id * 32 + e;
-        if (be < (unsigned)B && ((valid >> e) & 1u)) g[(size_t)be * row_len + col0 + k] = tile[e * OBS_PITCH + k];
+__device__ __forceinline__ void flush_rows(const float* tile, float* g0, unsigned row_len, int n, unsigned tile_id, unsigned lane, unsigned valid, int B) {
+    // env e of the tile: n floats staged at tile[e*OBS_PITCH ..]  ->  g0[e*row_len ..]; g0 already points at (first env of the tile, first column)
+    const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
+    const float* src = tile + lane; float* dst = g0 + lane;
+    for (int e = 0; e < ne; ++e, src += OBS_PITCH, dst += row_len) {
+        if (!((valid >> e) & 1u)) continue;
+        if ((int)lane < n) dst[0] = src[0];
+        if ((int)lane + 32 < n) dst[32] = src[32];
     }
 }
 
@@ -381,52 +392,90 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
     double Lx = 0, Ly = 0;
-    if (ok) { Lx = AREC(c, leader, AR_X); Ly = AREC(c, leader, AR_Y); }
+    if (ok) { const double2 p = AREC2(c, leader, 0); Lx = p.x; Ly = p.y; }
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK;
     const int chunk = blockIdx.y;
-    if (chunk < NA) {                                                         // ---- agent rows
+    if (chunk < NA) {                                                         // ---- agent rows (:165-180)
         if (!O.agent_obs) return;
         const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
         const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
         if (ok) {
-            St<TW> st;
+            u64 feas[TW];
 #pragma unroll
-            for (int w = 0; w < TW; ++w) st.feas[w] = EL(c, m_feas, TW, w);
-            st.route = EL(c, am_route, 1, 0); st.depot = EL(c, am_depot, 1, 0); st.assigned = EL(c, am_assigned, 1, 0);
+            for (int w = 0; w < TW; ++w) feas[w] = EL(c, m_feas, TW, w);
+            const u64 route = EL(c, am_route, 1, 0), depot = EL(c, am_depot, 1, 0), assigned = EL(c, am_assigned, 1, 0);
             const double now = EL(c, now, 1, 0);
 #pragma unroll
-            for (int i = 0; i < OBS_AGENTS_PER_CHUNK; ++i) if (i < na) obs_agent_row(c, st, now, Lx, Ly, c0 + i, mine + 6 * i);
+            for (int h = 0; h < OBS_AGENTS_PER_CHUNK; h += 5) {               // five agents per batch: 15 + 10 loads in flight
+                double2 xy[5], ld[5], ti[5]; double du[5]; unsigned kk[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); xy[q] = AREC2(c, i, 0); ld[q] = AREC2(c, i, 1); kk[q] = EL(c, a_node, A, i); }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { const unsigned k = kk[q] == DCM_NODE_DEPOT ? 0u : kk[q]; ti[q] = TINFO2(c, k); du[q] = EL(c, s_dur, T, k); }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) if (h + q < na) {
+                    const int i = c0 + h + q; const u64 bit = 1ull << i;
+                    double travel_t = 0.0, wait = 0.0, remain = 0.0;
+                    if ((route & bit) && !(depot & bit)) {                    // :168
+                        const bool fe = tbit<TW>(feas, (int)kk[q]);
+                        const double arr = ld[q].x;
+                        const double ts = fe ? ti[q].x : 0.0;                 // time_start is 0 until the task is feasible (Q6)
+                        const double tf = fe ? ti[q].y : 0.0 + du[q];         // fl(time_start + time)
+                        const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;                       // :169
+                        if (now <= ts) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }     // :170
+                        if (now >= ts) { const double qv = tf - now; remain = qv < 0.0 ? 0.0 : qv; }    // :171
+                    }
+                    float* r = mine + 6 * (h + q);                            // :176-177
+                    r[0] = __double2float_rn(travel_t); r[1] = __double2float_rn(remain); r[2] = __double2float_rn(wait);
+                    r[3] = __double2float_rn(Lx - xy[q].x); r[4] = __double2float_rn(Ly - xy[q].y); r[5] = (assigned & bit) ? 1.0f : 0.0f;
+                }
+            }
         }
         __syncwarp();
-        flush_floats(tile, O.agent_obs, (size_t)6 * A, 6 * c0, 6 * na, tile_id, lane, valid, B);
+        flush_rows(tile, O.agent_obs + (size_t)tile_id * 32 * 6 * A + 6 * c0, 6 * A, 6 * na, tile_id, lane, valid, B);
         return;
     }
-    // ---- task rows (row 0 = depot) + mask bytes
+    // ---- task rows (:182-190; row 0 = depot) + mask bytes
     const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
     const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
-    unsigned char* mbytes = (unsigned char*)(mine + 40);
     if (ok) {
         u64 open[TW]; bool any_open = false;
 #pragma unroll
         for (int w = 0; w < TW; ++w) { open[w] = EL(c, m_open, TW, w); any_open = any_open || open[w] != 0; }
+        unsigned mlo = 0, mhi = 0, mtop = 0;                                  // mask bytes of the chunk, packed (1 = forbidden)
 #pragma unroll
-        for (int i = 0; i < OBS_ROWS_PER_CHUNK; ++i) if (i < nr) {
-            if (O.task_obs) obs_task_row(c, Lx, Ly, r0 + i, mine + 5 * i);
-            const bool is_open = r0 + i > 0 && tbit<TW>(open, r0 + i - 1);    // task_env.py:199
-            mbytes[i] = is_open ? 0 : 1;
+        for (int h = 0; h < OBS_ROWS_PER_CHUNK; h += 6) {                     // six rows per batch: 30 loads in flight
+            double tx[6], ty[6], du[6]; int st[6], rq[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int jj = r0 + (h + q < nr ? h + q : 0); const int j = jj > 0 ? jj - 1 : 0;
+                tx[q] = EL(c, s_tx, T, j); ty[q] = EL(c, s_ty, T, j); du[q] = EL(c, s_dur, T, j); st[q] = EL(c, t_status, T, j); rq[q] = EL(c, s_req, T, j);
+            }
+            if (r0 == 0 && h == 0) { tx[0] = EL(c, s_dep, 2, 0); ty[0] = EL(c, s_dep, 2, 1); }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) if (h + q < nr) {
+                const int jj = r0 + h + q;
+                float* r = mine + 5 * (h + q);
+                if (O.task_obs) {
+                    if (jj == 0) { r[0] = 0.f; r[1] = 0.f; r[2] = 0.f; }      // :188 depot row
+                    else { r[0] = (float)st[q]; r[1] = (float)rq[q]; r[2] = __double2float_rn(du[q]); }   // :185
+                    r[3] = __double2float_rn(tx[q] - Lx); r[4] = __double2float_rn(ty[q] - Ly);           // :186
+                }
+                // :199 task bit: forbidden unless open;  worker.py:58-61 depot bit: allowed only when nothing is open
+                const unsigned forbidden = jj == 0 ? (any_open ? 1u : 0u) : (tbit<TW>(open, jj - 1) ? 0u : 1u);
+                const int sl = h + q;
+                if (sl < 4) mlo |= forbidden << (8 * sl); else if (sl < 8) mhi |= forbidden << (8 * (sl - 4)); else mtop |= forbidden << (8 * (sl - 8));
+            }
         }
-        if (r0 == 0) mbytes[0] = any_open ? 1 : 0;                            // worker.py:58-61 depot bit: allowed only when nothing is open
+        unsigned* mw = (unsigned*)(mine + 60);
+        mw[0] = mlo; mw[1] = mhi; mw[2] = mtop;
     }
     __syncwarp();
-    if (O.task_obs) flush_floats(tile, O.task_obs, (size_t)5 * (T + 1), 5 * r0, 5 * nr, tile_id, lane, valid, B);
+    if (O.task_obs) flush_rows(tile, O.task_obs + (size_t)tile_id * 32 * 5 * (T + 1) + 5 * r0, 5 * (T + 1), 5 * nr, tile_id, lane, valid, B);
     if (O.mask) {
-        const unsigned inv = (1048576u + nr - 1) / nr;
-        for (unsigned q = lane; q < 32u * nr; q += 32) {
-            const unsigned e = (q * inv) >> 20, k = q - e * nr;
-            const unsigned be = tile_id * 32 + e;
-            if (be < (unsigned)B && ((valid >> e) & 1u))
-                O.mask[(size_t)be * (T + 1) + r0 + k] = ((const unsigned char*)(tile + e * OBS_PITCH + 40))[k];
-        }
+        const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
+        const unsigned char* src = (const unsigned char*)(tile + 60) + lane; unsigned char* dst = O.mask + (size_t)tile_id * 32 * (T + 1) + r0 + lane;
+        for (int e = 0; e < ne; ++e, src += 4 * OBS_PITCH, dst += T + 1) if (((valid >> e) & 1u) && (int)lane < nr) dst[0] = src[0];
     }
 }
 
