@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
             }
             EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
             EL(c, am_depot, 1, 0) = 0; EL(c, am_touched, 1, 0) = 0; EL(c, am_watch, 1, 0) = 0;
+            EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF;
             EL(c, now, 1, 0) = 0.0; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = 0;
             EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = nflags;
             if (P.next_leader) P.next_leader[be] = leader;
@@ -411,7 +412,10 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
 #pragma unroll
                 for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); xy[q] = AREC2(c, i, 0); ld[q] = AREC2(c, i, 1); kk[q] = EL(c, a_node, A, i); }
 #pragma unroll
-                for (int q = 0; q < 5; ++q) { const unsigned k = kk[q] == DCM_NODE_DEPOT ? 0u : kk[q]; ti[q] = TINFO2(c, k); du[q] = EL(c, s_dur, T, k); }
+                for (int q = 0; q < 5; ++q) {                                   // one gather per agent that stands at a task, none otherwise
+                    const bool at_task = kk[q] != DCM_NODE_DEPOT; const unsigned k = at_task ? kk[q] : 0u; const bool fe = at_task && tbit<TW>(feas, (int)k);
+                    ti[q] = fe ? TINFO2(c, k) : make_double2(0.0, 0.0); du[q] = (at_task && !fe) ? EL(c, s_dur, T, k) : 0.0;
+                }
 #pragma unroll
                 for (int q = 0; q < 5; ++q) if (h + q < na) {
                     const int i = c0 + h + q; const u64 bit = 1ull << i;
@@ -630,6 +634,7 @@ __global__ void k_init(const __grid_constant__ EnvArgs E) {                   //
     if (b >= E.S.NT * 32) return;
     const TC c = make_tc(E, b);
     EL(c, flags, 1, 0) = ENV_DONE | ENV_ACCOUNTED; EL(c, leader, 1, 0) = -1;
+    EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF;
 }
 
 // tiled SoA <-> per-env record of dcm_layout.h (export / import / checkpoint format)
@@ -671,6 +676,7 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
 #pragma unroll
     for (int w = 0; w < TW; ++w) { st.feas[w] = st.fin[w] = st.ne[w] = st.open[w] = st.dirty[w] = 0; }
     st.route = st.assigned = st.returned = st.member = st.depot = st.touched = st.watch = 0;
+    st.xfin = st.xamin = st.xasg = CUDART_INF;
     const unsigned char* r = src + (size_t)b * L.dyn_bytes;
     const int T = c.T, A = c.A, Tp = L.Tp;
     for (int j = 0; j < T; ++j) {
@@ -681,7 +687,10 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
             SARR(c, j, s) = a; SMEM(c, j, s) = (r + L.o_mem)[s * Tp + j]; amin = a < amin ? a : amin;
         }
         const double ts = ((const double*)(r + L.o_tstart))[j];
-        if (tf & DCM_TF_FEAS) { TINFO(c, j, 0) = ts; TINFO(c, j, 1) = ts + EL(c, s_dur, T, j); } else TINFO(c, j, 0) = amin;
+        if (tf & DCM_TF_FEAS) {
+            const double tfin = ts + EL(c, s_dur, T, j); TINFO(c, j, 0) = ts; TINFO(c, j, 1) = tfin;
+            if (!(tf & DCM_TF_FIN) && tfin < st.xfin) st.xfin = tfin;
+        } else { TINFO(c, j, 0) = amin; if (n > 0 && amin < st.xamin) st.xamin = amin; }
         EL(c, t_nab, T, j) = ((const unsigned short*)(r + L.o_tnab))[j];
         EL(c, t_nmem, T, j) = (unsigned char)n; EL(c, t_status, T, j) = (signed char)stt;
         tset<TW>(st.feas, j, tf & DCM_TF_FEAS); tset<TW>(st.fin, j, tf & DCM_TF_FIN); tset<TW>(st.dirty, j, tf & DCM_TF_STALE);
@@ -698,7 +707,7 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
         if (af & DCM_AF_RETURNED) st.returned |= bit;
         if (af & DCM_AF_MEMBER) st.member |= bit;
         if (af & DCM_AF_TOUCHED) st.touched |= bit;
-        if ((af & DCM_AF_WATCH) && node != DCM_NODE_DEPOT) { st.watch |= bit; EL(c, a_ts, A, i) = ((const double*)(r + L.o_tstart))[node]; }
+        if ((af & DCM_AF_WATCH) && node != DCM_NODE_DEPOT) { const double ts = ((const double*)(r + L.o_tstart))[node]; st.watch |= bit; EL(c, a_ts, A, i) = ts; if (ts < st.xasg) st.xasg = ts; }
         if ((af & DCM_AF_ROUTE) && node == DCM_NODE_DEPOT) st.depot |= bit;
     }
     st_state(c, st0, st);
@@ -782,7 +791,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(NT, K, elem) + 255) / 256 * 256; return o; };
     const int MCB = M <= 8 ? 8 : 16; S.MCB = MCB;
     const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32),
-                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
+                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_asg = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
                  o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
                  o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
                  o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
@@ -799,7 +808,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
     S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec);
-    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
+    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_asg = (double*)(a + o_x_asg); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
     S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
     S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_dirty = (u64*)(a + o_m_dirty);
     S.am_route = (u64*)(a + o_am_route); S.am_assigned = (u64*)(a + o_am_assigned); S.am_returned = (u64*)(a + o_am_returned); S.am_member = (u64*)(a + o_am_member);

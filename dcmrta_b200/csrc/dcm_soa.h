@@ -55,6 +55,7 @@ struct DcmSoa {
     unsigned long long* am_watch;     // member of a feasible task, not assigned yet: re-check `now >= time_start`
     // ---- per env (rows: 1) ----
     double* now;
+    double* x_fin; double* x_amin; double* x_asg;   // conservative lower bounds that let a step skip whole scans (dcm_thread.cuh St)
     unsigned long long* pending;
     unsigned long long* group;
     unsigned* n_steps; unsigned* episode; unsigned* flags; unsigned* instance; unsigned* total;

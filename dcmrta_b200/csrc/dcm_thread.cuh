@@ -45,6 +45,10 @@ enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
 template <int TW> struct St {
     u64 feas[TW], fin[TW], ne[TW], open[TW], dirty[TW];
     u64 route, assigned, returned, member, depot, touched, watch;
+    // conservative lower bounds (never too high, +inf when the set is empty) that let a step skip whole scans:
+    double xfin;    // <= time_finish of every feasible, unfinished task
+    double xamin;   // <= earliest member arrival of every non-feasible task that has members
+    double xasg;    // <= time_start awaited by every watched agent
 };
 
 __device__ __forceinline__ int ctz64(u64 m) { return __ffsll((long long)m) - 1; }
@@ -91,6 +95,7 @@ template <int TW> __device__ __forceinline__ void ld_state(const TC& c, St<TW>& 
     st.route = EL(c, am_route, 1, 0); st.assigned = EL(c, am_assigned, 1, 0); st.returned = EL(c, am_returned, 1, 0);
     st.member = EL(c, am_member, 1, 0); st.depot = EL(c, am_depot, 1, 0); st.touched = EL(c, am_touched, 1, 0);
     st.watch = EL(c, am_watch, 1, 0);
+    st.xfin = EL(c, x_fin, 1, 0); st.xamin = EL(c, x_amin, 1, 0); st.xasg = EL(c, x_asg, 1, 0);
 }
 template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St<TW>& o, const St<TW>& st) {
 #pragma unroll
@@ -108,6 +113,9 @@ template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St
     if (o.depot != st.depot) EL(c, am_depot, 1, 0) = st.depot;
     if (o.touched != st.touched) EL(c, am_touched, 1, 0) = st.touched;
     if (o.watch != st.watch) EL(c, am_watch, 1, 0) = st.watch;
+    if (o.xfin != st.xfin) EL(c, x_fin, 1, 0) = st.xfin;
+    if (o.xamin != st.xamin) EL(c, x_amin, 1, 0) = st.xamin;
+    if (o.xasg != st.xasg) EL(c, x_asg, 1, 0) = st.xasg;
 }
 
 // Philox4x32-10 (Salmon et al. 2011)
@@ -161,7 +169,9 @@ template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW
         double mx = SARR(c, j, 0), mn = mx;
         for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; mn = a < mn ? a : mn; }
         if (mx - mn <= c.W) {                                                 // :255
-            TINFO(c, j, 0) = mx; TINFO(c, j, 1) = mx + EL(c, s_dur, T, j);    // :256-257 time_start, time_finish
+            const double tf = mx + EL(c, s_dur, T, j);
+            TINFO(c, j, 0) = mx; TINFO(c, j, 1) = tf;                         // :256-257 time_start, time_finish
+            st.xfin = tf < st.xfin ? tf : st.xfin;
             feas = bit; open = 0;                                             // :258
             if (newly) newly[j] = 1;
             for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
@@ -209,16 +219,21 @@ template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW
 
 template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly) {
     const int T = c.T;
-    // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished
+    // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished.  Both scans are skipped
+    //      while the clock has not reached the per-env lower bounds (fl(now - x) >= W and now >= x are monotone in x).
+    const bool scan_wait = now - st.xamin >= c.W, scan_fin = now >= st.xfin;
+    double new_amin = CUDART_INF, new_fin = CUDART_INF;
     u64 hot[TW], done[TW];
 #pragma unroll
     for (int w = 0; w < TW; ++w) {
         hot[w] = st.dirty[w] & ~st.feas[w] & st.ne[w]; done[w] = 0;
         u64 h = 0, dn = 0;
-        for_bits4<double>(~st.feas[w] & st.ne[w] & ~st.dirty[w], 64 * w,                // waiting coalitions: earliest arrival only
-                          [&](int j) { return TINFO(c, j, 0); }, [&](u64 bit, int, double amin) { if (now - amin >= c.W) h |= bit; });
-        for_bits4<double>(st.feas[w] & ~st.fin[w], 64 * w,                              // :272-274
-                          [&](int j) { return TINFO(c, j, 1); }, [&](u64 bit, int, double tf) { if (now >= tf) dn |= bit; });
+        if (scan_wait) for_bits4<double>(~st.feas[w] & st.ne[w], 64 * w,               // waiting coalitions: earliest arrival only
+                          [&](int j) { return TINFO(c, j, 0); },
+                          [&](u64 bit, int, double amin) { if (now - amin >= c.W) h |= bit & ~st.dirty[w]; new_amin = amin < new_amin ? amin : new_amin; });
+        if (scan_fin) for_bits4<double>(st.feas[w] & ~st.fin[w], 64 * w,                // :272-274
+                          [&](int j) { return TINFO(c, j, 1); },
+                          [&](u64 bit, int, double tf) { if (now >= tf) dn |= bit; else new_fin = tf < new_fin ? tf : new_fin; });
         hot[w] |= h; done[w] = dn;
     }
     // ---- tasks that lost their last member in an EARLIER call: status = requirements (:252 with no members); tasks whose
@@ -233,6 +248,8 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
         st.dirty[w] &= ~st.feas[w] & st.ne[w];
         st.fin[w] |= done[w];
     }
+    if (scan_wait) st.xamin = new_amin;                                       // exact again (tasks evaluated below only raise theirs)
+    if (scan_fin) st.xfin = new_fin;
     // ---- full evaluation (rare: the task that was just joined, a coalition whose earliest member gives up)
 #pragma unroll
     for (int w = 0; w < TW; ++w)
@@ -256,10 +273,11 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which) {
     const int A = c.A;
-    {                                                                         // watch: load-only pass
-        u64 asg = 0;
-        for_bits4<double>(st.watch & ~which, 0, [&](int i) { return EL(c, a_ts, A, i); }, [&](u64 bit, int, double ts) { if (now >= ts) asg |= bit; });
-        st.assigned |= asg; st.watch &= ~asg;
+    if (now >= st.xasg) {                                                     // watch: load-only pass, only when somebody can become assigned
+        u64 asg = 0; double nx = CUDART_INF;
+        for_bits4<double>(st.watch & ~which, 0, [&](int i) { return EL(c, a_ts, A, i); },
+                          [&](u64 bit, int, double ts) { if (now >= ts) asg |= bit; else nx = ts < nx ? ts : nx; });
+        st.assigned |= asg; st.watch &= ~asg; st.xasg = nx;
     }
     // full recomputation, four agents per trip: level 1 = their nodes, level 2 = task info + last arrival, then the stores
     for (u64 m = which & st.route; m;) {                                      // :209
@@ -277,7 +295,7 @@ template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St
             else if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) {        // :229-230
                 nd = tinfo.y;                                                 // :231 time_finish
                 if (now >= tinfo.x) st.assigned |= bit;                       // :232-233 (otherwise unchanged: Q5)
-                else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = tinfo.x; }
+                else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = tinfo.x; st.xasg = tinfo.x < st.xasg ? tinfo.x : st.xasg; }
             } else {
                 nd = last + c.W;                                              // :235 / :238
                 st.assigned &= ~bit;
@@ -367,11 +385,11 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
     if (pos >= 0) {                                                           // re-visit by a current member (Q8): last arrival wins
         SARR(c, j, pos) = arrival; st.member |= bit;
-        if (!feas) { double am = CUDART_INF; for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); am = a < am ? a : am; } TINFO(c, j, 0) = am; }
+        if (!feas) { double am = CUDART_INF; for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); am = a < am ? a : am; } TINFO(c, j, 0) = am; st.xamin = am < st.xamin ? am : st.xamin; }
     } else if (n < c.MC) {
         SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
         EL(c, t_nmem, T, j) = (unsigned char)(n + 1);
-        if (!feas && (n == 0 || arrival < amin)) TINFO(c, j, 0) = arrival;
+        if (!feas) { if (n == 0 || arrival < amin) TINFO(c, j, 0) = arrival; st.xamin = arrival < st.xamin ? arrival : st.xamin; }
         tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true);
         st.member |= bit;
     } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }
