@@ -45,7 +45,8 @@ struct StepArgs {
     int* next_leader; float* reward; unsigned char* done; int* used_action;
 };
 
-struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask; };
+struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask;
+                 int fresh_only; /* only envs that k_episode restarted in this call (ENV_FRESH) */ };
 
 enum GranOp { OP_NEXT_DECISION = 1, OP_UNIQUE_GROUP, OP_SET_CLOCK, OP_GET_CLOCK, OP_TASK_UPDATE, OP_AGENT_UPDATE, OP_APPLY_MEMBERS,
               OP_CHECK_FINISHED, OP_COMPUTE_METRICS, OP_ENV_FLAGS };
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ E
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
     const TC c = make_tc(E, b);
-    unsigned flags = EL(c, flags, 1, 0);
+    unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
     if (flags & ENV_DONE) {                                                   // finished earlier and not restarted: untouched
         if (F.next_leader) F.next_leader[b] = -1;
         if (F.reward) F.reward[b] = 0.f;
@@ -206,19 +207,31 @@ struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int
 __device__ __forceinline__ double wmax(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; } return v; }
 __device__ __forceinline__ double wmin(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; } return v; }
 
+// per-warp scratch of k_episode, carved from dynamic shared memory and sized for the handle's (A, T, MC)
 struct EpiScratch {
-    double sa[32][DCM_MAX_M];        // arrivals of the slots of the 32 tasks of a batch
-    double smx[32];                  // latest arrival per task
-    double s_task[DCM_MAX_TASKS + 2], s_ts[DCM_MAX_TASKS + 2], s_agent[DCM_MAX_AGENTS], s_dist[DCM_MAX_AGENTS];
-    unsigned char sm[32][DCM_MAX_M]; // member ids
-    unsigned char sn[32];            // member count | feasible << 7
+    double* sa;            // [32][MC]  arrivals of the slots of the 32 tasks of a batch
+    double* smx;           // [32]      latest arrival per task
+    double *s_task, *s_ts; // [T]
+    double *s_agent, *s_dist;   // [A]
+    unsigned char* sm;     // [32][MC]  member ids
+    unsigned char* sn;     // [32]      member count | feasible << 7
+    int MC;
 };
+__host__ __device__ inline size_t epi_scratch_bytes(int A, int T, int MC) {
+    return (size_t)8 * (32 * MC + 32 + 2 * T + 2 * A) + (((size_t)32 * MC + 32 + 7) / 8) * 8;
+}
+__device__ __forceinline__ EpiScratch epi_scratch(unsigned char* base, int A, int T, int MC) {
+    EpiScratch S; double* d = (double*)base;
+    S.sa = d; d += 32 * MC; S.smx = d; d += 32; S.s_task = d; d += T; S.s_ts = d; d += T; S.s_agent = d; d += A; S.s_dist = d; d += A;
+    S.sm = (unsigned char*)d; S.sn = S.sm + 32 * MC; S.MC = MC;
+    return S;
+}
 
 // out[8]: reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions.  Returns the final clock.
 // Warp-cooperative: tasks are staged 32 at a time (lane <-> task, all slot loads in flight at once), then the agent sums are
 // accumulated in the reference order (tasks ascending, members in list order, :358-362) from shared memory.
 template <int TW>
-__device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, EpiScratch& S) {
+__device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, const EpiScratch& S) {
     const int T = c.T, A = c.A;
     double acc0 = 0.0, acc1 = 0.0;
     for (int j0 = 0; j0 < T; j0 += 32) {
@@ -229,17 +242,17 @@ __device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& s
         if (n) { const u64* idw = (const u64*)&SMEM(c, j, 0); ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1]; }
         for (int s0 = 0; s0 < n; s0 += 4) {                                   // four arrivals in flight
             const double a0 = SARR(c, j, s0), a1 = SARR(c, j, s0 + 1 < n ? s0 + 1 : s0), a2 = SARR(c, j, s0 + 2 < n ? s0 + 2 : s0), a3 = SARR(c, j, s0 + 3 < n ? s0 + 3 : s0);
-            S.sa[lane][s0] = a0; mx = (s0 == 0 || a0 > mx) ? a0 : mx;
-            if (s0 + 1 < n) { S.sa[lane][s0 + 1] = a1; mx = a1 > mx ? a1 : mx; }
-            if (s0 + 2 < n) { S.sa[lane][s0 + 2] = a2; mx = a2 > mx ? a2 : mx; }
-            if (s0 + 3 < n) { S.sa[lane][s0 + 3] = a3; mx = a3 > mx ? a3 : mx; }
+            S.sa[lane * S.MC + s0] = a0; mx = (s0 == 0 || a0 > mx) ? a0 : mx;
+            if (s0 + 1 < n) { S.sa[lane * S.MC + s0 + 1] = a1; mx = a1 > mx ? a1 : mx; }
+            if (s0 + 2 < n) { S.sa[lane * S.MC + s0 + 2] = a2; mx = a2 > mx ? a2 : mx; }
+            if (s0 + 3 < n) { S.sa[lane * S.MC + s0 + 3] = a3; mx = a3 > mx ? a3 : mx; }
         }
-        for (int sl = 0; sl < n; ++sl) S.sm[lane][sl] = (unsigned char)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu);
+        for (int sl = 0; sl < n; ++sl) S.sm[lane * S.MC + sl] = (unsigned char)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu);
         S.sn[lane] = (unsigned char)(n | (feas ? 0x80 : 0)); S.smx[lane] = mx;
         if (j < T) {                                                          // task['sum_waiting_time'] :349-357
             const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
             double v = w_ab;
-            if (n) { double acc = 0.0; for (int s = 0; s < n; ++s) { const double a = S.sa[lane][s]; acc += feas ? (mx - a) : (now - a); } v = acc + w_ab; }
+            if (n) { double acc = 0.0; for (int s = 0; s < n; ++s) { const double a = S.sa[lane * S.MC + s]; acc += feas ? (mx - a) : (now - a); } v = acc + w_ab; }
             S.s_task[j] = v;
             S.s_ts[j] = feas ? TINFO(c, j, 0) : 0.0;
         }
@@ -248,7 +261,7 @@ __device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& s
         for (int t = 0; t < nt; ++t) {
             const int cnt = S.sn[t] & 0x7f; const bool ft = S.sn[t] & 0x80; const double mxt = S.smx[t];
             for (int s = 0; s < cnt; ++s) {
-                const unsigned m = S.sm[t][s]; const double a = S.sa[t][s];
+                const unsigned m = S.sm[t * S.MC + s]; const double a = S.sa[t * S.MC + s];
                 double add;
                 if (ft) add = mxt - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }     // :360 / :362
                 if (lane == (m & 31u)) { if (m < 32u) acc0 += add; else acc1 += add; }
@@ -290,10 +303,11 @@ __device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& s
 // one block per tile; the block's warps share the tile's envs that need work (warp w takes the w-th, (w+4)-th, ... of them)
 template <int TW>
 __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
-    __shared__ EpiScratch scratch[EPI_WARPS];
+    extern __shared__ __align__(16) unsigned char epi_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned tile = blockIdx.x;
     const int B = E.S.B, A = E.S.A, T = E.S.T;
+    const EpiScratch scratch = epi_scratch(epi_smem + warp * epi_scratch_bytes(A, T, E.S.MC), A, T, E.S.MC);
     const int b = (int)(tile * 32 + lane);
     bool need = false;
     if (b < B) {
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
         unsigned flags = EL(c, flags, 1, 0), episode = EL(c, episode, 1, 0);
         const u64 gid = E.first_gid + (u64)be;
         if (P.mode == 0) {
-            const double now = w_episode_metrics(c, st, lane, EL(c, now, 1, 0), EL(c, n_steps, 1, 0), P.metrics + (size_t)be * 8, scratch[warp]);
+            const double now = w_episode_metrics(c, st, lane, EL(c, now, 1, 0), EL(c, n_steps, 1, 0), P.metrics + (size_t)be * 8, scratch);
             ++episode; flags |= ENV_ACCOUNTED;
             if (!(E.cflags & DCM_FLAG_AUTO_RESET)) {
                 if (lane == 0) { EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, episode, 1, 0) = episode; }
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
         }
         // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
         const u64 all = A >= 64 ? ~0ull : ((1ull << A) - 1);
-        unsigned nflags = 0; u64 pending = all, group = all; int leader;
+        unsigned nflags = P.mode == 0 ? ENV_FRESH : 0u; u64 pending = all, group = all; int leader;
         if (!(0.0 < E.max_time)) { nflags = ENV_DONE | ENV_ACCOUNTED; pending = 0; group = 0; leader = -1; }
         else {
             const int inj = P.leader_in ? P.leader_in[be] : -1;
@@ -389,6 +403,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
     const TC c = make_tc(E, b < B ? b : B - 1);
     int leader = -1;
     if (b < B) leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0);
+    if (O.fresh_only && b < B && !(EL(c, flags, 1, 0) & ENV_FRESH)) leader = -1;
     const bool ok = leader >= 0 && leader < A;
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
@@ -819,6 +834,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status); S.a_node = a + o_a_node; S.s_req = a + o_s_req;
     k_init<<<(S.NT * 32 + 127) / 128, 128>>>(v->E);
     e = cudaDeviceSynchronize();
+
     if (e != cudaSuccess) { dcm_destroy(v); return fail_cuda(e, "dcm_create init"); }
     v->launches = 1;
     *out = v;
@@ -909,7 +925,10 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 }
 
 static int launch_episode(dcm_env* v, const EpiArgs& P, cudaStream_t s) {
-    LAUNCH_TW(v, k_episode, v->E.S.NT, 32 * EPI_WARPS, s, v->E, P);
+    const size_t smem = EPI_WARPS * epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
+    if (v->E.S.TW == 1) k_episode<1><<<v->E.S.NT, 32 * EPI_WARPS, smem, s>>>(v->E, P);
+    else if (v->E.S.TW == 2) k_episode<2><<<v->E.S.NT, 32 * EPI_WARPS, smem, s>>>(v->E, P);
+    else k_episode<4><<<v->E.S.NT, 32 * EPI_WARPS, smem, s>>>(v->E, P);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
@@ -924,7 +943,7 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
     EpiArgs P{1, which, leader_in, next_leader, v->metrics};
     int rc = launch_episode(v, P, s);
     if (rc) return rc;
-    ObsArgs O{nullptr, agent_obs, task_obs, mask};
+    ObsArgs O{nullptr, agent_obs, task_obs, mask, 0};
     if (agent_obs || task_obs || mask) return launch_obs(v, O, s);
     return DCM_OK;
 }
@@ -945,11 +964,12 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     CK(cudaGetLastError());
     v->launches++;
     // episode accounting (+ restart with DCM_FLAG_AUTO_RESET) of the envs that just finished; the injected leader of a
-    // restarted env is the same next_leader_in entry
+    // restarted env is the same next_leader_in entry.  (Running this beside k_obs on a side stream was measured and is
+    // slower: 206 vs 194 us per step at 65,536 envs -- see DESIGN.md.)
     EpiArgs P{0, nullptr, next_leader_in, next_leader, v->metrics};
     int rc = launch_episode(v, P, s);
     if (rc) return rc;
-    ObsArgs O{nullptr, agent_obs, task_obs, mask};
+    ObsArgs O{nullptr, agent_obs, task_obs, mask, 0};
     if (agent_obs || task_obs || mask) return launch_obs(v, O, s);
     return DCM_OK;
 }
@@ -1031,7 +1051,7 @@ int dcm_build_obs(dcm_env* v, const int32_t* leader, float* agent_obs, float* ta
     if (!v || !leader) return fail(DCM_ERR_ARG, "dcm_build_obs: NULL argument");
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_build_obs: load or generate instances first");
     DeviceGuard g(v->device);
-    ObsArgs O{leader, agent_obs, task_obs, mask};
+    ObsArgs O{leader, agent_obs, task_obs, mask, 0};
     return launch_obs(v, O, (cudaStream_t)stream);
 }
 int dcm_check_finished(dcm_env* v, uint8_t* finished, void* stream) {

@@ -19,7 +19,7 @@ namespace dcm {
 typedef unsigned long long u64;
 
 constexpr unsigned ENV_DONE = 1u, ENV_FINISHED = 2u, ENV_STUCK = 4u, ENV_ERR_OVERFLOW = 16u, ENV_ERR_ACTION = 32u,
-                   ENV_ERR_FOLLOW = 64u, ENV_ERR_LEADER = 128u, ENV_ACCOUNTED = 256u;
+                   ENV_ERR_FOLLOW = 64u, ENV_ERR_LEADER = 128u, ENV_ACCOUNTED = 256u, ENV_FRESH = 512u;
 
 // thread context: which env, plus the scalar parameters
 struct TC {

@@ -62,6 +62,7 @@ enum dcm_status {
 #define DCM_ENV_ERR_FOLLOW   64u  /* injected followers are not what step() could have drawn (task_env.py:331) */
 #define DCM_ENV_ERR_LEADER  128u  /* injected leader is not in the current group (worker.py:54) */
 #define DCM_ENV_ACCOUNTED   256u  /* the finished episode's metrics have been computed (dcm_episode_metrics has them) */
+#define DCM_ENV_FRESH       512u  /* restarted by the last dcm_step (auto-reset); cleared by the next one */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */
 
