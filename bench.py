@@ -14,7 +14,8 @@ uniform-random policy over unmasked actions (in-kernel Philox), auto-reset, fp64
   e2e          same metric through the host-buffer C-ABI call (dcm_step_host): actions H2D from pinned memory,
                reward/done/next-leader D2H every step, observations written to the device-resident policy buffers
   e2e_full_obs as e2e but the observations and mask are also copied to pinned host memory every step (PCIe-bound)
-  roofline     HBM: algorithmic bytes/step (w=8) x B / average k_fused duration vs MEASURED_PEAKS.json
+  roofline     HBM: algorithmic bytes/step (w=8) x B / average duration of one pass (k_step + k_episode + k_obs,
+               CUDA events on the launching stream) vs MEASURED_PEAKS.json; traffic = ncu DRAM bytes of the same pass
   cpu_baseline the C oracle port of the reference TaskEnv on the host cores, bounded sample of the same workload
 """
 from __future__ import annotations
@@ -180,10 +181,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.sharding import dist_env, shard_range
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = dist_env()
     if world != args.gpus and world == 1 and args.gpus > 1:
         # not launched under torchrun: re-exec ourselves with one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
@@ -198,8 +198,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    B, A, T = args.envs, args.agents, args.tasks
-    env = BatchedTaskEnv(B, A, T, M=5, device=local, auto_reset=True, seed=1234, first_gid=rank * B)
+    A, T = args.agents, args.tasks
+    first_gid, B = shard_range(args.envs * world, rank, world)      # weak scaling: args.envs per GPU, global ids are shard-invariant
+    env = BatchedTaskEnv(B, A, T, M=5, device=local, auto_reset=True, seed=1234, first_gid=first_gid)
     env.generate(max_duration=5.0)
     env.reset()
     launches0 = env.launch_count()
@@ -242,14 +243,14 @@ def run_ours(args):
     # ---- end-to-end through the host-buffer C-ABI call ---------------------------------------------------------------
     def e2e(full_obs):
         K = args.e2e_steps
-        env.seed(4321, first_gid=rank * B)
+        env.seed(4321, first_gid=first_gid)
         env.reset()
         acts = torch.empty(K + 8, B, dtype=torch.int32).pin_memory()
         for k in range(K + 8):                      # record a valid action trace (deterministic given the Philox contract)
             env.step(policy=args.policy)
             acts[k].copy_(env.used_action, non_blocking=True)
         torch.cuda.synchronize()
-        env.seed(4321, first_gid=rank * B)
+        env.seed(4321, first_gid=first_gid)
         env.reset()
         torch.cuda.synchronize()
         out = {"next_leader": torch.empty(B, dtype=torch.int32).pin_memory(), "reward": torch.empty(B, dtype=torch.float32).pin_memory(),
@@ -305,7 +306,7 @@ def run_ours(args):
                          "what": "as e2e plus agent_obs/task_obs/mask copied to pinned host memory every step"},
         "gpu_launches": launched, "env_steps_timed": total_steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_fused", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
+                     "kernel": "k_step+k_episode+k_obs (one pass)", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
                      "launch_us": per_launch_s * 1e6},
         "clocks": clocks,
     }
