@@ -14,12 +14,14 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 
 #include "../../include/dcmrta.h"
 #include "dcm_thread.cuh"
+#include "dcm_fast.cuh"
 
 using namespace dcm;
 
@@ -60,7 +62,7 @@ struct GranArgs {
 };
 
 __device__ __forceinline__ TC make_tc(const EnvArgs& E, int b) {
-    return TC{E.S, (unsigned)b >> 5, (unsigned)b & 31u, E.S.A, E.S.T, E.S.MC, E.W, E.vel, E.max_time};
+    return TC{E.S, (unsigned)b >> 5, (unsigned)b & 31u, (size_t)((unsigned)b >> 5) * E.S.tile_stride, E.S.A, E.S.T, E.S.MC, E.W, E.vel, E.max_time};
 }
 
 // on-device instance generation for one env; Philox ctr = (gid_lo, gid_hi, instance#, 0x80000000 + 2*j + b)
@@ -195,6 +197,159 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ E
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_step_fast: the same decision as k_step with the chosen task, the node ids and the per-env masks held in registers
+// (dcm_fast.cuh).  Used whenever the handle has at most 8 member slots per task; k_step stays the generic version.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, const St<TW>& st) {
+#pragma unroll
+    for (int w = 0; w < TW; ++w) {
+        EL(c, m_feas, TW, w) = st.feas[w]; EL(c, m_fin, TW, w) = st.fin[w]; EL(c, m_ne, TW, w) = st.ne[w];
+        EL(c, m_open, TW, w) = st.open[w]; EL(c, m_dirty, TW, w) = st.dirty[w];
+    }
+    EL(c, am_route, 1, 0) = st.route; EL(c, am_assigned, 1, 0) = st.assigned; EL(c, am_returned, 1, 0) = st.returned;
+    EL(c, am_member, 1, 0) = st.member; EL(c, am_depot, 1, 0) = st.depot; EL(c, am_touched, 1, 0) = st.touched; EL(c, am_watch, 1, 0) = st.watch;
+    EL(c, x_fin, 1, 0) = st.xfin; EL(c, x_amin, 1, 0) = st.xamin; EL(c, x_asg, 1, 0) = st.xasg; EL(c, x_ret, 1, 0) = st.xret; EL(c, x_last, 1, 0) = st.xlast;
+}
+
+template <int TW, int NW>
+__global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
+    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (b >= E.S.B) return;
+    const TC c = make_tc(E, b);
+    // ---- round 1: everything that does not depend on the action
+    unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
+    St<TW> st; ld_state(c, st);
+    Nodes<NW> nodes; ld_nodes<NW>(c, nodes);
+    double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
+    unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0);
+    int leader = EL(c, leader, 1, 0);
+    const int action_in = F.policy == 0 ? F.action[b] : 0;
+    if (flags & ENV_DONE) {                                                   // finished earlier and not restarted: untouched
+        if (F.next_leader) F.next_leader[b] = -1;
+        if (F.reward) F.reward[b] = 0.f;
+        if (F.done) F.done[b] = 1;
+        if (F.used_action) F.used_action[b] = -1;
+        return;
+    }
+    const Rng rng{E.seed, E.first_gid + (u64)b};
+    float reward_out = 0.f; int action_out = -1;
+    bool ok = true;
+    uint4 b0 = make_uint4(0, 0, 0, 0);
+    bool have_b0 = false;
+    int action;
+    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
+    else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
+    else action = action_in;
+    if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
+    const bool to_task = ok && action != 0; const int j = to_task ? action - 1 : 0;
+    // ---- round 2: the chosen task, its coordinates, the leader's location
+    TaskR R; r_load<TW>(c, st, j, to_task, R);
+    double tx, ty; node_xy(c, to_task ? (unsigned)j : DCM_NODE_DEPOT, tx, ty);
+    const double2 L = AREC2(c, ok ? leader : 0, 0);
+    int want = 0; u64 g = group & ~(1ull << leader);                          // task_env.py:328
+    const int* fp = F.followers ? F.followers + (size_t)b * F.fstride : nullptr;
+    if (ok) {
+        const int vacancy = action == 0 ? __popcll(group) : R.status0;        // :327
+        if (vacancy > 1) { const int avail = __popcll(g); want = vacancy - 1 < avail ? vacancy - 1 : avail; }   // :330-331
+        if (fp && action != 0) {                                              // validate injected followers before touching state
+            u64 gg = g;
+            for (int k = 0; k < want && ok; ++k) {
+                const int fo = k < F.fstride ? fp[k] : -1;
+                if (fo < 0 || fo >= c.A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
+            }
+            if (ok && want < F.fstride && fp[want] >= 0) ok = false;
+            if (!ok) flags |= ENV_ERR_FOLLOW;
+        }
+    }
+    if (ok) {
+        action_out = action;
+        // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
+        double d, tt; travel(c, L.x, L.y, tx, ty, d, tt);
+        const double arrival = now + tt;                                      // :318
+        double reward = 0.0; int nm = 0; u64 mv = 0; bool appended = false;
+        auto move = [&](int i) {                                              // agent_step (:300-324)
+            const u64 bit = 1ull << i;
+            AREC2(c, i, 0) = make_double2(tx, ty);                            // :320
+            AREC(c, i, AR_LAST) = arrival;                                    // :318
+            atomicAdd(&AREC(c, i, AR_DIST), d);                               // :317 travel_dist += d, no load
+            const unsigned nn = to_task ? (unsigned)j : DCM_NODE_DEPOT;
+            ANODE(c, i) = (unsigned char)nn; nset<NW>(nodes, i, nn);          // :314
+            st.route |= bit; st.touched |= bit; mv |= bit; pending &= ~bit;
+            if (!to_task) { st.depot |= bit; st.member &= ~bit; }
+            else { st.depot &= ~bit; r_join<TW>(c, st, R, i, arrival, flags, appended); }
+            reward += -tt; ++nm;
+        };
+        move(leader);
+        if (action == 0) {                                                    // Q11: the whole remaining group follows to the depot
+            for (; g; g &= g - 1) move(ctz64(g));
+        } else {
+            uint4 blk = b0;
+            for (int k = 0; k < want; ++k) {
+                int fo;
+                if (fp) fo = fp[k];                                           // injected (trace replay)
+                else {                                                        // :331 uniform without replacement
+                    const int slot = 2 + k;
+                    if ((slot & 3) == 0 || !have_b0) { blk = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2)); have_b0 = true; }
+                    fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
+                }
+                g &= ~(1ull << fo);
+                move(fo);
+            }
+        }
+        if (to_task) {
+            if (appended) { tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
+            if (!tbit<TW>(st.feas, j) && R.n > 0 && R.wr) {                   // earliest member arrival of a waiting coalition
+                const double am = r_amin(R);
+                if (!R.had || am != R.info.x) TINFO(c, j, 0) = am;
+                R.info.x = am; st.xamin = am < st.xamin ? am : st.xamin;
+            }
+        }
+        reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
+        st.xlast = arrival > st.xlast ? arrival : st.xlast;
+        if (!to_task) st.xret = arrival < st.xret ? arrival : st.xret;
+        ++n_steps; atomicAdd(&EL(c, total, 1, 0), 1u);
+        // One loop body serves the updates after the decision (worker.py:74,76) and the updates of every slot start that
+        // follows (worker.py:45-51, :85) -- a single copy of the code in the instruction cache.
+        double2 jinfo = R.info;
+        int jr = to_task ? j : -1; bool slot_start = false; u64 dec = 0; int empty_slots = 0;
+        for (;;) {
+            f_task_update<TW, NW>(c, st, nodes, now, jr, R, jinfo, slot_start, dec);
+            const int jk = (jr >= 0 && tbit<TW>(st.feas, jr)) ? jr : -1;
+            f_agent_update<TW, NW>(c, st, nodes, now, st.touched, mv, arrival, jk, jinfo);
+            if (pending) break;
+            if (slot_start && ++empty_slots >= 2) { flags |= ENV_DONE | ENV_STUCK; break; }   // see t_advance
+            double t; dec = f_next_decision<TW>(c, st, t);                    // :283-289
+            if (dec == 0) {                                                   // check_finished :368-370
+                now = t;
+                if (t_all_returned_and_finished(c, st)) flags |= ENV_FINISHED;
+            }
+            if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; break; }     // worker.py:45
+            pending = dec; now = t;                                           // worker.py:47-49
+            slot_start = true; jr = -1; mv = 0;
+        }
+        if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
+        else {
+            group = f_current_group<NW>(c, nodes, pending);                   // :291-298
+            const int inj = F.leader_in ? F.leader_in[b] : -1;
+            if (inj >= 0) {
+                if (inj < c.A && ((group >> inj) & 1ull)) leader = inj;
+                else { flags |= ENV_ERR_LEADER; leader = ctz64(group); }
+            } else {
+                const int n = __popcll(group);
+                leader = n == 1 ? ctz64(group) : kth_bit(group, pick(draw_block(rng, episode, n_steps, 0).y, n));   // worker.py:54
+            }
+        }
+        st_state_all(c, st);
+    }
+    if (F.next_leader) F.next_leader[b] = leader;
+    if (F.reward) F.reward[b] = reward_out;
+    if (F.done) F.done[b] = (flags & ENV_DONE) ? 1 : 0;
+    if (F.used_action) F.used_action[b] = action_out;
+    EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
+    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // k_episode: episode accounting (worker.py:87, :103-108) and restart (clear_decisions + first slot + first leader) for
 // the envs that need it -- about 1 env in 125 per step -- done WARP-COOPERATIVELY (lanes over tasks / agents) by the
 // warp that owns the tile, so that this rare, long path stays off the critical path of k_step.
@@ -312,7 +467,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
     bool need = false;
     if (b < B) {
         if (P.mode == 1) need = !P.which || P.which[b];
-        else { const unsigned f = E.S.flags[b]; need = (f & ENV_DONE) && !(f & ENV_ACCOUNTED); }   // K == 1: tiled index == linear index
+        else { const TC cb = make_tc(E, b); const unsigned f = EL(cb, flags, 1, 0); need = (f & ENV_DONE) && !(f & ENV_ACCOUNTED); }
     }
     unsigned todo = __ballot_sync(0xffffffffu, need);
     for (unsigned k = 0; todo; todo &= todo - 1, ++k) {
@@ -342,7 +497,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
         const double dx = EL(c, s_dep, 2, 0), dy = EL(c, s_dep, 2, 1);
         for (int i = lane; i < A; i += 32) {
             AREC(c, i, AR_LAST) = 0.0; AREC(c, i, AR_X) = dx; AREC(c, i, AR_Y) = dy; AREC(c, i, AR_DIST) = 0.0;
-            EL(c, a_nd, A, i) = 0.0; EL(c, a_node, A, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
+            EL(c, a_nd, A, i) = 0.0; ANODE(c, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
         }
         // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
         const u64 all = A >= 64 ? ~0ull : ((1ull << A) - 1);
@@ -362,7 +517,7 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
             }
             EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
             EL(c, am_depot, 1, 0) = 0; EL(c, am_touched, 1, 0) = 0; EL(c, am_watch, 1, 0) = 0;
-            EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF;
+            EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF; EL(c, x_last, 1, 0) = 0.0;
             EL(c, now, 1, 0) = 0.0; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = 0;
             EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = nflags;
             if (P.next_leader) P.next_leader[be] = leader;
@@ -425,7 +580,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
             for (int h = 0; h < OBS_AGENTS_PER_CHUNK; h += 5) {               // five agents per batch: 15 + 10 loads in flight
                 double2 xy[5], ld[5], ti[5]; double du[5]; unsigned kk[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); xy[q] = AREC2(c, i, 0); ld[q] = AREC2(c, i, 1); kk[q] = EL(c, a_node, A, i); }
+                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); xy[q] = AREC2(c, i, 0); ld[q] = AREC2(c, i, 1); kk[q] = ANODE(c, i); }
 #pragma unroll
                 for (int q = 0; q < 5; ++q) {                                   // one gather per agent that stands at a task, none otherwise
                     const bool at_task = kk[q] != DCM_NODE_DEPOT; const unsigned k = at_task ? kk[q] : 0u; const bool fe = at_task && tbit<TW>(feas, (int)k);
@@ -572,7 +727,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__
                                                          unsigned char* cursor /*[B,A] scratch*/, double* makespan) {
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
-    const TC c{E.S, (unsigned)b >> 5, (unsigned)b & 31u, E.S.A, E.S.T, E.S.MC, 100.0 /* :564 */, E.vel, E.max_time};
+    const TC c{E.S, (unsigned)b >> 5, (unsigned)b & 31u, (size_t)((unsigned)b >> 5) * E.S.tile_stride, E.S.A, E.S.T, E.S.MC, 100.0 /* :564 */, E.vel, E.max_time};
     double now = EL(c, now, 1, 0); unsigned flags = EL(c, flags, 1, 0); unsigned n_steps = EL(c, n_steps, 1, 0);
     unsigned char* pos = cursor + (size_t)b * c.A;
     for (int i = 0; i < c.A; ++i) pos[i] = 0;
@@ -649,7 +804,7 @@ __global__ void k_init(const __grid_constant__ EnvArgs E) {                   //
     if (b >= E.S.NT * 32) return;
     const TC c = make_tc(E, b);
     EL(c, flags, 1, 0) = ENV_DONE | ENV_ACCOUNTED; EL(c, leader, 1, 0) = -1;
-    EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF;
+    EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF;
 }
 
 // tiled SoA <-> per-env record of dcm_layout.h (export / import / checkpoint format)
@@ -670,7 +825,7 @@ __global__ void k_export(const __grid_constant__ EnvArgs E, const DcmLayout L, u
     }
     for (int i = 0; i < A; ++i) {
         ((double*)(r + L.o_alast))[i] = AREC(c, i, AR_LAST); ((double*)(r + L.o_and))[i] = EL(c, a_nd, A, i); ((double*)(r + L.o_adist))[i] = AREC(c, i, AR_DIST);
-        ((unsigned short*)(r + L.o_anab))[i] = EL(c, a_nab, A, i); (r + L.o_anode)[i] = EL(c, a_node, A, i);
+        ((unsigned short*)(r + L.o_anab))[i] = EL(c, a_nab, A, i); (r + L.o_anode)[i] = ANODE(c, i);
         const u64 bit = 1ull << i;
         (r + L.o_aflags)[i] = (unsigned char)(((st.route & bit) ? DCM_AF_ROUTE : 0u) | ((st.assigned & bit) ? DCM_AF_ASSIGNED : 0u) | ((st.returned & bit) ? DCM_AF_RETURNED : 0u) |
                                               ((st.member & bit) ? DCM_AF_MEMBER : 0u) | ((st.touched & bit) ? DCM_AF_TOUCHED : 0u) | ((st.watch & bit) ? DCM_AF_WATCH : 0u));
@@ -691,7 +846,7 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
 #pragma unroll
     for (int w = 0; w < TW; ++w) { st.feas[w] = st.fin[w] = st.ne[w] = st.open[w] = st.dirty[w] = 0; }
     st.route = st.assigned = st.returned = st.member = st.depot = st.touched = st.watch = 0;
-    st.xfin = st.xamin = st.xasg = CUDART_INF;
+    st.xfin = st.xamin = st.xasg = st.xret = CUDART_INF; st.xlast = 0.0;
     const unsigned char* r = src + (size_t)b * L.dyn_bytes;
     const int T = c.T, A = c.A, Tp = L.Tp;
     for (int j = 0; j < T; ++j) {
@@ -716,14 +871,15 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
         double x, y; node_xy(c, node, x, y);
         AREC(c, i, AR_LAST) = ((const double*)(r + L.o_alast))[i]; AREC(c, i, AR_X) = x; AREC(c, i, AR_Y) = y; AREC(c, i, AR_DIST) = ((const double*)(r + L.o_adist))[i];
         EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i];
-        EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; EL(c, a_node, A, i) = (unsigned char)node;
+        EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; ANODE(c, i) = (unsigned char)node;
         if (af & DCM_AF_ROUTE) st.route |= bit;
         if (af & DCM_AF_ASSIGNED) st.assigned |= bit;
         if (af & DCM_AF_RETURNED) st.returned |= bit;
         if (af & DCM_AF_MEMBER) st.member |= bit;
         if (af & DCM_AF_TOUCHED) st.touched |= bit;
         if ((af & DCM_AF_WATCH) && node != DCM_NODE_DEPOT) { const double ts = ((const double*)(r + L.o_tstart))[node]; st.watch |= bit; EL(c, a_ts, A, i) = ts; if (ts < st.xasg) st.xasg = ts; }
-        if ((af & DCM_AF_ROUTE) && node == DCM_NODE_DEPOT) st.depot |= bit;
+        if ((af & DCM_AF_ROUTE) && node == DCM_NODE_DEPOT) { st.depot |= bit; if (!(af & DCM_AF_RETURNED)) { const double la = ((const double*)(r + L.o_alast))[i]; if (la < st.xret) st.xret = la; } }
+        { const double la = ((const double*)(r + L.o_alast))[i]; if (la > st.xlast) st.xlast = la; }
     }
     st_state(c, st0, st);
     const DcmHdr h = *(const DcmHdr*)(r + L.o_hdr);
@@ -757,6 +913,7 @@ static int fail_cuda(cudaError_t e, const char* where) {
 
 struct dcm_env {
     int device; EnvArgs E; DcmLayout L; bool have_instances;
+    bool generic_step;               // DCM_STEP_GENERIC=1 at dcm_create: use the generic k_step even when the fast path applies (cross-check)
     unsigned char* arena; size_t arena_bytes;
     double* metrics;                 // [B,8]
     unsigned long long* d_counter;   // scratch for reductions
@@ -795,35 +952,37 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!v) return fail(DCM_ERR_NOMEM, "dcm_create: host allocation failed");
     memset(v, 0, sizeof *v);
     v->device = device;
+    { const char* gs = getenv("DCM_STEP_GENERIC"); v->generic_step = gs && gs[0] == '1'; }
     v->L = dcm_make_layout(A, T, M);
     DcmSoa& S = v->E.S;
     S.B = B; S.NT = (B + 31) / 32; S.A = A; S.T = T; S.M = M; S.MC = M; S.TW = T <= 64 ? 1 : (T <= 128 ? 2 : 4);
     v->E.W = 10.0; v->E.vel = 0.2; v->E.max_time = 100.0; v->E.seed = 0; v->E.first_gid = 0; v->E.cflags = flags;
     v->E.gen_max_duration = 5.0; v->E.gen_random_duration = 0;
-    // carve one arena; every array is [NT][K][32], 256-byte aligned
+    // carve one tile block; every array is [K][32 lanes] inside it, 256-byte aligned; the arena is NT such blocks
     const int NT = S.NT, TW = S.TW;
     size_t off = 0;
-    auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(NT, K, elem) + 255) / 256 * 256; return o; };
-    const int MCB = M <= 8 ? 8 : 16; S.MCB = MCB;
+    auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(K, elem) + 255) / 256 * 256; return o; };
+    const int MCB = M <= 8 ? 8 : 16; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
     const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32),
-                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_asg = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
+                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_asg = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
                  o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
                  o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
                  o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
                  o_am_touched = carve(1, 8), o_am_watch = carve(1, 8),
                  o_n_steps = carve(1, 4), o_episode = carve(1, 4), o_flags = carve(1, 4), o_instance = carve(1, 4), o_total = carve(1, 4), o_leader = carve(1, 4),
                  o_t_nab = carve(T, 2), o_a_nab = carve(A, 2),
-                 o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(A, 1), o_s_req = carve(T, 1);
-    v->arena_bytes = off;
-    cudaError_t e = cudaMalloc((void**)&v->arena, off);
-    if (e == cudaSuccess) e = cudaMemset(v->arena, 0, off);
+                 o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(1, S.ANB), o_s_req = carve(T, 1);
+    S.tile_stride = off;
+    v->arena_bytes = off * (size_t)NT;
+    cudaError_t e = cudaMalloc((void**)&v->arena, v->arena_bytes);
+    if (e == cudaSuccess) e = cudaMemset(v->arena, 0, v->arena_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->metrics, (size_t)B * 8 * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(v->metrics, 0, (size_t)B * 8 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_counter, sizeof(unsigned long long));
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
     S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec);
-    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_asg = (double*)(a + o_x_asg); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
+    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_asg = (double*)(a + o_x_asg); S.x_ret = (double*)(a + o_x_ret); S.x_last = (double*)(a + o_x_last); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
     S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
     S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_dirty = (u64*)(a + o_m_dirty);
     S.am_route = (u64*)(a + o_am_route); S.am_assigned = (u64*)(a + o_am_assigned); S.am_returned = (u64*)(a + o_am_returned); S.am_member = (u64*)(a + o_am_member);
@@ -960,7 +1119,12 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     StepArgs F; memset(&F, 0, sizeof F);
     F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
     F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action;
-    LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
+    if (v->E.S.MC <= 8 && !v->generic_step) {
+        const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
+#define LAUNCH_FAST(tw) do { if (small) k_step_fast<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step_fast<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
+        if (TW == 1) LAUNCH_FAST(1); else if (TW == 2) LAUNCH_FAST(2); else LAUNCH_FAST(4);
+#undef LAUNCH_FAST
+    } else LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
     CK(cudaGetLastError());
     v->launches++;
     // episode accounting (+ restart with DCM_FLAG_AUTO_RESET) of the envs that just finished; the injected leader of a

@@ -25,6 +25,8 @@ struct DcmSoa {
     int NT;       // tiles = ceil(B / 32)
     int A, T, M, MC, TW;
     int MCB;      // bytes reserved per (task, lane) for member ids: 8 (MC <= 8) or 16
+    int ANB;      // bytes reserved per env for the agents' node ids: 32 (A <= 32) or 64
+    size_t tile_stride;   // bytes of one tile's block; every pointer below addresses tile 0, tile t is at + t * tile_stride
     // ---- per task, lane-contiguous ----
     double* t_slot_arr;        // [T][32][MC]   arrival of member slot s (last visit, task_env.py:202-205)
     unsigned char* t_slot_mem; // [T][32][MCB]  member ids, ordered
@@ -43,7 +45,7 @@ struct DcmSoa {
     double* a_rec;             // [A][32][4]   {arrival_time[-1], x, y, travel_dist}   (one 32-byte sector)
     double* a_nd;              // [A]   next_decision
     double* a_ts;              // [A]   time_start of the feasible task the agent is a member of (valid with the watch bit)
-    unsigned char* a_node;     // [A]   route[-1] or DCM_NODE_DEPOT
+    unsigned char* a_node;     // [32 lanes][ANB]  route[-1] or DCM_NODE_DEPOT, per-env contiguous (ANB = 32 for A <= 32, else 64)
     unsigned short* a_nab;     // [A]   entries in abandoned_agent lists
     // ---- agent masks (rows: 1) ----
     unsigned long long* am_route;     // len(route) > 0
@@ -55,7 +57,8 @@ struct DcmSoa {
     unsigned long long* am_watch;     // member of a feasible task, not assigned yet: re-check `now >= time_start`
     // ---- per env (rows: 1) ----
     double* now;
-    double* x_fin; double* x_amin; double* x_asg;   // conservative lower bounds that let a step skip whole scans (dcm_thread.cuh St)
+    double* x_fin; double* x_amin; double* x_asg; double* x_ret;   // conservative lower bounds that let a step skip whole scans (dcm_thread.cuh St)
+    double* x_last;            // max arrival_time[-1] over the agents (check_finished clock jump, task_env.py:286/369)
     unsigned long long* pending;
     unsigned long long* group;
     unsigned* n_steps; unsigned* episode; unsigned* flags; unsigned* instance; unsigned* total;
@@ -68,6 +71,6 @@ struct DcmSoa {
 };
 
 #ifdef __cplusplus
-// bytes of one array with K rows per tile and `per_lane` bytes per (row, lane)
-static inline size_t dcm_soa_bytes(int NT, int K, size_t per_lane) { return (size_t)NT * K * 32 * per_lane; }
+// bytes of one tile's part of an array with K rows per tile and `per_lane` bytes per (row, lane)
+static inline size_t dcm_soa_bytes(int K, size_t per_lane) { return (size_t)K * 32 * per_lane; }
 #endif

@@ -25,21 +25,28 @@ constexpr unsigned ENV_DONE = 1u, ENV_FINISHED = 2u, ENV_STUCK = 4u, ENV_ERR_OVE
 struct TC {
     const DcmSoa& s;
     unsigned tile, l;          // b = tile*32 + l
+    size_t tb;                 // byte offset of the tile's block in the arena
     int A, T, MC;
     double W, vel, max_time;
 };
 
+// The arena is TILE-MAJOR: all arrays of one tile of 32 envs are contiguous (c.tb = tile * tile_stride bytes), so the
+// working set of a warp-step lies in one or two 2 MB pages instead of one page per array (TLB reach is 256 MB, the state
+// of 65,536 envs is ~400 MB).  DcmSoa pointers address tile 0.
+#define TB(c, arr) ((decltype(+(c).s.arr))((char*)(c).s.arr + (c).tb))
 // row-major arrays: element (row k) of this thread's env in an array with K rows per tile
-#define EL(c, arr, K, k) ((c).s.arr[(((c).tile * (unsigned)(K) + (unsigned)(k)) << 5) + (c).l])
+#define EL(c, arr, K, k) (TB(c, arr)[((unsigned)(k) << 5) + (c).l])
 // lane-contiguous arrays
-#define LANE_ROW(c, K, k) ((size_t)((((c).tile * (unsigned)(K) + (unsigned)(k)) << 5) + (c).l))
-#define SARR(c, j, sl) ((c).s.t_slot_arr[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
-#define SMEM(c, j, sl) ((c).s.t_slot_mem[LANE_ROW(c, (c).T, j) * (unsigned)(c).s.MCB + (unsigned)(sl)])   // member id of slot s
-#define TINFO(c, j, k) ((c).s.t_info[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
-#define AREC(c, i, f) ((c).s.a_rec[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // {x, y, last arrival, travel_dist}
+#define LANE_ROW(c, K, k) ((size_t)(((unsigned)(k) << 5) + (c).l))
+#define SARR(c, j, sl) (TB(c, t_slot_arr)[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
+#define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * (unsigned)(c).s.MCB + (unsigned)(sl)])   // member id of slot s
+#define TINFO(c, j, k) (TB(c, t_info)[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
+#define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // {x, y, last arrival, travel_dist}
 enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
-#define AREC2(c, i, h) (((double2*)(c).s.a_rec)[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
-#define TINFO2(c, j) (((double2*)(c).s.t_info)[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
+#define AREC2(c, i, h) (((double2*)TB(c, a_rec))[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
+#define TINFO2(c, j) (((double2*)TB(c, t_info))[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
+// route[-1] of the agents of one env, packed: one 32- or 64-byte line per env so that a step can hold them all in registers
+#define ANODE(c, i) (TB(c, a_node)[(size_t)(c).l * (unsigned)(c).s.ANB + (unsigned)(i)])
 
 // register-resident boolean state of one env
 template <int TW> struct St {
@@ -49,6 +56,8 @@ template <int TW> struct St {
     double xfin;    // <= time_finish of every feasible, unfinished task
     double xamin;   // <= earliest member arrival of every non-feasible task that has members
     double xasg;    // <= time_start awaited by every watched agent
+    double xret;    // <= arrival at the depot of every agent that went there and is not `returned` yet
+    double xlast;   // == max over agents of arrival_time[-1] (an agent's arrivals never decrease: it decides at or after its last one)
 };
 
 __device__ __forceinline__ int ctz64(u64 m) { return __ffsll((long long)m) - 1; }
@@ -96,6 +105,7 @@ template <int TW> __device__ __forceinline__ void ld_state(const TC& c, St<TW>& 
     st.member = EL(c, am_member, 1, 0); st.depot = EL(c, am_depot, 1, 0); st.touched = EL(c, am_touched, 1, 0);
     st.watch = EL(c, am_watch, 1, 0);
     st.xfin = EL(c, x_fin, 1, 0); st.xamin = EL(c, x_amin, 1, 0); st.xasg = EL(c, x_asg, 1, 0);
+    st.xret = EL(c, x_ret, 1, 0); st.xlast = EL(c, x_last, 1, 0);
 }
 template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St<TW>& o, const St<TW>& st) {
 #pragma unroll
@@ -116,6 +126,8 @@ template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St
     if (o.xfin != st.xfin) EL(c, x_fin, 1, 0) = st.xfin;
     if (o.xamin != st.xamin) EL(c, x_amin, 1, 0) = st.xamin;
     if (o.xasg != st.xasg) EL(c, x_asg, 1, 0) = st.xasg;
+    if (o.xret != st.xret) EL(c, x_ret, 1, 0) = st.xret;
+    if (o.xlast != st.xlast) EL(c, x_last, 1, 0) = st.xlast;
 }
 
 // Philox4x32-10 (Salmon et al. 2011)
@@ -156,7 +168,7 @@ __device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW> __device__ __forceinline__ void abandon(const TC& c, St<TW>& st, unsigned m, int j) {
     EL(c, a_nab, c.A, m) = (unsigned short)(EL(c, a_nab, c.A, m) + 1);
-    if (EL(c, a_node, c.A, m) == (unsigned)j) st.member &= ~(1ull << m);      // it no longer belongs to the task it stands at
+    if (ANODE(c, m) == (unsigned)j) st.member &= ~(1ull << m);      // it no longer belongs to the task it stands at
 }
 
 template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly) {
@@ -176,7 +188,7 @@ template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW
             if (newly) newly[j] = 1;
             for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
                 const unsigned m = SMEM(c, j, s);
-                if (EL(c, a_node, c.A, m) == (unsigned)j) st.touched |= 1ull << m;
+                if (ANODE(c, m) == (unsigned)j) st.touched |= 1ull << m;
             }
         } else {                                                              // :260-265 (iterates a copy: no skipping, Q4)
             const double thr = mx - c.W;
@@ -257,11 +269,11 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
     bool allf = true;
 #pragma unroll
     for (int w = 0; w < TW; ++w) allf = allf && st.feas[w] == all_tasks<TW>(T, w);
-    if (allf) {                                                               // :277-280 depot members
-        u64 ret = 0;
+    if (allf && now >= st.xret) {                                             // :277-280 depot members
+        u64 ret = 0; double nx = CUDART_INF;
         for_bits4<double>(st.depot & st.route & ~st.returned, 0, [&](int i) { return AREC(c, i, AR_LAST); },
-                          [&](u64 bit, int, double last) { if (now >= last) ret |= bit; });
-        st.returned |= ret;
+                          [&](u64 bit, int, double last) { if (now >= last) ret |= bit; else nx = last < nx ? last : nx; });
+        st.returned |= ret; st.xret = nx;
     }
 }
 
@@ -284,7 +296,7 @@ template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St
         const u64 b0 = m & (0 - m); m ^= b0; const u64 b1 = m & (0 - m); m ^= b1;
         const u64 b2 = m & (0 - m); m ^= b2; const u64 b3 = m & (0 - m); m ^= b3;
         const int i0 = ctz64(b0), i1 = b1 ? ctz64(b1) : i0, i2 = b2 ? ctz64(b2) : i0, i3 = b3 ? ctz64(b3) : i0;
-        const unsigned n0 = EL(c, a_node, A, i0), n1 = EL(c, a_node, A, i1), n2 = EL(c, a_node, A, i2), n3 = EL(c, a_node, A, i3);
+        const unsigned n0 = ANODE(c, i0), n1 = ANODE(c, i1), n2 = ANODE(c, i2), n3 = ANODE(c, i3);
         const unsigned k0 = n0 == DCM_NODE_DEPOT ? 0u : n0, k1 = n1 == DCM_NODE_DEPOT ? 0u : n1, k2 = n2 == DCM_NODE_DEPOT ? 0u : n2, k3 = n3 == DCM_NODE_DEPOT ? 0u : n3;
         const double2 t0 = TINFO2(c, k0), t1 = TINFO2(c, k1), t2 = TINFO2(c, k2), t3 = TINFO2(c, k3);
         const double l0 = AREC(c, i0, AR_LAST), l1 = AREC(c, i1, AR_LAST), l2 = AREC(c, i2, AR_LAST), l3 = AREC(c, i3, AR_LAST);
@@ -377,9 +389,10 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     const double arrival = now + tt;                                          // :318
     AREC2(c, i, 1) = make_double2(arrival, ld.y + d);                         // :317-318
     AREC2(c, i, 0) = make_double2(tx, ty);                                    // :320
-    EL(c, a_node, A, i) = (unsigned char)(to_task ? (unsigned)j : DCM_NODE_DEPOT);   // :314
+    ANODE(c, i) = (unsigned char)(to_task ? (unsigned)j : DCM_NODE_DEPOT);   // :314
     st.route |= bit; st.touched |= bit;
-    if (!to_task) { st.depot |= bit; st.member &= ~bit; return; }
+    st.xlast = arrival > st.xlast ? arrival : st.xlast;
+    if (!to_task) { st.depot |= bit; st.member &= ~bit; st.xret = arrival < st.xret ? arrival : st.xret; return; }
     st.depot &= ~bit;
     int pos = -1;                                                             // :321-322
     for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
@@ -536,7 +549,7 @@ template <int TW> __device__ __forceinline__ void obs_agent_row(const TC& c, con
     double travel_t = 0.0, wait = 0.0, remain = 0.0;
     const double ax = AREC(c, i, AR_X), ay = AREC(c, i, AR_Y);
     if ((st.route & bit) && !(st.depot & bit)) {                              // :168
-        const unsigned k = EL(c, a_node, c.A, i);
+        const unsigned k = ANODE(c, i);
         const double arr = AREC(c, i, AR_LAST);
         const bool feas = tbit<TW>(st.feas, (int)k);
         const double ts = feas ? TINFO(c, k, 0) : 0.0;                        // time_start is 0 until the task is feasible (Q6)
