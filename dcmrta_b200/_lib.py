@@ -62,6 +62,7 @@ SIGNATURES = {
     "dcm_total_steps": (i32, [vp, C.POINTER(u64)]),
     "dcm_algorithmic_bytes_per_step": (sz, [vp]),
     "dcm_launch_count": (u64, [vp]),
+    "dcm_debug_pass_trace": (i32, [vp, vp, sz]),
     "dcm_last_error": (C.c_char_p, []),
     "dcm_version": (C.c_char_p, []),
 }

@@ -48,7 +48,7 @@ struct StepArgs {
 };
 
 struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask;
-                 int fresh_only; /* only envs that k_episode restarted in this call (ENV_FRESH) */ };
+                 int skip_ended; /* leave out the envs whose episode ended in this step: the episode kernel, running beside k_obs, writes theirs */ };
 
 enum GranOp { OP_NEXT_DECISION = 1, OP_UNIQUE_GROUP, OP_SET_CLOCK, OP_GET_CLOCK, OP_TASK_UPDATE, OP_AGENT_UPDATE, OP_APPLY_MEMBERS,
               OP_CHECK_FINISHED, OP_COMPUTE_METRICS, OP_ENV_FLAGS };
@@ -82,18 +82,6 @@ __device__ __noinline__ void t_generate(const TC& c, u64 seed, u64 gid, unsigned
     EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w);                // :67
 }
 
-__device__ __forceinline__ void w_generate(const TC& c, unsigned lane, u64 seed, u64 gid, unsigned instance, double max_duration, int random_duration) {
-    const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), g0 = (unsigned)gid, g1 = (unsigned)(gid >> 32);
-    for (int j = lane; j < c.T; j += 32) {                                    // same streams as t_generate, lanes over tasks
-        const uint4 a = philox(g0, g1, instance, 0x80000000u + 2u * j, k0, k1);
-        const uint4 b = philox(g0, g1, instance, 0x80000001u + 2u * j, k0, k1);
-        EL(c, s_tx, c.T, j) = u01(a.x, a.y); EL(c, s_ty, c.T, j) = u01(a.z, a.w);
-        EL(c, s_req, c.T, j) = (unsigned char)(1 + pick(b.x, c.s.M));
-        EL(c, s_dur, c.T, j) = random_duration ? u01(b.y, b.z) * max_duration : max_duration;
-    }
-    if (lane == 0) { const uint4 a = philox(g0, g1, instance, 0xFFFFFFFFu, k0, k1); EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w); }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // k_step: one leader decision per env
 // ---------------------------------------------------------------------------------------------------------------
@@ -112,10 +100,21 @@ __device__ __forceinline__ int choose_leader(const TC& c, const Rng& rng, unsign
     return kth_bit(group, pick(blk.y, n));                                    // worker.py:54
 }
 
+// every mask and bound of the env (full-warp 8-byte stores; cheaper than keeping a copy of the loaded state to diff against)
+template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, const St<TW>& st) {
+#pragma unroll
+    for (int w = 0; w < TW; ++w) {
+        EL(c, m_feas, TW, w) = st.feas[w]; EL(c, m_fin, TW, w) = st.fin[w]; EL(c, m_ne, TW, w) = st.ne[w];
+        EL(c, m_open, TW, w) = st.open[w]; EL(c, m_dirty, TW, w) = st.dirty[w];
+    }
+    EL(c, am_route, 1, 0) = st.route; EL(c, am_assigned, 1, 0) = st.assigned; EL(c, am_returned, 1, 0) = st.returned;
+    EL(c, am_member, 1, 0) = st.member; EL(c, am_depot, 1, 0) = st.depot; EL(c, am_touched, 1, 0) = st.touched; EL(c, am_watch, 1, 0) = st.watch;
+    EL(c, x_fin, 1, 0) = st.xfin; EL(c, x_amin, 1, 0) = st.xamin; EL(c, x_asg, 1, 0) = st.xasg; EL(c, x_ret, 1, 0) = st.xret; EL(c, x_last, 1, 0) = st.xlast;
+}
+
+// one leader decision of env b; returns the env's status bits after it
 template <int TW>
-__global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
-    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (b >= E.S.B) return;
+__device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b) {
     const TC c = make_tc(E, b);
     unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
     if (flags & ENV_DONE) {                                                   // finished earlier and not restarted: untouched
@@ -123,9 +122,9 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ E
         if (F.reward) F.reward[b] = 0.f;
         if (F.done) F.done[b] = 1;
         if (F.used_action) F.used_action[b] = -1;
-        return;
+        return flags;
     }
-    St<TW> st, st0; ld_state(c, st); st0 = st;
+    St<TW> st; ld_state(c, st);
     double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
     unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0);
     int leader = EL(c, leader, 1, 0);
@@ -192,25 +191,22 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const __grid_constant__ E
     if (F.done) F.done[b] = (flags & ENV_DONE) ? 1 : 0;
     if (F.used_action) F.used_action[b] = action_out;
     EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
-    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags;
-    st_state(c, st0, st);
+    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags; EL(c, ended, 1, 0) = (flags & ENV_DONE) ? 1 : 0;
+    if (ok) st_state_all(c, st);
+    return flags;
+}
+
+template <int TW>
+__global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
+    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (b >= E.S.B) return;
+    step_env<TW>(E, F, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_step_fast: the same decision as k_step with the chosen task, the node ids and the per-env masks held in registers
 // (dcm_fast.cuh).  Used whenever the handle has at most 8 member slots per task; k_step stays the generic version.
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, const St<TW>& st) {
-#pragma unroll
-    for (int w = 0; w < TW; ++w) {
-        EL(c, m_feas, TW, w) = st.feas[w]; EL(c, m_fin, TW, w) = st.fin[w]; EL(c, m_ne, TW, w) = st.ne[w];
-        EL(c, m_open, TW, w) = st.open[w]; EL(c, m_dirty, TW, w) = st.dirty[w];
-    }
-    EL(c, am_route, 1, 0) = st.route; EL(c, am_assigned, 1, 0) = st.assigned; EL(c, am_returned, 1, 0) = st.returned;
-    EL(c, am_member, 1, 0) = st.member; EL(c, am_depot, 1, 0) = st.depot; EL(c, am_touched, 1, 0) = st.touched; EL(c, am_watch, 1, 0) = st.watch;
-    EL(c, x_fin, 1, 0) = st.xfin; EL(c, x_amin, 1, 0) = st.xamin; EL(c, x_asg, 1, 0) = st.xasg; EL(c, x_ret, 1, 0) = st.xret; EL(c, x_last, 1, 0) = st.xlast;
-}
-
 template <int TW, int NW>
 __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
@@ -346,7 +342,7 @@ __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, 
     if (F.done) F.done[b] = (flags & ENV_DONE) ? 1 : 0;
     if (F.used_action) F.used_action[b] = action_out;
     EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
-    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags;
+    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags; EL(c, ended, 1, 0) = (flags & ENV_DONE) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -357,7 +353,8 @@ __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, 
 //   mode 1: dcm_reset (every env, or those selected by `which`)
 // ---------------------------------------------------------------------------------------------------------------
 #define EPI_WARPS 4
-struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int* next_leader; double* metrics; };
+struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int* next_leader; double* metrics;
+                 ObsArgs obs; int write_obs; /* mode 0 + auto-reset: write the restarted env's observation (k_obs runs beside this kernel and skips it) */ };
 
 __device__ __forceinline__ double wmax(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; } return v; }
 __device__ __forceinline__ double wmin(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; } return v; }
@@ -455,6 +452,216 @@ __device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& s
     return now;
 }
 
+// numpy pairwise add.reduce of n <= 128 values in shared memory by 8 lanes (lane8 = 0..7 of the group); same order of
+// additions as np_sum_le128: eight strided accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail
+__device__ __forceinline__ double g_np_sum_le128(const double* v, int base, int n, unsigned lane8, unsigned gmask) {
+    if (n < 8) { double r = 0.0; for (int i = 0; i < n; ++i) r += v[base + i]; return r; }
+    double r = v[base + lane8];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) r += v[base + i + lane8];
+    const double p1 = r + __shfl_xor_sync(gmask, r, 1);                       // lanes 0,2,4,6 hold r0+r1, r2+r3, ...
+    const double p2 = p1 + __shfl_xor_sync(gmask, p1, 2);                     // lanes 0,4 hold (r0+r1)+(r2+r3), ...
+    double res = p2 + __shfl_xor_sync(gmask, p2, 4);                          // lane 0: the eight-way combination in numpy's order
+    for (; i < n; ++i) res += v[base + i];
+    return res;                                                               // valid in lane8 == 0
+}
+__device__ __forceinline__ double g_np_sum(const double* v, int n, unsigned lane8, unsigned gmask) {   // n <= 256
+    if (n <= 128) return g_np_sum_le128(v, 0, n, lane8, gmask);
+    int n2 = n / 2; n2 -= n2 % 8;
+    return g_np_sum_le128(v, 0, n2, lane8, gmask) + g_np_sum_le128(v, n2, n - n2, lane8, gmask);
+}
+
+// w_episode_metrics with every load of a 32-task batch issued in one round (and the next batch's before this one is
+// consumed), for handles with at most 8 member slots; the four final sums run on four groups of 8 lanes.  Same arithmetic.
+template <int TW>
+__device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, const EpiScratch& S) {
+    const int T = c.T, A = c.A, MC = c.MC;
+    struct TL { int n; bool feas; u64 ids; double a[8]; unsigned nab; double ts; };
+    auto load_task = [&](int j, TL& L) {
+        L.n = 0; L.feas = false; L.ids = 0; L.nab = 0; L.ts = 0.0;
+        const bool in = j < T; const int jj = in ? j : 0;
+        const bool ne = in && tbit<TW>(st.ne, jj); L.feas = in && tbit<TW>(st.feas, jj);
+        if (ne) { L.n = EL(c, t_nmem, T, jj); L.ids = *(const u64*)&SMEM(c, jj, 0); }
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) L.a[s2] = (ne && s2 < MC) ? SARR(c, jj, s2) : 0.0;
+        if (in) L.nab = EL(c, t_nab, T, jj);
+        if (L.feas) L.ts = TINFO(c, jj, 0);
+    };
+    // agents (lane, lane + 32): issue these loads first as well
+    double a_nd_v[2], a_last[2], a_dist[2]; int a_nab_v[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = lane + 32 * r; const bool in = i < A; const int ii = in ? i : 0;
+        a_nd_v[r] = in ? EL(c, a_nd, A, ii) : CUDART_NAN; const double2 ld = AREC2(c, ii, 1);
+        a_last[r] = in ? ld.x : 0.0; a_dist[r] = ld.y; a_nab_v[r] = in ? (int)EL(c, a_nab, A, ii) : 0;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+    TL cur, nxt;
+    load_task((int)lane, cur);
+    for (int j0 = 0; j0 < T; j0 += 32) {
+        if (j0 + 32 < T) load_task(j0 + 32 + (int)lane, nxt);
+        const int j = j0 + (int)lane; const int n = cur.n; const bool feas = cur.feas;
+        double mx = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) if (s2 < n) { S.sa[lane * S.MC + s2] = cur.a[s2]; mx = (s2 == 0 || cur.a[s2] > mx) ? cur.a[s2] : mx; S.sm[lane * S.MC + s2] = (unsigned char)((cur.ids >> (8 * s2)) & 0xffu); }
+        S.sn[lane] = (unsigned char)(n | (feas ? 0x80 : 0)); S.smx[lane] = mx;
+        if (j < T) {                                                          // task['sum_waiting_time'] :349-357
+            const double w_ab = (double)cur.nab * c.W;
+            double v = w_ab;
+            if (n) {
+                double acc = 0.0;
+#pragma unroll
+                for (int s2 = 0; s2 < 8; ++s2) if (s2 < n) acc += feas ? (mx - cur.a[s2]) : (now - cur.a[s2]);
+                v = acc + w_ab;
+            }
+            S.s_task[j] = v;
+            S.s_ts[j] = feas ? cur.ts : 0.0;
+        }
+        __syncwarp();
+        const int nt = T - j0 < 32 ? T - j0 : 32;
+        for (int t = 0; t < nt; ++t) {                                        // reference order: tasks ascending, members in list order (:358-362)
+            const int cnt = S.sn[t] & 0x7f;
+            if (!cnt) continue;
+            const bool ft = S.sn[t] & 0x80; const double mxt = S.smx[t];
+            for (int s2 = 0; s2 < cnt; ++s2) {
+                const unsigned m = S.sm[t * S.MC + s2]; const double a = S.sa[t * S.MC + s2];
+                double add;
+                if (ft) add = mxt - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }     // :360 / :362
+                if (lane == (m & 31u)) { if (m < 32u) acc0 += add; else acc1 += add; }
+            }
+        }
+        __syncwarp();
+        cur = nxt;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {                                             // + W per abandoned_agent entry (:363-364; added last, ~1e-16 rel.)
+        const int i = lane + 32 * r;
+        if (i < A) {
+            double acc = r ? acc1 : acc0;
+            for (int k = 0; k < a_nab_v[r]; ++k) acc += c.W;
+            S.s_agent[i] = acc; S.s_dist[i] = a_dist[r];
+        }
+    }
+    // :422 check_finished side effect on the clock
+    double mn = CUDART_INF, la = 0.0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { if (a_nd_v[r] < mn) mn = a_nd_v[r]; la = a_last[r] > la ? a_last[r] : la; }
+    mn = wmin(mn); la = wmax(la);
+    if (mn == CUDART_INF) now = la;
+    int nfin = 0;
+#pragma unroll
+    for (int w = 0; w < TW; ++w) nfin += __popcll(st.fin[w]);
+    __syncwarp();
+    {                                                                         // four sums on four groups of 8 lanes
+        const unsigned grp = lane >> 3, lane8 = lane & 7, gmask = 0xffu << (8 * grp);
+        double r;
+        if (grp == 0) r = g_np_sum(S.s_ts, T, lane8, gmask);                  // :105 nanmean(time_start)
+        else if (grp == 1) r = g_np_sum(S.s_agent, A, lane8, gmask);          // :106
+        else if (grp == 2) r = g_np_sum(S.s_dist, A, lane8, gmask);           // :107
+        else r = g_np_sum(S.s_task, T, lane8, gmask);                         // :108
+        if (lane8 == 0) {
+            if (grp == 0) { out[3] = r / (double)T; out[0] = -now; out[1] = (double)nfin / (double)T; out[2] = now; out[7] = (double)n_steps; }   // :424, worker.py:103-104
+            else if (grp == 1) out[4] = r / (double)A;
+            else if (grp == 2) out[5] = r;
+            else out[6] = r / (double)T;
+        }
+    }
+    __syncwarp();
+    return now;
+}
+
+// episode accounting (mode 0) and restart of ONE env by a whole warp.  With O (fused pass, auto-reset) the observation of
+// the restarted env is written from registers: every agent stands at the depot without a route, so the agent rows are zero,
+// task row j is [requirement, requirement, duration, task - depot] and only the depot is masked (task_env.py:165-200).
+template <int TW>
+__device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, int be, unsigned lane, const EpiScratch& scratch, const ObsArgs* O = nullptr) {
+    const int A = E.S.A, T = E.S.T;
+    const TC c = make_tc(E, be);
+    St<TW> st; ld_state(c, st);
+    unsigned flags = EL(c, flags, 1, 0), episode = EL(c, episode, 1, 0);
+    unsigned inst = EL(c, instance, 1, 0);
+    const u64 gid = E.first_gid + (u64)be;
+    const bool regen = P.mode == 0 && (E.cflags & DCM_FLAG_REGENERATE);
+    if (P.mode == 0) {
+        const double now0 = EL(c, now, 1, 0); const unsigned ns = EL(c, n_steps, 1, 0);
+        const double now = E.S.MC <= 8 ? w_episode_metrics8(c, st, lane, now0, ns, P.metrics + (size_t)be * 8, scratch)
+                                       : w_episode_metrics(c, st, lane, now0, ns, P.metrics + (size_t)be * 8, scratch);
+        ++episode; flags |= ENV_ACCOUNTED;
+        if (!(E.cflags & DCM_FLAG_AUTO_RESET)) {
+            if (lane == 0) { EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, episode, 1, 0) = episode; }
+            __syncwarp();
+            return;
+        }
+        if (regen) { ++inst; if (lane == 0) EL(c, instance, 1, 0) = inst; }
+    }
+    const bool alive = 0.0 < E.max_time;
+    const bool obs = O && alive;
+    // ---- the instance: generated (same streams as t_generate) or read back; everything below uses registers only
+    const unsigned k0 = (unsigned)E.seed, k1 = (unsigned)(E.seed >> 32), g0 = (unsigned)gid, g1 = (unsigned)(gid >> 32);
+    double dx, dy;
+    if (regen) { const uint4 a = philox(g0, g1, inst, 0xFFFFFFFFu, k0, k1); dx = u01(a.x, a.y); dy = u01(a.z, a.w); if (lane == 0) { EL(c, s_dep, 2, 0) = dx; EL(c, s_dep, 2, 1) = dy; } }
+    else { dx = EL(c, s_dep, 2, 0); dy = EL(c, s_dep, 2, 1); }
+    // ---- clear_decisions (task_env.py:129-140), lanes over tasks / agents
+    for (int j = lane; j < T; j += 32) {
+        double tx, ty, du; unsigned rq;
+        if (regen) {
+            const uint4 a = philox(g0, g1, inst, 0x80000000u + 2u * j, k0, k1);
+            const uint4 b2 = philox(g0, g1, inst, 0x80000001u + 2u * j, k0, k1);
+            tx = u01(a.x, a.y); ty = u01(a.z, a.w);                            // task_env.py:69
+            rq = 1u + (unsigned)pick(b2.x, E.S.M);                            // :71
+            du = E.gen_random_duration ? u01(b2.y, b2.z) * E.gen_max_duration : E.gen_max_duration;   // :70
+            EL(c, s_tx, T, j) = tx; EL(c, s_ty, T, j) = ty; EL(c, s_req, T, j) = (unsigned char)rq; EL(c, s_dur, T, j) = du;
+        } else { rq = EL(c, s_req, T, j); if (obs) { tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j); du = EL(c, s_dur, T, j); } }
+        EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)rq; EL(c, t_nab, T, j) = 0;
+        if (obs) {
+            if (O->task_obs) {
+                float* r = O->task_obs + ((size_t)be * (T + 1) + j + 1) * 5;  // :185-186
+                r[0] = (float)(int)rq; r[1] = (float)rq; r[2] = __double2float_rn(du); r[3] = __double2float_rn(tx - dx); r[4] = __double2float_rn(ty - dy);
+            }
+            if (O->mask) O->mask[(size_t)be * (T + 1) + j + 1] = 0;           // :199 every task is open
+        }
+    }
+    if (obs) {
+        if (O->task_obs && lane < 5) O->task_obs[(size_t)be * (T + 1) * 5 + lane] = 0.f;       // :188 depot row (depot - depot)
+        if (O->mask && lane == 0) O->mask[(size_t)be * (T + 1)] = 1;                            // worker.py:58-61
+        if (O->agent_obs) for (int k = lane; k < 6 * A; k += 32) O->agent_obs[(size_t)be * 6 * A + k] = 0.f;   // :165-180 nobody has a route
+    }
+    for (int i = lane; i < A; i += 32) {
+        AREC2(c, i, 0) = make_double2(dx, dy); AREC2(c, i, 1) = make_double2(0.0, 0.0);
+        EL(c, a_nd, A, i) = 0.0; ANODE(c, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
+    }
+    // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
+    const u64 all = A >= 64 ? ~0ull : ((1ull << A) - 1);
+    unsigned nflags = P.mode == 0 ? ENV_FRESH : 0u; u64 pending = all, group = all; int leader;
+    if (!alive) { nflags = ENV_DONE | ENV_ACCOUNTED; pending = 0; group = 0; leader = -1; }
+    else {
+        const int inj = P.leader_in ? P.leader_in[be] : -1;
+        if (inj >= 0) { if (inj < A) leader = inj; else { nflags |= ENV_ERR_LEADER; leader = 0; } }
+        else if (A == 1) leader = 0;
+        else { const Rng rng{E.seed, gid}; leader = kth_bit(all, pick(draw_block(rng, episode, 0, 0).y, A)); }   // worker.py:54
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int w = 0; w < TW; ++w) {
+            EL(c, m_feas, TW, w) = 0; EL(c, m_fin, TW, w) = 0; EL(c, m_ne, TW, w) = 0; EL(c, m_dirty, TW, w) = 0;
+            EL(c, m_open, TW, w) = all_tasks<TW>(T, w);
+        }
+        EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
+        EL(c, am_depot, 1, 0) = 0; EL(c, am_touched, 1, 0) = 0; EL(c, am_watch, 1, 0) = 0;
+        EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF; EL(c, x_last, 1, 0) = 0.0;
+        EL(c, now, 1, 0) = 0.0; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = 0;
+        EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = nflags;
+        if (P.next_leader) P.next_leader[be] = leader;
+    }
+    __syncwarp();
+}
+
+// out-of-line copy for k_pass: the rare episode path must not raise the register pressure of the step / observe loop
+template <int TW>
+__device__ __noinline__ void episode_env_cold(const EnvArgs& E, const EpiArgs& P, int be, unsigned lane, unsigned char* smem, const ObsArgs* O) {
+    episode_env<TW>(E, P, be, lane, epi_scratch(smem, E.S.A, E.S.T, E.S.MC), O);
+}
+
 // one block per tile; the block's warps share the tile's envs that need work (warp w takes the w-th, (w+4)-th, ... of them)
 template <int TW>
 __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
@@ -470,59 +677,10 @@ __global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constan
         else { const TC cb = make_tc(E, b); const unsigned f = EL(cb, flags, 1, 0); need = (f & ENV_DONE) && !(f & ENV_ACCOUNTED); }
     }
     unsigned todo = __ballot_sync(0xffffffffu, need);
+    const unsigned nwarps = blockDim.x >> 5;
     for (unsigned k = 0; todo; todo &= todo - 1, ++k) {
-        if ((k % EPI_WARPS) != warp) continue;
-        const int be = (int)(tile * 32 + (__ffs(todo) - 1));
-        const TC c = make_tc(E, be);
-        St<TW> st; ld_state(c, st);
-        unsigned flags = EL(c, flags, 1, 0), episode = EL(c, episode, 1, 0);
-        const u64 gid = E.first_gid + (u64)be;
-        if (P.mode == 0) {
-            const double now = w_episode_metrics(c, st, lane, EL(c, now, 1, 0), EL(c, n_steps, 1, 0), P.metrics + (size_t)be * 8, scratch);
-            ++episode; flags |= ENV_ACCOUNTED;
-            if (!(E.cflags & DCM_FLAG_AUTO_RESET)) {
-                if (lane == 0) { EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, episode, 1, 0) = episode; }
-                continue;
-            }
-            if (E.cflags & DCM_FLAG_REGENERATE) {
-                const unsigned inst = EL(c, instance, 1, 0) + 1;
-                __syncwarp();
-                if (lane == 0) EL(c, instance, 1, 0) = inst;
-                w_generate(c, lane, E.seed, gid, inst, E.gen_max_duration, E.gen_random_duration);
-                __syncwarp();
-            }
-        }
-        // ---- clear_decisions (task_env.py:129-140), lanes over tasks / agents
-        for (int j = lane; j < T; j += 32) { EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)EL(c, s_req, T, j); EL(c, t_nab, T, j) = 0; }
-        const double dx = EL(c, s_dep, 2, 0), dy = EL(c, s_dep, 2, 1);
-        for (int i = lane; i < A; i += 32) {
-            AREC(c, i, AR_LAST) = 0.0; AREC(c, i, AR_X) = dx; AREC(c, i, AR_Y) = dy; AREC(c, i, AR_DIST) = 0.0;
-            EL(c, a_nd, A, i) = 0.0; ANODE(c, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
-        }
-        // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
-        const u64 all = A >= 64 ? ~0ull : ((1ull << A) - 1);
-        unsigned nflags = P.mode == 0 ? ENV_FRESH : 0u; u64 pending = all, group = all; int leader;
-        if (!(0.0 < E.max_time)) { nflags = ENV_DONE | ENV_ACCOUNTED; pending = 0; group = 0; leader = -1; }
-        else {
-            const int inj = P.leader_in ? P.leader_in[be] : -1;
-            if (inj >= 0) { if (inj < A) leader = inj; else { nflags |= ENV_ERR_LEADER; leader = 0; } }
-            else if (A == 1) leader = 0;
-            else { const Rng rng{E.seed, gid}; leader = kth_bit(all, pick(draw_block(rng, episode, 0, 0).y, A)); }   // worker.py:54
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int w = 0; w < TW; ++w) {
-                EL(c, m_feas, TW, w) = 0; EL(c, m_fin, TW, w) = 0; EL(c, m_ne, TW, w) = 0; EL(c, m_dirty, TW, w) = 0;
-                EL(c, m_open, TW, w) = all_tasks<TW>(T, w);
-            }
-            EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
-            EL(c, am_depot, 1, 0) = 0; EL(c, am_touched, 1, 0) = 0; EL(c, am_watch, 1, 0) = 0;
-            EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF; EL(c, x_last, 1, 0) = 0.0;
-            EL(c, now, 1, 0) = 0.0; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = 0;
-            EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = nflags;
-            if (P.next_leader) P.next_leader[be] = leader;
-        }
-        __syncwarp();
+        if ((k % nwarps) != warp) continue;
+        episode_env<TW>(E, P, (int)(tile * 32 + (__ffs(todo) - 1)), lane, scratch, P.write_obs ? &P.obs : nullptr);
     }
 }
 
@@ -545,27 +703,23 @@ __device__ __forceinline__ void flush_rows(const float* tile, float* g0, unsigne
     }
 }
 
+// one (tile, chunk) unit by one warp; `tile` is the warp's staging area of 32 * OBS_PITCH floats
 template <int TW>
-__global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O) {
-    __shared__ float smem[(OBS_THREADS / 32) * 32 * OBS_PITCH];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned tile_id = blockIdx.x * (OBS_THREADS / 32) + warp;
+__device__ __forceinline__ void obs_unit(const EnvArgs& E, const ObsArgs& O, unsigned tile_id, int chunk, unsigned lane, float* tile, unsigned skip = 0) {
     const int b = (int)(tile_id * 32 + lane);
     const int B = E.S.B, A = E.S.A, T = E.S.T;
     if (tile_id * 32 >= (unsigned)B) return;
-    float* tile = smem + warp * 32 * OBS_PITCH;
     float* mine = tile + lane * OBS_PITCH;
     const TC c = make_tc(E, b < B ? b : B - 1);
     int leader = -1;
     if (b < B) leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0);
-    if (O.fresh_only && b < B && !(EL(c, flags, 1, 0) & ENV_FRESH)) leader = -1;
-    const bool ok = leader >= 0 && leader < A;
+    if (O.skip_ended && b < B && EL(c, ended, 1, 0)) leader = -1;
+    const bool ok = leader >= 0 && leader < A && !((skip >> lane) & 1u);      // skip: envs whose observation is built by the warp that restarts them
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
     double Lx = 0, Ly = 0;
     if (ok) { const double2 p = AREC2(c, leader, 0); Lx = p.x; Ly = p.y; }
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK;
-    const int chunk = blockIdx.y;
     if (chunk < NA) {                                                         // ---- agent rows (:165-180)
         if (!O.agent_obs) return;
         const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
@@ -650,6 +804,101 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
         const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
         const unsigned char* src = (const unsigned char*)(tile + 60) + lane; unsigned char* dst = O.mask + (size_t)tile_id * 32 * (T + 1) + r0 + lane;
         for (int e = 0; e < ne; ++e, src += 4 * OBS_PITCH, dst += T + 1) if (((valid >> e) & 1u) && (int)lane < nr) dst[0] = src[0];
+    }
+}
+
+template <int TW>
+__global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O) {
+    __shared__ float smem[(OBS_THREADS / 32) * 32 * OBS_PITCH];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    obs_unit<TW>(E, O, blockIdx.x * (OBS_THREADS / 32) + warp, (int)blockIdx.y, lane, smem + warp * 32 * OBS_PITCH);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_pass: the whole pass (one leader decision of every env + the observation of the next leader) in ONE launch.
+// Persistent warps take work units from a ticket counter:
+//   units [0, NT)            step   : one tile of 32 envs, thread per env (step_env); the tile id and the mask of the envs
+//                                     whose episode just ended are published in the TILE QUEUE.
+//   units [NT, NT + NT*CH)   observe: unit u serves chunk k = (u - NT) % CH of the (u - NT) / CH-th tile IN COMPLETION ORDER,
+//                                     as soon as that entry is published, for the envs that are not in the entry's mask (obs_unit).
+//   episode accounting + restart of an env whose episode ended, and its observation, by a whole warp (episode_env): the
+//   first such env of a tile by the step warp itself right after it published the tile, the (k+1)-th by the tile's k-th
+//   observe unit -- the long, rare episode path runs beside everything else instead of after it.
+// The bandwidth-bound observation work of the tiles that are done overlaps the latency-bound tail of the step work (the
+// step is less than one wave: 14 warps per SM at 65,536 envs), and nothing waits on a kernel boundary.
+// Forward progress: every step ticket is taken before any observe ticket (one monotonic counter) and a warp that holds a
+// step unit never waits, so every entry an observe unit spins on is being produced by a running warp.
+// Entries carry the launch epoch (the queue is never cleared); the last warp to leave resets the counters.
+// ---------------------------------------------------------------------------------------------------------------
+struct PassCtl { unsigned ticket, tail, warps_done, pad; };
+#define PASS_WARPS 2
+
+__host__ __device__ inline size_t pass_warp_smem(int A, int T, int MC) {
+    const size_t o = (size_t)32 * OBS_PITCH * sizeof(float), e = epi_scratch_bytes(A, T, MC);
+    return ((o > e ? o : e) + 15) / 16 * 16;
+}
+__device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *(const volatile unsigned*)p; }
+__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+
+template <int TW>
+__global__ void __launch_bounds__(32 * PASS_WARPS, 7) k_pass(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F, const __grid_constant__ EpiArgs P,
+                                                             const __grid_constant__ ObsArgs O, PassCtl* ctl, unsigned long long* queue, unsigned* qmask,
+                                                             unsigned epoch, int CH, unsigned long long* trace) {
+    extern __shared__ __align__(16) unsigned char pass_smem[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B = E.S.B, A = E.S.A, T = E.S.T;
+    const unsigned NT = (unsigned)E.S.NT, total = NT + NT * (unsigned)CH;
+    unsigned char* mysmem = pass_smem + warp * pass_warp_smem(A, T, E.S.MC);
+    for (;;) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(&ctl->ticket, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total) break;
+        unsigned long long t_take = 0;
+        if (trace && lane == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_take)); trace[4 * (size_t)u] = t_take; }
+        if (u < NT) {                                                         // ---- step unit
+            const int b = (int)(u * 32 + lane);
+            unsigned flags = 0;
+            if (b < B) flags = step_env<TW>(E, F, b);
+            const bool need = b < B && (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
+            unsigned todo = __ballot_sync(0xffffffffu, need);
+            if (CH == 0) {                                                    // nobody observes: the step warp does the episode work itself
+                for (; todo; todo &= todo - 1) episode_env_cold<TW>(E, P, (int)(u * 32 + (__ffs(todo) - 1)), lane, mysmem, nullptr);
+                continue;
+            }
+            __threadfence();                                                  // the tile's state is visible device-wide ...
+            __syncwarp();
+            if (lane == 0) {                                                  // ... before the entry that points at it is
+                const unsigned slot = atomicAdd(&ctl->tail, 1u);
+                *(volatile unsigned*)&qmask[slot] = todo;
+                __threadfence();
+                *(volatile unsigned long long*)&queue[slot] = ((unsigned long long)epoch << 32) | u;
+                if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4 * (size_t)u + 1] = t_take; trace[4 * (size_t)u + 2] = t; trace[4 * (size_t)u + 3] = ((unsigned long long)__popc(todo) << 32) | slot; }
+            }
+            if (todo) episode_env_cold<TW>(E, P, (int)(u * 32 + (__ffs(todo) - 1)), lane, mysmem, &O);   // nobody is earlier than this warp
+        } else {                                                              // ---- observe unit
+            const unsigned q = (u - NT) / (unsigned)CH; const int chunk = (int)((u - NT) % (unsigned)CH);
+            unsigned tile_id = 0, ended = 0;
+            if (lane == 0) {
+                unsigned long long e;
+                while ((unsigned)((e = ld_vol(&queue[q])) >> 32) != epoch) __nanosleep(100);
+                __threadfence();
+                tile_id = (unsigned)e; ended = ld_vol(&qmask[q]);
+                if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4 * (size_t)u + 1] = t; }
+            }
+            tile_id = __shfl_sync(0xffffffffu, tile_id, 0); ended = __shfl_sync(0xffffffffu, ended, 0);
+            unsigned mine = ended & (ended - 1);                              // the first ended env is restarted by the step warp itself;
+            for (int k = 0; k < chunk && mine; ++k) mine &= mine - 1;         // this unit takes the (chunk+1)-th, the last chunk all that is left
+            if (chunk != CH - 1) mine &= 0u - mine;
+            for (; mine; mine &= mine - 1) episode_env_cold<TW>(E, P, (int)(tile_id * 32 + (__ffs(mine) - 1)), lane, mysmem, &O);
+            obs_unit<TW>(E, O, tile_id, chunk, lane, (float*)mysmem, ended);
+            __syncwarp();                                                     // the staging tile is reused by the next unit
+            if (trace && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4 * (size_t)u + 2] = t; trace[4 * (size_t)u + 3] = ((unsigned long long)__popc(ended) << 32) | tile_id; }
+        }
+    }
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl->warps_done, 1u) == gridDim.x * PASS_WARPS - 1) { ctl->ticket = 0; ctl->tail = 0; ctl->warps_done = 0; __threadfence(); }
     }
 }
 
@@ -913,7 +1162,11 @@ static int fail_cuda(cudaError_t e, const char* where) {
 
 struct dcm_env {
     int device; EnvArgs E; DcmLayout L; bool have_instances;
-    bool generic_step;               // DCM_STEP_GENERIC=1 at dcm_create: use the generic k_step even when the fast path applies (cross-check)
+    bool fast_step;                  // DCM_STEP_FAST=1 at dcm_create: use the experimental register-resident k_step_fast (measured slower)
+    bool fused_pass;                 // DCM_PASS_FUSED=1 at dcm_create: the whole pass in the single persistent kernel k_pass (measured slower)
+    bool serial_pass;                // DCM_PASS_SERIAL=1 at dcm_create: k_step, k_episode, k_obs one after the other on the caller's stream (cross-check)
+    PassCtl* d_ctl; unsigned long long* d_queue; unsigned* d_qmask; unsigned epoch; int pass_grid;
+    unsigned long long* d_trace; size_t trace_units;   // DCM_PASS_TRACE=1: per-unit globaltimer stamps of the last k_pass (tools/pass_trace.py)
     unsigned char* arena; size_t arena_bytes;
     double* metrics;                 // [B,8]
     unsigned long long* d_counter;   // scratch for reductions
@@ -922,6 +1175,7 @@ struct dcm_env {
     // dcm_step_host staging
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
     cudaStream_t hstream;
+    cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // k_episode runs beside k_obs
     uint64_t launches;
 };
 
@@ -952,7 +1206,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!v) return fail(DCM_ERR_NOMEM, "dcm_create: host allocation failed");
     memset(v, 0, sizeof *v);
     v->device = device;
-    { const char* gs = getenv("DCM_STEP_GENERIC"); v->generic_step = gs && gs[0] == '1'; }
+    { const char* gs = getenv("DCM_STEP_FAST"); v->fast_step = gs && gs[0] == '1'; gs = getenv("DCM_PASS_FUSED"); v->fused_pass = gs && gs[0] == '1' && !v->fast_step; gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; }
     v->L = dcm_make_layout(A, T, M);
     DcmSoa& S = v->E.S;
     S.B = B; S.NT = (B + 31) / 32; S.A = A; S.T = T; S.M = M; S.MC = M; S.TW = T <= 64 ? 1 : (T <= 128 ? 2 : 4);
@@ -971,7 +1225,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
                  o_am_touched = carve(1, 8), o_am_watch = carve(1, 8),
                  o_n_steps = carve(1, 4), o_episode = carve(1, 4), o_flags = carve(1, 4), o_instance = carve(1, 4), o_total = carve(1, 4), o_leader = carve(1, 4),
                  o_t_nab = carve(T, 2), o_a_nab = carve(A, 2),
-                 o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(1, S.ANB), o_s_req = carve(T, 1);
+                 o_ended = carve(1, 1), o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(1, S.ANB), o_s_req = carve(T, 1);
     S.tile_stride = off;
     v->arena_bytes = off * (size_t)NT;
     cudaError_t e = cudaMalloc((void**)&v->arena, v->arena_bytes);
@@ -979,6 +1233,18 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->metrics, (size_t)B * 8 * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(v->metrics, 0, (size_t)B * 8 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_counter, sizeof(unsigned long long));
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // highest priority: the few long episode chains must get their blocks in before the six waves of k_obs that run beside them
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&v->side, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_ctl, sizeof(PassCtl));
+    if (e == cudaSuccess) e = cudaMemset(v->d_ctl, 0, sizeof(PassCtl));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_queue, (size_t)NT * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(v->d_queue, 0, (size_t)NT * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_qmask, (size_t)NT * sizeof(unsigned));
+    { const char* tr = getenv("DCM_PASS_TRACE"); if (e == cudaSuccess && tr && tr[0] == '1') { v->trace_units = (size_t)NT * 64; e = cudaMalloc((void**)&v->d_trace, v->trace_units * 4 * sizeof(unsigned long long)); if (e == cudaSuccess) e = cudaMemset(v->d_trace, 0, v->trace_units * 4 * sizeof(unsigned long long)); } }
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
     S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec);
@@ -990,7 +1256,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     S.n_steps = (unsigned*)(a + o_n_steps); S.episode = (unsigned*)(a + o_episode); S.flags = (unsigned*)(a + o_flags);
     S.instance = (unsigned*)(a + o_instance); S.total = (unsigned*)(a + o_total); S.leader = (int*)(a + o_leader);
     S.t_nab = (unsigned short*)(a + o_t_nab); S.a_nab = (unsigned short*)(a + o_a_nab);
-    S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status); S.a_node = a + o_a_node; S.s_req = a + o_s_req;
+    S.ended = a + o_ended; S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status); S.a_node = a + o_a_node; S.s_req = a + o_s_req;
     k_init<<<(S.NT * 32 + 127) / 128, 128>>>(v->E);
     e = cudaDeviceSynchronize();
 
@@ -1003,9 +1269,12 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
 int dcm_destroy(dcm_env* v) {
     if (!v) return DCM_OK;
     DeviceGuard g(v->device);
-    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_cursor); cudaFree(v->d_record);
+    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_ctl); cudaFree(v->d_queue); cudaFree(v->d_qmask); cudaFree(v->d_trace); cudaFree(v->d_cursor); cudaFree(v->d_record);
     cudaFree(v->d_action); cudaFree(v->d_agent); cudaFree(v->d_task); cudaFree(v->d_mask); cudaFree(v->d_leader); cudaFree(v->d_reward); cudaFree(v->d_done);
     if (v->hstream) cudaStreamDestroy(v->hstream);
+    if (v->side) cudaStreamDestroy(v->side);
+    if (v->ev_fork) cudaEventDestroy(v->ev_fork);
+    if (v->ev_join) cudaEventDestroy(v->ev_join);
     delete v;
     return DCM_OK;
 }
@@ -1084,10 +1353,13 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 }
 
 static int launch_episode(dcm_env* v, const EpiArgs& P, cudaStream_t s) {
-    const size_t smem = EPI_WARPS * epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
-    if (v->E.S.TW == 1) k_episode<1><<<v->E.S.NT, 32 * EPI_WARPS, smem, s>>>(v->E, P);
-    else if (v->E.S.TW == 2) k_episode<2><<<v->E.S.NT, 32 * EPI_WARPS, smem, s>>>(v->E, P);
-    else k_episode<4><<<v->E.S.NT, 32 * EPI_WARPS, smem, s>>>(v->E, P);
+    // four warps per tile share the tile's envs that need work.  (One warp per tile, to hold fewer registers beside k_obs, was
+    // measured slower: a tile with two or three ended envs then serialises 50 us chains -- profiles/r01w.)
+    const int warps = EPI_WARPS;
+    const size_t smem = warps * epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
+    if (v->E.S.TW == 1) k_episode<1><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, P);
+    else if (v->E.S.TW == 2) k_episode<2><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, P);
+    else k_episode<4><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, P);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
@@ -1099,7 +1371,8 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_reset: load or generate instances first");
     DeviceGuard g(v->device);
     cudaStream_t s = (cudaStream_t)stream;
-    EpiArgs P{1, which, leader_in, next_leader, v->metrics};
+    CK(cudaMemsetAsync(v->d_ctl, 0, sizeof(PassCtl), s));                     // k_pass work-queue counters (they reset themselves; this heals an aborted launch)
+    EpiArgs P{1, which, leader_in, next_leader, v->metrics, ObsArgs{nullptr, nullptr, nullptr, nullptr, 0}, 0};
     int rc = launch_episode(v, P, s);
     if (rc) return rc;
     ObsArgs O{nullptr, agent_obs, task_obs, mask, 0};
@@ -1119,7 +1392,32 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     StepArgs F; memset(&F, 0, sizeof F);
     F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
     F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action;
-    if (v->E.S.MC <= 8 && !v->generic_step) {
+    ObsArgs O{nullptr, agent_obs, task_obs, mask, 0};
+    EpiArgs P{0, nullptr, next_leader_in, next_leader, v->metrics, O, 0};
+    const bool want_obs = agent_obs || task_obs || mask;
+    if (v->fused_pass) {                                                      // the whole pass in one launch (k_pass)
+        const int NA = (v->E.S.A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (v->E.S.T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
+        const int CH = want_obs ? NA + NR : 0;
+        const size_t smem = PASS_WARPS * pass_warp_smem(v->E.S.A, v->E.S.T, v->E.S.MC);
+        if (!v->pass_grid) {
+            int per_sm = 0, sms = 0;
+            const void* fn = v->E.S.TW == 1 ? (const void*)k_pass<1> : v->E.S.TW == 2 ? (const void*)k_pass<2> : (const void*)k_pass<4>;
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * PASS_WARPS, smem));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
+            v->pass_grid = per_sm * sms > 0 ? per_sm * sms : sms;
+        }
+        const unsigned units = (unsigned)v->E.S.NT * (unsigned)(1 + CH);
+        int grid = v->pass_grid; if ((unsigned)grid * PASS_WARPS > units) grid = (int)((units + PASS_WARPS - 1) / PASS_WARPS);
+        const unsigned epoch = ++v->epoch;
+        if (v->E.S.TW == 1) k_pass<1><<<grid, 32 * PASS_WARPS, smem, s>>>(v->E, F, P, O, v->d_ctl, v->d_queue, v->d_qmask, epoch, CH, v->d_trace);
+        else if (v->E.S.TW == 2) k_pass<2><<<grid, 32 * PASS_WARPS, smem, s>>>(v->E, F, P, O, v->d_ctl, v->d_queue, v->d_qmask, epoch, CH, v->d_trace);
+        else k_pass<4><<<grid, 32 * PASS_WARPS, smem, s>>>(v->E, F, P, O, v->d_ctl, v->d_queue, v->d_qmask, epoch, CH, v->d_trace);
+        CK(cudaGetLastError());
+        v->launches++;
+        return DCM_OK;
+    }
+    if (v->E.S.MC <= 8 && v->fast_step) {
         const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
 #define LAUNCH_FAST(tw) do { if (small) k_step_fast<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step_fast<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
         if (TW == 1) LAUNCH_FAST(1); else if (TW == 2) LAUNCH_FAST(2); else LAUNCH_FAST(4);
@@ -1127,14 +1425,26 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     } else LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
     CK(cudaGetLastError());
     v->launches++;
-    // episode accounting (+ restart with DCM_FLAG_AUTO_RESET) of the envs that just finished; the injected leader of a
-    // restarted env is the same next_leader_in entry.  (Running this beside k_obs on a side stream was measured and is
-    // slower: 206 vs 194 us per step at 65,536 envs -- see DESIGN.md.)
-    EpiArgs P{0, nullptr, next_leader_in, next_leader, v->metrics};
-    int rc = launch_episode(v, P, s);
+    // Episode accounting (+ restart with DCM_FLAG_AUTO_RESET) of the envs that just finished; the injected leader of a
+    // restarted env is the same next_leader_in entry.  The episode kernel is a few hundred long, latency-bound warp
+    // chains (~30 us) and k_obs is bandwidth-bound (~60 us): they run side by side.  k_obs leaves out the envs k_step marked
+    // `ended`; k_episode writes the observation of the envs it restarts from registers (episode_env).
+    if (v->serial_pass || !want_obs) {
+        int rc = launch_episode(v, P, s);
+        if (rc) return rc;
+        if (want_obs) return launch_obs(v, O, s);
+        return DCM_OK;
+    }
+    CK(cudaEventRecord(v->ev_fork, s));
+    CK(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
+    P.obs = O; P.write_obs = (v->E.cflags & DCM_FLAG_AUTO_RESET) ? 1 : 0;
+    int rc = launch_episode(v, P, v->side);
     if (rc) return rc;
-    ObsArgs O{nullptr, agent_obs, task_obs, mask, 0};
-    if (agent_obs || task_obs || mask) return launch_obs(v, O, s);
+    CK(cudaEventRecord(v->ev_join, v->side));
+    O.skip_ended = 1;
+    rc = launch_obs(v, O, s);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s, v->ev_join, 0));
     return DCM_OK;
 }
 
@@ -1305,5 +1615,14 @@ size_t dcm_algorithmic_bytes_per_step(const dcm_env* v) {
 }
 
 uint64_t dcm_launch_count(const dcm_env* v) { return v ? v->launches : 0; }
+
+int dcm_debug_pass_trace(dcm_env* v, uint64_t* out_h, size_t n_words) {
+    if (!v || !out_h) return fail(DCM_ERR_ARG, "dcm_debug_pass_trace: NULL argument");
+    if (!v->d_trace) return fail(DCM_ERR_STATE, "dcm_debug_pass_trace: create the handle with DCM_PASS_TRACE=1");
+    DeviceGuard g(v->device);
+    const size_t have = v->trace_units * 4;
+    CK(cudaMemcpy(out_h, v->d_trace, (n_words < have ? n_words : have) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DCM_OK;
+}
 
 }  // extern "C"

@@ -63,6 +63,7 @@ struct DcmSoa {
     unsigned long long* group;
     unsigned* n_steps; unsigned* episode; unsigned* flags; unsigned* instance; unsigned* total;
     int* leader;
+    unsigned char* ended;     // 1 = the env's episode ended in the last step (its observation comes from the episode kernel, not from k_obs)
     // ---- static instance (rows: T, depot: 2) ----
     double* s_tx; double* s_ty; double* s_dur; double* s_dep;
     unsigned char* s_req;

@@ -173,6 +173,10 @@ size_t dcm_algorithmic_bytes_per_step(const dcm_env* env);
 /* number of kernels this handle has launched since creation */
 uint64_t dcm_launch_count(const dcm_env* env);
 
+/* developer aid: with DCM_PASS_TRACE=1 in the environment at dcm_create, the fused pass kernel stamps every work unit with
+ * %globaltimer: out_h[4*u .. 4*u+3] = {taken, ready, finished, info} in ns for unit u of the last dcm_step (synchronises) */
+int dcm_debug_pass_trace(dcm_env* env, uint64_t* out_h, size_t n_words);
+
 const char* dcm_last_error(void);
 const char* dcm_version(void);
 

@@ -234,40 +234,44 @@ def test_shard_invariance():
     big.close(); small.close()
 
 
+@pytest.mark.parametrize("variant", ["DCM_PASS_SERIAL", "DCM_PASS_FUSED", "DCM_STEP_FAST"])
 @pytest.mark.parametrize("shape,policy", [((20, 50), "random"), ((20, 50), "greedy"), ((10, 20), "random"), ((50, 200), "random"), ((30, 100), "greedy")])
-def test_fast_step_equals_generic_step(shape, policy, monkeypatch):
-    """The register-resident k_step_fast (dcm_fast.cuh) against the generic k_step (dcm_thread.cuh) on the same batch: raw
-    records (every field, bookkeeping bits included), observations, rewards and metrics identical after every 50 decisions."""
+def test_fused_pass_equals_split_kernels(shape, policy, variant, monkeypatch):
+    """The default pass (k_step, then k_episode on a side stream writing the restarted envs' observations from registers
+    beside k_obs) against (a) the three kernels one after the other with k_obs building every observation from memory,
+    (b) the single persistent kernel k_pass (tile completion queue) and (c) the experimental register-resident k_step_fast:
+    raw records (every field, bookkeeping bits included), observations, rewards, leaders and metrics identical on a batch
+    that is not a multiple of the tile size."""
     from dcmrta_b200 import BatchedTaskEnv
     A, T = shape
     B = 4099
-    fast = BatchedTaskEnv(B, A, T, auto_reset=True, seed=11, first_gid=5)
-    monkeypatch.setenv("DCM_STEP_GENERIC", "1")
-    gen = BatchedTaskEnv(B, A, T, auto_reset=True, seed=11, first_gid=5)
-    monkeypatch.delenv("DCM_STEP_GENERIC")
-    for e in (fast, gen):
+    fused = BatchedTaskEnv(B, A, T, auto_reset=True, seed=11, first_gid=5)
+    monkeypatch.setenv(variant, "1")
+    other = BatchedTaskEnv(B, A, T, auto_reset=True, seed=11, first_gid=5)
+    monkeypatch.delenv(variant)
+    for e in (fused, other):
         e.generate(max_duration=5.0, random_duration=(policy == "greedy"))
         e.reset()
-    keys = [k for k in fast.export_state([0])[0].keys()]
+    assert fused.launch_count() == other.launch_count()
+    keys = [k for k in fused.export_state([0])[0].keys()]
     for k in range(600):
-        fast.step(policy=policy)
-        gen.step(policy=policy)
+        fused.step(policy=policy)
+        other.step(policy=policy)
         if k % 50 == 49 or k < 3:
-            assert np.array_equal(fast.reward.cpu().numpy(), gen.reward.cpu().numpy()), k
-            assert np.array_equal(fast.leader.cpu().numpy(), gen.leader.cpu().numpy()), k
-            assert np.array_equal(fast.done_u8.cpu().numpy(), gen.done_u8.cpu().numpy()), k
-            assert np.array_equal(fast.used_action.cpu().numpy(), gen.used_action.cpu().numpy()), k
-            assert np.array_equal(fast.agent_obs.cpu().numpy(), gen.agent_obs.cpu().numpy()), k
-            assert np.array_equal(fast.task_obs.cpu().numpy(), gen.task_obs.cpu().numpy()), k
-            assert np.array_equal(fast.mask_u8.cpu().numpy(), gen.mask_u8.cpu().numpy()), k
-            a, b = fast.export_raw(), gen.export_raw()
+            assert np.array_equal(fused.reward.cpu().numpy(), other.reward.cpu().numpy()), k
+            assert np.array_equal(fused.leader.cpu().numpy(), other.leader.cpu().numpy()), k
+            assert np.array_equal(fused.done_u8.cpu().numpy(), other.done_u8.cpu().numpy()), k
+            assert np.array_equal(fused.used_action.cpu().numpy(), other.used_action.cpu().numpy()), k
+            assert np.array_equal(fused.agent_obs.cpu().numpy(), other.agent_obs.cpu().numpy()), k
+            assert np.array_equal(fused.task_obs.cpu().numpy(), other.task_obs.cpu().numpy()), k
+            assert np.array_equal(fused.mask_u8.cpu().numpy(), other.mask_u8.cpu().numpy()), k
+            a, b = fused.export_raw(), other.export_raw()
             if not np.array_equal(a, b):
                 bad = int(np.argwhere((a != b).any(1))[0, 0])
-                sa, sb = fast.export_state([bad])[0], gen.export_state([bad])[0]
-                diff = [key for key in keys if not np.array_equal(np.asarray(sa[key]), np.asarray(sb[key]), equal_nan=True)] \
-                    if True else []
+                sa, sb = fused.export_state([bad])[0], other.export_state([bad])[0]
+                diff = [key for key in keys if not np.array_equal(np.asarray(sa[key]), np.asarray(sb[key]), equal_nan=True)]
                 raise AssertionError(f"decision {k}: env {bad} differs in {diff}")
-    ma, mb = fast.episode_metrics().cpu().numpy(), gen.episode_metrics().cpu().numpy()
+    ma, mb = fused.episode_metrics().cpu().numpy(), other.episode_metrics().cpu().numpy()
     assert np.array_equal(ma, mb)
-    assert fast.total_steps() == gen.total_steps() == B * 600
-    fast.close(); gen.close()
+    assert fused.total_steps() == other.total_steps() == B * 600
+    fused.close(); other.close()

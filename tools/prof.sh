@@ -13,4 +13,6 @@ if [ "$2" = "full" ]; then
   DCM_PROFILE_AT=600 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_${tag} -f python bench.py --steps 700 --warmup 20 --e2e-steps 8 --no-cpu-baseline > gpurun_out/ncu_full_${tag}.log 2>&1
   ls -la gpurun_out/prof_${tag}.ncu-rep
 fi
-python bench.py --steps 1000 --warmup 200 --e2e-steps 8 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_${tag}.json | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value', d['value'], 'us', d['roofline']['launch_us'])"
+for B in 16384 65536; do
+python bench.py --envs $B --steps 1000 --warmup 200 --e2e-steps 8 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_${tag}_$B.json | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('B', d['config']['envs_per_gpu'], 'value', d['value'], 'us', d['roofline']['launch_us'], 'e2e', d['e2e']['value'])"
+done
