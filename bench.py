@@ -50,6 +50,11 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=200)
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--mode", default="env", choices=["env", "rollout", "train"],
+                   help="env: the headline metric (step kernels only).  rollout / train: BASELINE configs[4], the same env-steps/s with the "
+                        "PyTorch attention policy in the loop (rollout) and with the REINFORCE update + gradient all-reduce (train)")
+    p.add_argument("--iters", type=int, default=3, help="--mode rollout/train: timed iterations (one episode per env each)")
+    p.add_argument("--amp", action="store_true", help="--mode rollout/train: bf16 autocast for the rollout forward passes")
     return p.parse_args()
 
 
@@ -320,10 +325,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_training(args):
+    """BASELINE configs[4]: env-steps/s with the policy in the loop.  rollout: one sampled episode per env (policy forward +
+    sampling + dcm_step per decision).  train: a full trainer iteration (sampled rollout, greedy baseline rollout, REINFORCE
+    updates with the NCCL gradient all-reduce); env-steps counted = decisions of the sampled rollout only."""
+    import torch
+    import torch.distributed as dist
+    from dcmrta_b200.sharding import dist_env
+    from dcmrta_b200.trainer import ReinforceTrainer, TrainerConfig
+
+    rank, local, world = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.envs if args.envs != 65536 else 8192
+    cfg = TrainerConfig(agents=args.agents, tasks=args.tasks, envs_per_rank=B, amp=args.amp, seed=1234, eval_instances=max(world, 64))
+    tr = ReinforceTrainer(cfg, device=local)
+
+    def one():
+        if args.mode == "train":
+            return tr.iteration()["decisions"]
+        tr.env.generate(max_duration=5.0)
+        ep = tr.rollout.run(tr.net, "sample", tr.gen, amp=cfg.amp)
+        return int(ep.active.sum())
+
+    one()                                                            # warm-up (allocator, cuBLAS handles, autotune)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    decisions = sum(one() for _ in range(args.iters))
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(decisions)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"env-steps/sec at {args.agents}A/{args.tasks}T with the attention policy in the loop ({args.mode})",
+            "value": float(cnt.item()) / (float(t.item()) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.iters, "warmup": 1,
+            "ms_per_step": float(t.item()) / args.iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 env / " + ("bf16" if args.amp else "fp32") + " policy", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {B} synthetic {args.agents}A/{args.tasks}T envs per GPU, one episode per env per iteration, "
+                                   f"AttentionNet(128) in PyTorch, mode={args.mode}", "envs_per_gpu": B, "iterations": args.iters,
+                       "parallelism": f"env shards x{world}" + (", one flat NCCL gradient all-reduce per update" if args.mode == "train" else "")},
+            "env_steps_timed": float(cnt.item())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode != "env":
+        run_training(args)
     else:
         run_ours(args)
 

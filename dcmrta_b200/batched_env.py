@@ -74,6 +74,18 @@ class BatchedTaskEnv:
         except Exception:
             pass
 
+    def set_output_buffers(self, agent_obs=None, task_obs=None, mask_u8=None):
+        """Make reset()/step() write the next observation straight into caller-owned tensors (e.g. the slot of an episode
+        buffer, dcmrta_b200/rollout.py): fp32 [B,A,6], fp32 [B,T+1,5], uint8 [B,T+1], contiguous, on this device."""
+        for name, t, shape, dt in (("agent_obs", agent_obs, (self.B, self.A, 6), torch.float32),
+                                   ("task_obs", task_obs, (self.B, self.T + 1, 5), torch.float32),
+                                   ("mask_u8", mask_u8, (self.B, self.T + 1), torch.uint8)):
+            if t is None:
+                continue
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise _lib.DcmError(-1, f"set_output_buffers: {name} must be a contiguous {dt} tensor of shape {shape} on {self.device}")
+            setattr(self, name, t)
+
     @property
     def mask(self):
         """bool view of the mask buffer, True = forbidden (reference worker.py:57-61)."""

@@ -1,0 +1,98 @@
+"""dcmrta_b200/rollout.py -- batched rollout loop: the device-resident replacement of the Ray CPU workers
+(reference worker.py:41-112 `Worker.run_episode`, :200-235 `baseline_test`, runner.py:32-71).
+
+One `BatchedRollout.run` plays one episode in EVERY env of a `BatchedTaskEnv`: per decision one batched policy forward over
+the B observations the step kernels wrote, on-device sampling (or argmax), one `dcm_step`.  Nothing crosses PCIe inside the
+loop except a done-flag poll every `check_every` decisions (the reference moves every observation to the device and every
+action back, worker.py:62-73).  The 7 used slots of the reference's 9-slot episode buffer (worker.py:42, :77-83) live in
+preallocated device tensors; the env writes each observation straight into its slot (`set_output_buffers`), so there is no
+copy between "observation" and "experience".
+
+Reward and advantage follow worker.py:87-101: the episode reward is -makespan (task_env.py:424), the advantage of every
+decision of an episode is reward - greedy-baseline reward of the same instance (GAMMA = 1, parameters.py:6).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .batched_env import BatchedTaskEnv
+from .policy import greedy_actions, sample_actions
+
+
+@dataclass
+class Episodes:
+    """Result of one batched rollout.  L = decisions actually played (max over envs)."""
+    reward: torch.Tensor        # [B] f64   -makespan (get_episode_reward, task_env.py:420-425); NaN where the env did not end within the horizon
+    metrics: torch.Tensor       # [B,8] f64 reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions
+    ended: torch.Tensor         # [B] bool
+    length: int
+    # experience (None when record=False); index [t, b]
+    agent_obs: torch.Tensor | None = None   # [L,B,A,6]  f32
+    task_obs: torch.Tensor | None = None    # [L,B,T+1,5] f32
+    mask: torch.Tensor | None = None        # [L,B,T+1]  u8 (1 = forbidden)
+    action: torch.Tensor | None = None      # [L,B]      i32
+    leader: torch.Tensor | None = None      # [L,B]      i32  (agent id, buffer slot 5 of the reference)
+    active: torch.Tensor | None = None      # [L,B]      bool: env b took its t-th decision
+
+
+class BatchedRollout:
+    def __init__(self, env: BatchedTaskEnv, horizon: int, record: bool = True, check_every: int = 16):
+        self.env, self.horizon, self.record, self.check_every = env, int(horizon), bool(record), int(check_every)
+        B, A, T, dev = env.B, env.A, env.T, env.device
+        L = self.horizon + 1 if record else 2                       # without recording two slots are ping-ponged
+        self.agent_obs = torch.zeros(L, B, A, 6, dtype=torch.float32, device=dev)
+        self.task_obs = torch.zeros(L, B, T + 1, 5, dtype=torch.float32, device=dev)
+        self.mask = torch.zeros(L, B, T + 1, dtype=torch.uint8, device=dev)
+        self.action = torch.zeros(self.horizon, B, dtype=torch.int32, device=dev) if record else None
+        self.leader = torch.zeros(self.horizon, B, dtype=torch.int32, device=dev) if record else None
+        self.active = torch.zeros(self.horizon, B, dtype=torch.bool, device=dev) if record else None
+
+    def _slot(self, t):
+        return t if self.record else t & 1
+
+    @torch.no_grad()
+    def run(self, net, mode: str = "sample", generator: torch.Generator | None = None, amp: bool = False) -> Episodes:
+        """Play one episode per env with `net` (sampling: worker.py:70; greedy: worker.py:222).  The env must not auto-reset."""
+        env = self.env
+        assert not env.auto_reset, "rollouts use one episode per env: create the env with auto_reset=False"
+        was_training = net.training
+        net.eval()
+        s = self._slot(0)
+        env.set_output_buffers(self.agent_obs[s], self.task_obs[s], self.mask[s])
+        env.reset()
+        t = 0
+        while t < self.horizon:
+            s = self._slot(t)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                logp = net(self.task_obs[s], self.agent_obs[s], self.mask[s].view(torch.bool))
+            act = sample_actions(logp.float(), generator) if mode == "sample" else greedy_actions(logp)
+            if self.record:
+                self.action[t].copy_(act)
+                self.leader[t].copy_(env.leader)
+                torch.logical_not(env.done, out=self.active[t])
+            n = self._slot(t + 1)
+            env.set_output_buffers(self.agent_obs[n], self.task_obs[n], self.mask[n])
+            if not self.record:                                      # an env that is done keeps a valid (stale) row in both slots
+                self.mask[n].copy_(self.mask[s])
+            env.step(act)
+            t += 1
+            if t % self.check_every == 0 and bool(env.done.all()):
+                break
+        ended = env.done.clone()
+        metrics = env.episode_metrics()
+        reward = torch.where(ended, metrics[:, 0], torch.full_like(metrics[:, 0], float("nan")))
+        if was_training:
+            net.train()
+        ep = Episodes(reward=reward, metrics=metrics, ended=ended, length=t)
+        if self.record:
+            ep.agent_obs, ep.task_obs, ep.mask = self.agent_obs[:t], self.task_obs[:t], self.mask[:t]
+            ep.action, ep.leader, ep.active = self.action[:t], self.leader[:t], self.active[:t]
+        return ep
+
+
+def clone_instances(src: BatchedTaskEnv, dst: BatchedTaskEnv) -> None:
+    """copy.deepcopy(self.env) of worker.py:33 for a batch: the baseline env plays the same instances."""
+    inst = src.get_instances()
+    dst.load_instances(inst["task_xy"], inst["depot_xy"], inst["req"], inst["dur"])
