@@ -64,8 +64,8 @@ template <int N, class V, class L, class U> __device__ __forceinline__ void for_
 }
 
 // ---- one task's coalition in registers (member slots <= 8) -----------------------------------------------------------
-struct TaskR {
-    double a[8];        // arrival of member slot s (last visit, task_env.py:202-205)
+template <int MCK> struct TaskR {
+    double a[MCK];        // arrival of member slot s (last visit, task_env.py:202-205)
     u64 ids;            // member ids, one byte per slot, list order
     int n, n0;          // len(members): current / as stored in memory
     unsigned wr;        // bit s: a[s] must be stored; bit 8: ids must be stored
@@ -77,47 +77,47 @@ struct TaskR {
 #define RID(R, s) ((unsigned)(((R).ids >> (8 * (s))) & 0xffull))
 
 // ONE round trip: every load is issued before any value is used
-template <int TW> __device__ __forceinline__ void r_load(const TC& c, const St<TW>& st, int j, bool valid, TaskR& R) {
+template <int TW, int MCK> __device__ __forceinline__ void r_load(const TC& c, const St<TW>& st, int j, bool valid, TaskR<MCK>& R) {
     const int T = c.T;
     const bool ne = valid && tbit<TW>(st.ne, j), fe = valid && tbit<TW>(st.feas, j);
     const int jj = valid ? j : 0;
     int n = 0; u64 ids = 0;
     if (ne) { n = EL(c, t_nmem, T, jj); ids = *(const u64*)&SMEM(c, jj, 0); }
 #pragma unroll
-    for (int s = 0; s < 8; ++s) R.a[s] = (ne && s < c.MC) ? SARR(c, jj, s) : 0.0;
+    for (int s = 0; s < MCK; ++s) R.a[s] = (ne && s < c.MC) ? SARR(c, jj, s) : 0.0;
     R.req = valid ? (int)EL(c, s_req, T, jj) : 1; R.status0 = valid ? (int)EL(c, t_status, T, jj) : 0; R.dur = valid ? EL(c, s_dur, T, jj) : 0.0;
     R.info = (ne || fe) ? TINFO2(c, jj) : make_double2(0.0, 0.0);
     R.n = R.n0 = n; R.ids = ids; R.wr = 0; R.had = ne;
 }
-__device__ __forceinline__ void r_flush(const TC& c, int j, TaskR& R) {
+template <int MCK> __device__ __forceinline__ void r_flush(const TC& c, int j, TaskR<MCK>& R) {
 #pragma unroll
-    for (int s = 0; s < 8; ++s) if ((R.wr >> s) & 1u) SARR(c, j, s) = R.a[s];
+    for (int s = 0; s < MCK; ++s) if ((R.wr >> s) & 1u) SARR(c, j, s) = R.a[s];
     if (R.wr & 0x100u) *(u64*)&SMEM(c, j, 0) = R.ids;
     if (R.n != R.n0) { EL(c, t_nmem, c.T, j) = (unsigned char)R.n; R.n0 = R.n; }
     R.wr = 0;
 }
-__device__ __forceinline__ double r_amin(const TaskR& R) {
+template <int MCK> __device__ __forceinline__ double r_amin(const TaskR<MCK>& R) {
     double am = CUDART_INF;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) if (s < R.n) am = R.a[s] < am ? R.a[s] : am;
+    for (int s = 0; s < MCK; ++s) if (s < R.n) am = R.a[s] < am ? R.a[s] : am;
     return am;
 }
 
 // the membership part of agent_step (task_env.py:321-322; Q8: a re-visit by a current member only updates its arrival)
-template <int TW> __device__ __forceinline__ void r_join(const TC& c, St<TW>& st, TaskR& R, int i, double arrival, unsigned& flags, bool& appended) {
+template <int TW, int MCK> __device__ __forceinline__ void r_join(const TC& c, St<TW>& st, TaskR<MCK>& R, int i, double arrival, unsigned& flags, bool& appended) {
     const u64 bit = 1ull << i;
     int pos = -1;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) if (s < R.n && RID(R, s) == (unsigned)i) pos = s;
+    for (int s = 0; s < MCK; ++s) if (s < R.n && RID(R, s) == (unsigned)i) pos = s;
     if (pos >= 0) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) if (s == pos) R.a[s] = arrival;
+        for (int s = 0; s < MCK; ++s) if (s == pos) R.a[s] = arrival;
         R.wr |= 1u << pos; st.member |= bit;
     } else if (R.n < c.MC) {
         const int n = R.n;
         R.ids = (R.ids & ~(0xffull << (8 * n))) | ((u64)(unsigned)i << (8 * n));
 #pragma unroll
-        for (int s = 0; s < 8; ++s) if (s == n) R.a[s] = arrival;
+        for (int s = 0; s < MCK; ++s) if (s == n) R.a[s] = arrival;
         R.wr |= (1u << n) | 0x100u; R.n = n + 1; appended = true; st.member |= bit;
     } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }
 }
@@ -125,8 +125,8 @@ template <int TW> __device__ __forceinline__ void r_join(const TC& c, St<TW>& st
 // task_update body for one non-feasible task with members (task_env.py:250-271), on registers.  Same cases as
 // t_eval_task: feasible (:255-258), spread too large (:260-265, Q4), still short (:266-271, Q2); status is the count
 // BEFORE removals (Q3).
-template <int TW, int NW>
-__device__ __forceinline__ void r_eval(const TC& c, St<TW>& st, const Nodes<NW>& nodes, double now, int j, TaskR& R) {
+template <int TW, int NW, int MCK>
+__device__ __forceinline__ void r_eval(const TC& c, St<TW>& st, const Nodes<NW>& nodes, double now, int j, TaskR<MCK>& R) {
     const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
     const int n = R.n;
     const int stt = R.req - n;                                                // :252
@@ -137,25 +137,25 @@ __device__ __forceinline__ void r_eval(const TC& c, St<TW>& st, const Nodes<NW>&
     if (stt <= 0) {                                                           // :254
         double mx = R.a[0], mn = mx;
 #pragma unroll
-        for (int s = 1; s < 8; ++s) if (s < n) { mx = R.a[s] > mx ? R.a[s] : mx; mn = R.a[s] < mn ? R.a[s] : mn; }
+        for (int s = 1; s < MCK; ++s) if (s < n) { mx = R.a[s] > mx ? R.a[s] : mx; mn = R.a[s] < mn ? R.a[s] : mn; }
         if (mx - mn <= c.W) {                                                 // :255
             const double tf = mx + R.dur;
             R.info = make_double2(mx, tf); TINFO2(c, j) = R.info;             // :256-257
             st.xfin = tf < st.xfin ? tf : st.xfin;
             feas = bit; open = 0;                                             // :258
 #pragma unroll
-            for (int s = 0; s < 8; ++s) if (s < n) { const unsigned m = RID(R, s); if (nget<NW>(nodes, (int)m) == (unsigned)j) st.touched |= 1ull << m; }
+            for (int s = 0; s < MCK; ++s) if (s < n) { const unsigned m = RID(R, s); if (nget<NW>(nodes, (int)m) == (unsigned)j) st.touched |= 1ull << m; }
         } else {                                                              // :260-265 (iterates a copy: Q4)
             const double thr = mx - c.W;
             keep = 0;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) if (s < n && !(R.a[s] <= thr)) keep |= 1u << s;
+            for (int s = 0; s < MCK; ++s) if (s < n && !(R.a[s] <= thr)) keep |= 1u << s;
             rewrite = true;
         }
     } else {                                                                  // :266-271 (mutates while iterating: Q2)
         keep = 0; bool skip = false;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < n) {
+        for (int s = 0; s < MCK; ++s) if (s < n) {
             if (skip) { keep |= 1u << s; skip = false; }                      // the element that moved into the erased slot is not examined
             else if (now - R.a[s] >= c.W) skip = true;                        // :269 (Q1: false when fl(arr + W) rounded down)
             else keep |= 1u << s;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void r_eval(const TC& c, St<TW>& st, const Nodes<NW>&
     if (rewrite) {
         int wv = 0; u64 nids = 0; double amin = CUDART_INF;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < n) {
+        for (int s = 0; s < MCK; ++s) if (s < n) {
             const unsigned m = RID(R, s);
             if ((keep >> s) & 1u) {
                 const double v = R.a[s];
@@ -205,8 +205,8 @@ __device__ __forceinline__ void r_eval(const TC& c, St<TW>& st, const Nodes<NW>&
 // examined by the NEXT task_update call, :272 is the else-branch) and states that did not come from the fused protocol
 // (dcm_import_state, granular calls) until the first slot start; a slot without deciders runs the full scan.
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW, int NW>
-__device__ __forceinline__ void f_task_update(const TC& c, St<TW>& st, const Nodes<NW>& nodes, double now, int jr, TaskR& R, double2& jinfo,
+template <int TW, int NW, int MCK>
+__device__ __forceinline__ void f_task_update(const TC& c, St<TW>& st, const Nodes<NW>& nodes, double now, int jr, TaskR<MCK>& R, double2& jinfo,
                                               bool slot_start, u64 dec) {
     const int T = c.T;
     const bool scan_wait = now - st.xamin >= c.W, scan_fin = now >= st.xfin || (slot_start && dec == 0);
@@ -263,9 +263,9 @@ __device__ __forceinline__ void f_task_update(const TC& c, St<TW>& st, const Nod
             for (int w = TW - 1; w >= 0; --w) if (hot[w]) j = 64 * w + ctz64(hot[w]);
             if (j < 0) break;
             tset<TW>(hot, j, false);
-            r_load<TW>(c, st, j, true, R);
+            r_load<TW, MCK>(c, st, j, true, R);
         }
-        r_eval<TW, NW>(c, st, nodes, now, j, R);
+        r_eval<TW, NW, MCK>(c, st, nodes, now, j, R);
         if (pre) { jinfo = R.info; pre = false; }
         r_flush(c, j, R);
     }
@@ -331,26 +331,14 @@ __device__ __forceinline__ void f_agent_update(const TC& c, St<TW>& st, const No
 template <int TW> __device__ __forceinline__ u64 f_next_decision(const TC& c, const St<TW>& st, double& t_out) {
     const int A = c.A;
     double mn = CUDART_INF; u64 mask = 0;
-    for (int i0 = 0; i0 < A; i0 += 32) {
-        double v0[16], v1[16];
-        const bool two = i0 + 16 < A;
+    for (int i0 = 0; i0 < A; i0 += 10) {                                       // ten loads in flight (A = 20: two round trips)
+        double v[10];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v0[q] = EL(c, a_nd, A, i0 + q < A ? i0 + q : i0);
-        if (two) {
+        for (int q = 0; q < 10; ++q) v[q] = EL(c, a_nd, A, i0 + q < A ? i0 + q : i0);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v1[q] = EL(c, a_nd, A, i0 + 16 + q < A ? i0 + 16 + q : i0);
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) if (i0 + q < A) {
-            if (v0[q] < mn) { mn = v0[q]; mask = 1ull << (i0 + q); }          // NaN compares false
-            else if (v0[q] == mn) mask |= 1ull << (i0 + q);                   // :288
-        }
-        if (two) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) if (i0 + 16 + q < A) {
-                if (v1[q] < mn) { mn = v1[q]; mask = 1ull << (i0 + 16 + q); }
-                else if (v1[q] == mn) mask |= 1ull << (i0 + 16 + q);
-            }
+        for (int q = 0; q < 10; ++q) if (i0 + q < A) {
+            if (v[q] < mn) { mn = v[q]; mask = 1ull << (i0 + q); }            // NaN compares false
+            else if (v[q] == mn) mask |= 1ull << (i0 + q);                    // :288
         }
     }
     t_out = mask ? mn : st.xlast;

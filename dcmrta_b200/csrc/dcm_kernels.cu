@@ -203,11 +203,22 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant_
     step_env<TW>(E, F, b);
 }
 
+// experiment (DCM_STEP_LANES=16 / 8): the same step with only 16 or 8 envs per warp -- fewer divergent paths per warp, more warps
+template <int TW>
+__global__ void __launch_bounds__(STEP_THREADS, 7) k_step_narrow(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F, int lanes) {
+    const unsigned gw = (blockIdx.x * STEP_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if ((int)lane >= lanes) return;
+    const unsigned per = 32u / (unsigned)lanes;
+    const int b = (int)((gw / per) * 32u + (gw % per) * (unsigned)lanes + lane);
+    if (b >= E.S.B) return;
+    step_env<TW>(E, F, b);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_step_fast: the same decision as k_step with the chosen task, the node ids and the per-env masks held in registers
 // (dcm_fast.cuh).  Used whenever the handle has at most 8 member slots per task; k_step stays the generic version.
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW, int NW>
+template <int TW, int NW, int MCK>
 __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
@@ -239,7 +250,7 @@ __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, 
     if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
     const bool to_task = ok && action != 0; const int j = to_task ? action - 1 : 0;
     // ---- round 2: the chosen task, its coordinates, the leader's location
-    TaskR R; r_load<TW>(c, st, j, to_task, R);
+    TaskR<MCK> R; r_load<TW, MCK>(c, st, j, to_task, R);
     double tx, ty; node_xy(c, to_task ? (unsigned)j : DCM_NODE_DEPOT, tx, ty);
     const double2 L = AREC2(c, ok ? leader : 0, 0);
     int want = 0; u64 g = group & ~(1ull << leader);                          // task_env.py:328
@@ -272,7 +283,7 @@ __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, 
             ANODE(c, i) = (unsigned char)nn; nset<NW>(nodes, i, nn);          // :314
             st.route |= bit; st.touched |= bit; mv |= bit; pending &= ~bit;
             if (!to_task) { st.depot |= bit; st.member &= ~bit; }
-            else { st.depot &= ~bit; r_join<TW>(c, st, R, i, arrival, flags, appended); }
+            else { st.depot &= ~bit; r_join<TW, MCK>(c, st, R, i, arrival, flags, appended); }
             reward += -tt; ++nm;
         };
         move(leader);
@@ -309,7 +320,7 @@ __global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, 
         double2 jinfo = R.info;
         int jr = to_task ? j : -1; bool slot_start = false; u64 dec = 0; int empty_slots = 0;
         for (;;) {
-            f_task_update<TW, NW>(c, st, nodes, now, jr, R, jinfo, slot_start, dec);
+            f_task_update<TW, NW, MCK>(c, st, nodes, now, jr, R, jinfo, slot_start, dec);
             const int jk = (jr >= 0 && tbit<TW>(st.feas, jr)) ? jr : -1;
             f_agent_update<TW, NW>(c, st, nodes, now, st.touched, mv, arrival, jk, jinfo);
             if (pending) break;
@@ -664,7 +675,7 @@ __device__ __noinline__ void episode_env_cold(const EnvArgs& E, const EpiArgs& P
 
 // one block per tile; the block's warps share the tile's envs that need work (warp w takes the w-th, (w+4)-th, ... of them)
 template <int TW>
-__global__ void __launch_bounds__(32 * EPI_WARPS) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
+__global__ void __launch_bounds__(32 * EPI_WARPS, 4) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
     extern __shared__ __align__(16) unsigned char epi_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned tile = blockIdx.x;
@@ -1164,6 +1175,7 @@ struct dcm_env {
     int device; EnvArgs E; DcmLayout L; bool have_instances;
     bool fast_step;                  // DCM_STEP_FAST=1 at dcm_create: use the experimental register-resident k_step_fast (measured slower)
     bool fused_pass;                 // DCM_PASS_FUSED=1 at dcm_create: the whole pass in the single persistent kernel k_pass (measured slower)
+    int step_lanes;                  // DCM_STEP_LANES=16|8 experiment
     bool serial_pass;                // DCM_PASS_SERIAL=1 at dcm_create: k_step, k_episode, k_obs one after the other on the caller's stream (cross-check)
     PassCtl* d_ctl; unsigned long long* d_queue; unsigned* d_qmask; unsigned epoch; int pass_grid;
     unsigned long long* d_trace; size_t trace_units;   // DCM_PASS_TRACE=1: per-unit globaltimer stamps of the last k_pass (tools/pass_trace.py)
@@ -1206,7 +1218,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!v) return fail(DCM_ERR_NOMEM, "dcm_create: host allocation failed");
     memset(v, 0, sizeof *v);
     v->device = device;
-    { const char* gs = getenv("DCM_STEP_FAST"); v->fast_step = gs && gs[0] == '1'; gs = getenv("DCM_PASS_FUSED"); v->fused_pass = gs && gs[0] == '1' && !v->fast_step; gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; }
+    { const char* gs = getenv("DCM_STEP_FAST"); v->fast_step = gs && gs[0] == '1'; gs = getenv("DCM_PASS_FUSED"); v->fused_pass = gs && gs[0] == '1' && !v->fast_step; gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; gs = getenv("DCM_STEP_LANES"); v->step_lanes = gs ? atoi(gs) : 0; if (v->step_lanes != 16 && v->step_lanes != 8) v->step_lanes = 0; }
     v->L = dcm_make_layout(A, T, M);
     DcmSoa& S = v->E.S;
     S.B = B; S.NT = (B + 31) / 32; S.A = A; S.T = T; S.M = M; S.MC = M; S.TW = T <= 64 ? 1 : (T <= 128 ? 2 : 4);
@@ -1419,9 +1431,12 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     }
     if (v->E.S.MC <= 8 && v->fast_step) {
         const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
-#define LAUNCH_FAST(tw) do { if (small) k_step_fast<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step_fast<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
+#define LAUNCH_FAST(tw) do { if (small && v->E.S.MC <= 5) k_step_fast<tw, 4, 5><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else if (small) k_step_fast<tw, 4, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step_fast<tw, 8, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
         if (TW == 1) LAUNCH_FAST(1); else if (TW == 2) LAUNCH_FAST(2); else LAUNCH_FAST(4);
 #undef LAUNCH_FAST
+    } else if (v->step_lanes) {
+        const int per = 32 / v->step_lanes; const int warps = v->E.S.NT * per; const int grid = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
+        LAUNCH_TW(v, k_step_narrow, grid, STEP_THREADS, s, v->E, F, v->step_lanes);
     } else LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
     CK(cudaGetLastError());
     v->launches++;
