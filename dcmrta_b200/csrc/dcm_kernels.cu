@@ -26,7 +26,7 @@
 using namespace dcm;
 
 #define STEP_THREADS 64
-#define OBS_THREADS 64
+#define OBS_THREADS 64          // 110 registers: capping them at 80 for 12 blocks / SM spills the load batches (92 vs 63 us, profiles/r02b)
 #define OBS_PITCH 65            // words per env in the staging tile: 60 floats + 12 mask bytes + pad (odd => conflict-free)
 #define OBS_AGENTS_PER_CHUNK 10 // 60 floats
 #define OBS_ROWS_PER_CHUNK 12   // 60 floats + 12 mask bytes
@@ -673,14 +673,15 @@ __device__ __noinline__ void episode_env_cold(const EnvArgs& E, const EpiArgs& P
     episode_env<TW>(E, P, be, lane, epi_scratch(smem, E.S.A, E.S.T, E.S.MC), O);
 }
 
-// one block per tile; the block's warps share the tile's envs that need work (warp w takes the w-th, (w+4)-th, ... of them)
+// EPI_WARPS single-warp blocks per tile: block (tile, r) takes the tile's r-th, (r + EPI_WARPS)-th, ... env that needs work.
+// One warp per block, because the blocks that do have work (about one tile in four has an env that ended, rarely two) run
+// for tens of microseconds beside k_obs and must hold as few registers as possible meanwhile; the others exit at once.
 template <int TW>
-__global__ void __launch_bounds__(32 * EPI_WARPS, 4) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
+__global__ void __launch_bounds__(32, 16) k_episode(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P) {
     extern __shared__ __align__(16) unsigned char epi_smem[];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned tile = blockIdx.x;
+    const unsigned lane = threadIdx.x;
+    const unsigned tile = blockIdx.x / EPI_WARPS, r = blockIdx.x % EPI_WARPS;
     const int B = E.S.B, A = E.S.A, T = E.S.T;
-    const EpiScratch scratch = epi_scratch(epi_smem + warp * epi_scratch_bytes(A, T, E.S.MC), A, T, E.S.MC);
     const int b = (int)(tile * 32 + lane);
     bool need = false;
     if (b < B) {
@@ -688,9 +689,10 @@ __global__ void __launch_bounds__(32 * EPI_WARPS, 4) k_episode(const __grid_cons
         else { const TC cb = make_tc(E, b); const unsigned f = EL(cb, flags, 1, 0); need = (f & ENV_DONE) && !(f & ENV_ACCOUNTED); }
     }
     unsigned todo = __ballot_sync(0xffffffffu, need);
-    const unsigned nwarps = blockDim.x >> 5;
+    if (!todo) return;
+    const EpiScratch scratch = epi_scratch(epi_smem, A, T, E.S.MC);
     for (unsigned k = 0; todo; todo &= todo - 1, ++k) {
-        if ((k % nwarps) != warp) continue;
+        if ((k % EPI_WARPS) != r) continue;
         episode_env<TW>(E, P, (int)(tile * 32 + (__ffs(todo) - 1)), lane, scratch, P.write_obs ? &P.obs : nullptr);
     }
 }
@@ -1365,13 +1367,11 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 }
 
 static int launch_episode(dcm_env* v, const EpiArgs& P, cudaStream_t s) {
-    // four warps per tile share the tile's envs that need work.  (One warp per tile, to hold fewer registers beside k_obs, was
-    // measured slower: a tile with two or three ended envs then serialises 50 us chains -- profiles/r01w.)
-    const int warps = EPI_WARPS;
-    const size_t smem = warps * epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
-    if (v->E.S.TW == 1) k_episode<1><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, P);
-    else if (v->E.S.TW == 2) k_episode<2><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, P);
-    else k_episode<4><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, P);
+    const size_t smem = epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
+    const int grid = v->E.S.NT * EPI_WARPS;
+    if (v->E.S.TW == 1) k_episode<1><<<grid, 32, smem, s>>>(v->E, P);
+    else if (v->E.S.TW == 2) k_episode<2><<<grid, 32, smem, s>>>(v->E, P);
+    else k_episode<4><<<grid, 32, smem, s>>>(v->E, P);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
