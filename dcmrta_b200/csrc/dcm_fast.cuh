@@ -28,7 +28,10 @@ template <int NW> struct Nodes { u64 w[NW]; };
 template <int NW> __device__ __forceinline__ void ld_nodes(const TC& c, Nodes<NW>& nd) {
     const ulonglong2* p = (const ulonglong2*)&ANODE(c, 0);
 #pragma unroll
-    for (int k = 0; k < NW / 2; ++k) { const ulonglong2 v = p[k]; nd.w[2 * k] = v.x; nd.w[2 * k + 1] = v.y; }
+    for (int k = 0; k < NW / 2; ++k) {                                        // the line of an env holds ANB = 32 or 64 bytes
+        if (16 * k < c.s.ANB) { const ulonglong2 v = p[k]; nd.w[2 * k] = v.x; nd.w[2 * k + 1] = v.y; }
+        else { nd.w[2 * k] = 0; nd.w[2 * k + 1] = 0; }
+    }
 }
 // the words are pinned to registers with empty asm statements: without them the compiler turns the select chains into a
 // dynamically indexed local-memory array (66 LDL per warp-step in profiles/r01m)
@@ -48,19 +51,6 @@ template <int NW> __device__ __forceinline__ void nset(Nodes<NW>& nd, int i, uns
 __device__ __forceinline__ void red_add_u16(unsigned short* p, unsigned v) {
     const size_t a = (size_t)p;
     atomicAdd((unsigned*)(a & ~(size_t)3), (a & 2) ? (v << 16) : v);
-}
-
-// visit the set bits of m N at a time, all N loads in flight before any result is used (absent bits alias the first one)
-template <int N, class V, class L, class U> __device__ __forceinline__ void for_bitsN(u64 m, int base, L load, U use) {
-    while (m) {
-        u64 bb[N]; int jj[N]; V v[N];
-#pragma unroll
-        for (int q = 0; q < N; ++q) { bb[q] = m & (0 - m); m ^= bb[q]; jj[q] = (q == 0 || bb[q]) ? base + ctz64(bb[q]) : jj[0]; }
-#pragma unroll
-        for (int q = 0; q < N; ++q) v[q] = load(jj[q]);
-#pragma unroll
-        for (int q = 0; q < N; ++q) if (bb[q]) use(bb[q], jj[q], v[q]);
-    }
 }
 
 // ---- one task's coalition in registers (member slots <= 8) -----------------------------------------------------------

@@ -113,7 +113,7 @@ template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, cons
 }
 
 // one leader decision of env b; returns the env's status bits after it
-template <int TW>
+template <int TW, int NW>
 __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b) {
     const TC c = make_tc(E, b);
     unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
@@ -125,6 +125,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         return flags;
     }
     St<TW> st; ld_state(c, st);
+    Nodes<NW> nodes; ld_nodes<NW>(c, nodes);          // route[-1] of every agent: who stands where decides the groups without reading coordinates
     double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
     unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0);
     int leader = EL(c, leader, 1, 0);
@@ -160,10 +161,11 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
         double d, tt; travel(c, AREC(c, leader, AR_X), AREC(c, leader, AR_Y), tx, ty, d, tt);
         double reward = 0.0; int nm = 1;
-        t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt;
+        const unsigned target = action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1);
+        t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt; nset<NW>(nodes, leader, target);
         pending &= ~(1ull << leader);
         if (action == 0) {                                                    // Q11: the whole remaining group follows to the depot
-            for (; g; g &= g - 1) { const int fo = ctz64(g); t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; pending &= ~(1ull << fo); }
+            for (; g; g &= g - 1) { const int fo = ctz64(g); t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; pending &= ~(1ull << fo); nset<NW>(nodes, fo, target); }
         } else {
             uint4 blk = b0;
             for (int k = 0; k < want; ++k) {
@@ -175,16 +177,27 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
                     fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
                 }
                 g &= ~(1ull << fo); pending &= ~(1ull << fo);
-                t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm;
+                t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; nset<NW>(nodes, fo, target);
             }
         }
         reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
-        t_task_update(c, st, now, nullptr);                                   // worker.py:74
-        t_agent_update(c, st, now, st.touched);                               // worker.py:76
+        auto node_of = [&](int m) -> unsigned { return nget<NW>(nodes, m); };
+        t_task_update<TW>(c, st, now, nullptr, node_of);                      // worker.py:74
+        t_agent_update<TW>(c, st, now, st.touched, node_of);                  // worker.py:76
         ++n_steps; EL(c, total, 1, 0) = EL(c, total, 1, 0) + 1;
-        if (!pending) t_advance(c, st, now, pending, flags);                  // worker.py:85, :45-51
+        if (!pending) t_advance<TW>(c, st, now, pending, flags, node_of);     // worker.py:85, :45-51
         if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
-        else leader = choose_leader(c, rng, episode, n_steps, pending, group, flags, F.leader_in, b);
+        else {
+            group = f_current_group<NW>(c, nodes, pending);                   // task_env.py:291-298
+            const int inj = F.leader_in ? F.leader_in[b] : -1;
+            if (inj >= 0) {
+                if (inj < c.A && ((group >> inj) & 1ull)) leader = inj;
+                else { flags |= ENV_ERR_LEADER; leader = ctz64(group); }
+            } else {
+                const int n = __popcll(group);
+                leader = n == 1 ? ctz64(group) : kth_bit(group, pick(draw_block(rng, episode, n_steps, 0).y, n));   // worker.py:54
+            }
+        }
     }
     if (F.next_leader) F.next_leader[b] = leader;
     if (F.reward) F.reward[b] = reward_out;
@@ -196,11 +209,11 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     return flags;
 }
 
-template <int TW>
+template <int TW, int NW>
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
-    step_env<TW>(E, F, b);
+    step_env<TW, NW>(E, F, b);
 }
 
 // experiment (DCM_STEP_LANES=16 / 8): the same step with only 16 or 8 envs per warp -- fewer divergent paths per warp, more warps
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step_narrow(const __grid_co
     const unsigned per = 32u / (unsigned)lanes;
     const int b = (int)((gw / per) * 32u + (gw % per) * (unsigned)lanes + lane);
     if (b >= E.S.B) return;
-    step_env<TW>(E, F, b);
+    step_env<TW, 8>(E, F, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -872,7 +885,7 @@ __global__ void __launch_bounds__(32 * PASS_WARPS, 7) k_pass(const __grid_consta
         if (u < NT) {                                                         // ---- step unit
             const int b = (int)(u * 32 + lane);
             unsigned flags = 0;
-            if (b < B) flags = step_env<TW>(E, F, b);
+            if (b < B) flags = step_env<TW, 8>(E, F, b);
             const bool need = b < B && (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
             unsigned todo = __ballot_sync(0xffffffffu, need);
             if (CH == 0) {                                                    // nobody observes: the step warp does the episode work itself
@@ -1437,7 +1450,12 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     } else if (v->step_lanes) {
         const int per = 32 / v->step_lanes; const int warps = v->E.S.NT * per; const int grid = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
         LAUNCH_TW(v, k_step_narrow, grid, STEP_THREADS, s, v->E, F, v->step_lanes);
-    } else LAUNCH_TW(v, k_step, grid_env(v, STEP_THREADS), STEP_THREADS, s, v->E, F);
+    } else {
+        const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
+#define LAUNCH_STEP(tw) do { if (small) k_step<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
+        if (TW == 1) LAUNCH_STEP(1); else if (TW == 2) LAUNCH_STEP(2); else LAUNCH_STEP(4);
+#undef LAUNCH_STEP
+    }
     CK(cudaGetLastError());
     v->launches++;
     // Episode accounting (+ restart with DCM_FLAG_AUTO_RESET) of the envs that just finished; the injected leader of a

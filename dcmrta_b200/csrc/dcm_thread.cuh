@@ -77,6 +77,18 @@ template <class V, class L, class U> __device__ __forceinline__ void for_bits4(u
         use(b0, j0, v0); if (b1) use(b1, j1, v1); if (b2) use(b2, j2, v2); if (b3) use(b3, j3, v3);
     }
 }
+// the same, N at a time
+template <int N, class V, class L, class U> __device__ __forceinline__ void for_bitsN(u64 m, int base, L load, U use) {
+    while (m) {
+        u64 bb[N]; int jj[N]; V v[N];
+#pragma unroll
+        for (int q = 0; q < N; ++q) { bb[q] = m & (0 - m); m ^= bb[q]; jj[q] = (q == 0 || bb[q]) ? base + ctz64(bb[q]) : jj[0]; }
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = load(jj[q]);
+#pragma unroll
+        for (int q = 0; q < N; ++q) if (bb[q]) use(bb[q], jj[q], v[q]);
+    }
+}
 template <int TW> __device__ __forceinline__ u64 all_tasks(int T, int w) {
     const int r = T - 64 * w;
     return r >= 64 ? ~0ull : (r <= 0 ? 0ull : ((1ull << r) - 1));
@@ -166,12 +178,15 @@ __device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double
 // A non-dirty task with members therefore costs one load and one compare; everything else is evaluated exactly as written
 // in the reference, including Q2 (skip after removal) and Q3 (status not refreshed after removals).
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ void abandon(const TC& c, St<TW>& st, unsigned m, int j) {
+// route[-1] of an agent: read from memory here; the fused step passes a functor that reads its register copy (dcm_fast.cuh Nodes)
+struct NodeFromMemory { const TC& c; __device__ __forceinline__ unsigned operator()(int m) const { return ANODE(c, m); } };
+
+template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c, St<TW>& st, unsigned m, int j, const NF& node_of) {
     EL(c, a_nab, c.A, m) = (unsigned short)(EL(c, a_nab, c.A, m) + 1);
-    if (ANODE(c, m) == (unsigned)j) st.member &= ~(1ull << m);      // it no longer belongs to the task it stands at
+    if (node_of((int)m) == (unsigned)j) st.member &= ~(1ull << m);           // it no longer belongs to the task it stands at
 }
 
-template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly) {
+template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of) {
     const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
     const int n = EL(c, t_nmem, T, j);                                        // :250
     const int stt = (int)EL(c, s_req, T, j) - n;                              // :252 (not refreshed after removals: Q3)
@@ -188,14 +203,14 @@ template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW
             if (newly) newly[j] = 1;
             for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
                 const unsigned m = SMEM(c, j, s);
-                if (ANODE(c, m) == (unsigned)j) st.touched |= 1ull << m;
+                if (node_of((int)m) == (unsigned)j) st.touched |= 1ull << m;
             }
         } else {                                                              // :260-265 (iterates a copy: no skipping, Q4)
             const double thr = mx - c.W;
             int wv = 0, nab = 0; double amin = CUDART_INF;
             for (int s = 0; s < n; ++s) {
                 const double a = SARR(c, j, s); const unsigned m = SMEM(c, j, s);
-                if (a <= thr) { ++nab; abandon(c, st, m, j); }
+                if (a <= thr) { ++nab; abandon(c, st, m, j, node_of); }
                 else { if (wv != s) { SARR(c, j, wv) = a; SMEM(c, j, wv) = (unsigned char)m; } ++wv; amin = a < amin ? a : amin; }
             }
             EL(c, t_nmem, T, j) = (unsigned char)wv; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
@@ -208,7 +223,7 @@ template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW
         while (i < nn) {
             const double a = SARR(c, j, i);
             if (now - a >= c.W) {                                             // :269 (Q1: false when fl(arr+W) rounded down)
-                abandon(c, st, SMEM(c, j, i), j);
+                abandon(c, st, SMEM(c, j, i), j, node_of);
                 for (int k = i; k < nn - 1; ++k) { SARR(c, j, k) = SARR(c, j, k + 1); SMEM(c, j, k) = SMEM(c, j, k + 1); }
                 --nn; ++nab;                                                  // the element that moved into slot i is skipped
             }
@@ -229,7 +244,7 @@ template <int TW> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW
     }
 }
 
-template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly) {
+template <int TW, class NF> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly, const NF& node_of) {
     const int T = c.T;
     // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished.  Both scans are skipped
     //      while the clock has not reached the per-env lower bounds (fl(now - x) >= W and now >= x are monotone in x).
@@ -240,7 +255,7 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
     for (int w = 0; w < TW; ++w) {
         hot[w] = st.dirty[w] & ~st.feas[w] & st.ne[w]; done[w] = 0;
         u64 h = 0, dn = 0;
-        if (scan_wait) for_bits4<double>(~st.feas[w] & st.ne[w], 64 * w,               // waiting coalitions: earliest arrival only
+        if (scan_wait) for_bitsN<8, double>(~st.feas[w] & st.ne[w], 64 * w,            // waiting coalitions: earliest arrival only
                           [&](int j) { return TINFO(c, j, 0); },
                           [&](u64 bit, int, double amin) { if (now - amin >= c.W) h |= bit & ~st.dirty[w]; new_amin = amin < new_amin ? amin : new_amin; });
         if (scan_fin) for_bits4<double>(st.feas[w] & ~st.fin[w], 64 * w,                // :272-274
@@ -265,7 +280,7 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
     // ---- full evaluation (rare: the task that was just joined, a coalition whose earliest member gives up)
 #pragma unroll
     for (int w = 0; w < TW; ++w)
-        for (u64 mm = hot[w]; mm; mm &= mm - 1) t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly);
+        for (u64 mm = hot[w]; mm; mm &= mm - 1) t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of);
     bool allf = true;
 #pragma unroll
     for (int w = 0; w < TW; ++w) allf = allf && st.feas[w] == all_tasks<TW>(T, w);
@@ -277,13 +292,17 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
     }
 }
 
+template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly) {
+    t_task_update<TW>(c, st, now, newly, NodeFromMemory{c});
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // agent_update (task_env.py:207-243, reactive_planning False).
 //   full:  agents in `which` are recomputed exactly as the reference does (pass st.route for its whole loop);
 //   watch: members of a feasible task that are not assigned yet only need `now >= time_start` re-checked (:232-233).
 // For every other agent the reference recomputes exactly what is already stored (see DESIGN.md "restricted update").
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which) {
+template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which, const NF& node_of) {
     const int A = c.A;
     if (now >= st.xasg) {                                                     // watch: load-only pass, only when somebody can become assigned
         u64 asg = 0; double nx = CUDART_INF;
@@ -296,7 +315,7 @@ template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St
         const u64 b0 = m & (0 - m); m ^= b0; const u64 b1 = m & (0 - m); m ^= b1;
         const u64 b2 = m & (0 - m); m ^= b2; const u64 b3 = m & (0 - m); m ^= b3;
         const int i0 = ctz64(b0), i1 = b1 ? ctz64(b1) : i0, i2 = b2 ? ctz64(b2) : i0, i3 = b3 ? ctz64(b3) : i0;
-        const unsigned n0 = ANODE(c, i0), n1 = ANODE(c, i1), n2 = ANODE(c, i2), n3 = ANODE(c, i3);
+        const unsigned n0 = node_of(i0), n1 = node_of(i1), n2 = node_of(i2), n3 = node_of(i3);
         const unsigned k0 = n0 == DCM_NODE_DEPOT ? 0u : n0, k1 = n1 == DCM_NODE_DEPOT ? 0u : n1, k2 = n2 == DCM_NODE_DEPOT ? 0u : n2, k3 = n3 == DCM_NODE_DEPOT ? 0u : n3;
         const double2 t0 = TINFO2(c, k0), t1 = TINFO2(c, k1), t2 = TINFO2(c, k2), t3 = TINFO2(c, k3);
         const double l0 = AREC(c, i0, AR_LAST), l1 = AREC(c, i1, AR_LAST), l2 = AREC(c, i2, AR_LAST), l3 = AREC(c, i3, AR_LAST);
@@ -319,19 +338,28 @@ template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St
     st.touched = 0;
 }
 
+template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which) {
+    t_agent_update<TW>(c, st, now, which, NodeFromMemory{c});
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // next_decision (task_env.py:283-289): earliest next_decision over the agents, deciders by exact equality (one pass)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 t_next_decision(const TC& c, double& t_out) {
+__device__ __forceinline__ u64 t_next_decision(const TC& c, double& t_out, const double* xlast = nullptr) {
     const int A = c.A;
     double mn = CUDART_INF; u64 mask = 0;
-#pragma unroll 8
-    for (int i = 0; i < A; ++i) {
-        const double nd = EL(c, a_nd, A, i);
-        if (nd < mn) { mn = nd; mask = 1ull << i; }                           // NaN compares false
-        else if (nd == mn) mask |= 1ull << i;                                 // :288
+    for (int i0 = 0; i0 < A; i0 += 10) {                                      // ten loads in flight per round trip
+        double v[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) v[q] = EL(c, a_nd, A, i0 + q < A ? i0 + q : i0);
+#pragma unroll
+        for (int q = 0; q < 10; ++q) if (i0 + q < A) {
+            if (v[q] < mn) { mn = v[q]; mask = 1ull << (i0 + q); }            // NaN compares false
+            else if (v[q] == mn) mask |= 1ull << (i0 + q);                    // :288
+        }
     }
     if (mask == 0) {                                                          // :285-286 everybody is NaN
+        if (xlast) { t_out = *xlast; return 0; }                              // fused protocol: the running maximum of all arrivals (St::xlast)
         double la = 0.0;
         for (int i = 0; i < A; ++i) { const double a = AREC(c, i, AR_LAST); la = a > la ? a : la; }
         t_out = la; return 0;
@@ -520,18 +548,18 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
 // ---------------------------------------------------------------------------------------------------------------
 // slot boundary (worker.py:45-51, :85): check_finished, loop condition, next_decision, clock, task_update, agent_update
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ void t_advance(const TC& c, St<TW>& st, double& now, u64& pending, unsigned& flags) {
+template <int TW, class NF> __device__ __forceinline__ void t_advance(const TC& c, St<TW>& st, double& now, u64& pending, unsigned& flags, const NF& node_of) {
     int empty_slots = 0;
     for (;;) {
-        double t; const u64 dec = t_next_decision(c, t);
+        double t; const u64 dec = t_next_decision(c, t, &st.xlast);
         if (dec == 0) {                                                       // check_finished :368-370
             now = t;
             if (t_all_returned_and_finished(c, st)) flags |= ENV_FINISHED;
         }
         if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; return; }     // worker.py:45
         pending = dec; now = t;                                               // worker.py:47-49
-        t_task_update(c, st, now, nullptr);                                   // :50
-        t_agent_update(c, st, now, st.touched);                               // :51
+        t_task_update<TW>(c, st, now, nullptr, node_of);                      // :50
+        t_agent_update<TW>(c, st, now, st.touched, node_of);                  // :51
         if (pending) return;
         // Nobody could decide.  One such slot is normal (it marks agents as returned); a second in a row means the
         // state can no longer change and the reference `while` (worker.py:45) would spin forever: stop and flag it.
