@@ -157,15 +157,52 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     }
     if (ok) {
         action_out = action;
-        // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
-        double tx, ty; node_xy(c, action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1), tx, ty);
-        double d, tt; travel(c, AREC(c, leader, AR_X), AREC(c, leader, AR_Y), tx, ty, d, tt);
-        double reward = 0.0; int nm = 1;
-        const unsigned target = action == 0 ? DCM_NODE_DEPOT : (unsigned)(action - 1);
-        t_agent_step(c, st, now, leader, action, tx, ty, d, tt, flags); reward += -tt; nset<NW>(nodes, leader, target);
-        pending &= ~(1ull << leader);
+        // every member stands where the leader stands and goes to the same node: one distance and one arrival for all (:315-318)
+        const bool to_task = action != 0; const int j = action - 1;
+        const unsigned target = to_task ? (unsigned)j : DCM_NODE_DEPOT;
+        double tx, ty; node_xy(c, target, tx, ty);
+        const double2 Lp = AREC2(c, leader, 0);
+        // the task's membership is read ONCE and then kept in registers while the members join (the reference re-reads its
+        // lists per agent_step; every load here would be another dependent round trip)
+        const bool feas_j = to_task && tbit<TW>(st.feas, j), ne_j = to_task && tbit<TW>(st.ne, j);
+        int n = 0; u64 ids0 = 0, ids1 = 0; double amin = CUDART_INF;
+        if (ne_j) {
+            n = EL(c, t_nmem, c.T, j);
+            const u64* idw = (const u64*)&SMEM(c, j, 0);
+            ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1];
+            amin = TINFO(c, j, 0);
+        }
+        const int n0 = n; bool amin_new = false, revisit = false;
+        double d, tt; travel(c, Lp.x, Lp.y, tx, ty, d, tt);
+        const double arrival = now + tt;                                      // :318
+        double reward = 0.0; int nm = 0;
+        auto move = [&](int i) {                                              // agent_step (:300-324)
+            const u64 bit = 1ull << i;
+            AREC2(c, i, 0) = make_double2(tx, ty);                            // :320
+            AREC(c, i, AR_LAST) = arrival;                                    // :318
+            atomicAdd(&AREC(c, i, AR_DIST), d);                               // :317 travel_dist += d: a reduction, no load
+            ANODE(c, i) = (unsigned char)target; nset<NW>(nodes, i, target);  // :314
+            st.route |= bit; st.touched |= bit; pending &= ~bit;
+            if (!to_task) { st.depot |= bit; st.member &= ~bit; }
+            else {
+                st.depot &= ~bit;
+                int pos = -1;                                                 // :321-322
+                for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
+                if (pos >= 0) {                                               // re-visit by a current member (Q8): last arrival wins
+                    SARR(c, j, pos) = arrival; st.member |= bit; revisit = true;
+                } else if (n < c.MC) {
+                    SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
+                    if (n < 8) ids0 = (ids0 & ~(0xffull << (8 * n))) | ((u64)(unsigned)i << (8 * n));          // (slots past n hold stale ids)
+                    else ids1 = (ids1 & ~(0xffull << (8 * (n - 8)))) | ((u64)(unsigned)i << (8 * (n - 8)));
+                    if (n == 0 || arrival < amin) { amin = arrival; amin_new = true; }
+                    ++n; st.member |= bit;
+                } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }
+            }
+            reward += -tt; ++nm;
+        };
+        move(leader);
         if (action == 0) {                                                    // Q11: the whole remaining group follows to the depot
-            for (; g; g &= g - 1) { const int fo = ctz64(g); t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; pending &= ~(1ull << fo); nset<NW>(nodes, fo, target); }
+            for (; g; g &= g - 1) move(ctz64(g));
         } else {
             uint4 blk = b0;
             for (int k = 0; k < want; ++k) {
@@ -176,8 +213,17 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
                     if ((slot & 3) == 0 || !have_b0) { blk = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2)); have_b0 = true; }
                     fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
                 }
-                g &= ~(1ull << fo); pending &= ~(1ull << fo);
-                t_agent_step(c, st, now, fo, action, tx, ty, d, tt, flags); reward += -tt; ++nm; nset<NW>(nodes, fo, target);
+                g &= ~(1ull << fo);
+                move(fo);
+            }
+        }
+        st.xlast = arrival > st.xlast ? arrival : st.xlast;
+        if (!to_task) st.xret = arrival < st.xret ? arrival : st.xret;
+        else {
+            if (n != n0) { EL(c, t_nmem, c.T, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
+            if (!feas_j) {                                                    // earliest member arrival of a waiting coalition
+                if (revisit) { amin = CUDART_INF; for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); amin = a < amin ? a : amin; } amin_new = true; }
+                if (amin_new) { TINFO(c, j, 0) = amin; st.xamin = amin < st.xamin ? amin : st.xamin; }
             }
         }
         reward_out = __double2float_rn(reward / (double)nm);                  // :337-341

@@ -244,11 +244,22 @@ template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC
     }
 }
 
-template <int TW, class NF> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly, const NF& node_of) {
+// slot_start (worker.py:50, the call right after the clock moved to `now` = min next_decision, deciders `dec`): which feasible
+// tasks finish (:272-274) is read off the deciders instead of scanning every running task.  Invariant of the fused protocol: a
+// feasible, unfinished task k always has a standing member m (the agent whose arrival made it feasible stays until
+// time_finish) and agent_update gave every standing member next_decision = time_finish (:231).  The clock is the minimum
+// next_decision, so it cannot pass time_finish_k without stopping AT it with m among the deciders, and a decider that is a
+// member of a feasible task has next_decision == time_finish == now.  Hence
+//     { k feasible, unfinished, now >= time_finish_k }  ==  { node(m) : m in dec, m member of a feasible unfinished task }.
+// st.xfin keeps covering what the rule does not: tasks that became feasible since the last slot start (only the NEXT
+// task_update call examines them, :272 is the else-branch) and states that did not come from the fused protocol
+// (dcm_import_state, granular calls) until their first slot start; a slot without deciders runs the full scan.
+template <int TW, class NF> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly, const NF& node_of,
+                                                                        bool slot_start = false, u64 dec = 0) {
     const int T = c.T;
     // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished.  Both scans are skipped
     //      while the clock has not reached the per-env lower bounds (fl(now - x) >= W and now >= x are monotone in x).
-    const bool scan_wait = now - st.xamin >= c.W, scan_fin = now >= st.xfin;
+    const bool scan_wait = now - st.xamin >= c.W, scan_fin = now >= st.xfin || (slot_start && dec == 0);
     double new_amin = CUDART_INF, new_fin = CUDART_INF;
     u64 hot[TW], done[TW];
 #pragma unroll
@@ -277,6 +288,13 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
     }
     if (scan_wait) st.xamin = new_amin;                                       // exact again (tasks evaluated below only raise theirs)
     if (scan_fin) st.xfin = new_fin;
+    if (slot_start) {
+        st.xfin = CUDART_INF;                                                 // everything feasible so far is covered by the rule from now on
+        for (u64 d = dec & st.member & ~st.depot; d; d &= d - 1) {
+            const int k = (int)node_of(ctz64(d));
+            if (tbit<TW>(st.feas, k) && !tbit<TW>(st.fin, k)) tset<TW>(st.fin, k, true);
+        }
+    }
     // ---- full evaluation (rare: the task that was just joined, a coalition whose earliest member gives up)
 #pragma unroll
     for (int w = 0; w < TW; ++w)
@@ -558,7 +576,7 @@ template <int TW, class NF> __device__ __forceinline__ void t_advance(const TC& 
         }
         if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; return; }     // worker.py:45
         pending = dec; now = t;                                               // worker.py:47-49
-        t_task_update<TW>(c, st, now, nullptr, node_of);                      // :50
+        t_task_update<TW>(c, st, now, nullptr, node_of, true, dec);           // :50
         t_agent_update<TW>(c, st, now, st.touched, node_of);                  // :51
         if (pending) return;
         // Nobody could decide.  One such slot is normal (it marks agents as returned); a second in a row means the
