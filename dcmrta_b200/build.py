@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libdcmrta_b200.so"
 SOURCES = [CSRC / "dcm_kernels.cu"]
-HEADERS = [CSRC / "dcm_thread.cuh", CSRC / "dcm_fast.cuh", CSRC / "dcm_soa.h", CSRC / "dcm_layout.h", PKG.parent / "include" / "dcmrta.h"]
+HEADERS = [CSRC / "dcm_thread.cuh", CSRC / "dcm_soa.h", CSRC / "dcm_layout.h", PKG.parent / "include" / "dcmrta.h"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

@@ -21,7 +21,6 @@
 
 #include "../../include/dcmrta.h"
 #include "dcm_thread.cuh"
-#include "dcm_fast.cuh"
 
 using namespace dcm;
 
@@ -260,159 +259,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant_
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
     step_env<TW, NW>(E, F, b);
-}
-
-// experiment (DCM_STEP_LANES=16 / 8): the same step with only 16 or 8 envs per warp -- fewer divergent paths per warp, more warps
-template <int TW>
-__global__ void __launch_bounds__(STEP_THREADS, 7) k_step_narrow(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F, int lanes) {
-    const unsigned gw = (blockIdx.x * STEP_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if ((int)lane >= lanes) return;
-    const unsigned per = 32u / (unsigned)lanes;
-    const int b = (int)((gw / per) * 32u + (gw % per) * (unsigned)lanes + lane);
-    if (b >= E.S.B) return;
-    step_env<TW, 8>(E, F, b);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_step_fast: the same decision as k_step with the chosen task, the node ids and the per-env masks held in registers
-// (dcm_fast.cuh).  Used whenever the handle has at most 8 member slots per task; k_step stays the generic version.
-// ---------------------------------------------------------------------------------------------------------------
-template <int TW, int NW, int MCK>
-__global__ void __maxnreg__(144) k_step_fast(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
-    const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (b >= E.S.B) return;
-    const TC c = make_tc(E, b);
-    // ---- round 1: everything that does not depend on the action
-    unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
-    St<TW> st; ld_state(c, st);
-    Nodes<NW> nodes; ld_nodes<NW>(c, nodes);
-    double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
-    unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0);
-    int leader = EL(c, leader, 1, 0);
-    const int action_in = F.policy == 0 ? F.action[b] : 0;
-    if (flags & ENV_DONE) {                                                   // finished earlier and not restarted: untouched
-        if (F.next_leader) F.next_leader[b] = -1;
-        if (F.reward) F.reward[b] = 0.f;
-        if (F.done) F.done[b] = 1;
-        if (F.used_action) F.used_action[b] = -1;
-        return;
-    }
-    const Rng rng{E.seed, E.first_gid + (u64)b};
-    float reward_out = 0.f; int action_out = -1;
-    bool ok = true;
-    uint4 b0 = make_uint4(0, 0, 0, 0);
-    bool have_b0 = false;
-    int action;
-    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
-    else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
-    else action = action_in;
-    if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
-    const bool to_task = ok && action != 0; const int j = to_task ? action - 1 : 0;
-    // ---- round 2: the chosen task, its coordinates, the leader's location
-    TaskR<MCK> R; r_load<TW, MCK>(c, st, j, to_task, R);
-    double tx, ty; node_xy(c, to_task ? (unsigned)j : DCM_NODE_DEPOT, tx, ty);
-    const double2 L = AREC2(c, ok ? leader : 0, 0);
-    int want = 0; u64 g = group & ~(1ull << leader);                          // task_env.py:328
-    const int* fp = F.followers ? F.followers + (size_t)b * F.fstride : nullptr;
-    if (ok) {
-        const int vacancy = action == 0 ? __popcll(group) : R.status0;        // :327
-        if (vacancy > 1) { const int avail = __popcll(g); want = vacancy - 1 < avail ? vacancy - 1 : avail; }   // :330-331
-        if (fp && action != 0) {                                              // validate injected followers before touching state
-            u64 gg = g;
-            for (int k = 0; k < want && ok; ++k) {
-                const int fo = k < F.fstride ? fp[k] : -1;
-                if (fo < 0 || fo >= c.A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
-            }
-            if (ok && want < F.fstride && fp[want] >= 0) ok = false;
-            if (!ok) flags |= ENV_ERR_FOLLOW;
-        }
-    }
-    if (ok) {
-        action_out = action;
-        // every member stands where the leader stands and goes to the same node: one distance for all (:315-317)
-        double d, tt; travel(c, L.x, L.y, tx, ty, d, tt);
-        const double arrival = now + tt;                                      // :318
-        double reward = 0.0; int nm = 0; u64 mv = 0; bool appended = false;
-        auto move = [&](int i) {                                              // agent_step (:300-324)
-            const u64 bit = 1ull << i;
-            AREC2(c, i, 0) = make_double2(tx, ty);                            // :320
-            AREC(c, i, AR_LAST) = arrival;                                    // :318
-            atomicAdd(&AREC(c, i, AR_DIST), d);                               // :317 travel_dist += d, no load
-            const unsigned nn = to_task ? (unsigned)j : DCM_NODE_DEPOT;
-            ANODE(c, i) = (unsigned char)nn; nset<NW>(nodes, i, nn);          // :314
-            st.route |= bit; st.touched |= bit; mv |= bit; pending &= ~bit;
-            if (!to_task) { st.depot |= bit; st.member &= ~bit; }
-            else { st.depot &= ~bit; r_join<TW, MCK>(c, st, R, i, arrival, flags, appended); }
-            reward += -tt; ++nm;
-        };
-        move(leader);
-        if (action == 0) {                                                    // Q11: the whole remaining group follows to the depot
-            for (; g; g &= g - 1) move(ctz64(g));
-        } else {
-            uint4 blk = b0;
-            for (int k = 0; k < want; ++k) {
-                int fo;
-                if (fp) fo = fp[k];                                           // injected (trace replay)
-                else {                                                        // :331 uniform without replacement
-                    const int slot = 2 + k;
-                    if ((slot & 3) == 0 || !have_b0) { blk = draw_block(rng, episode, n_steps, (unsigned)(slot >> 2)); have_b0 = true; }
-                    fo = kth_bit(g, pick(word_of(blk, slot & 3), __popcll(g)));
-                }
-                g &= ~(1ull << fo);
-                move(fo);
-            }
-        }
-        if (to_task) {
-            if (appended) { tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
-            if (!tbit<TW>(st.feas, j) && R.n > 0 && R.wr) {                   // earliest member arrival of a waiting coalition
-                const double am = r_amin(R);
-                if (!R.had || am != R.info.x) TINFO(c, j, 0) = am;
-                R.info.x = am; st.xamin = am < st.xamin ? am : st.xamin;
-            }
-        }
-        reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
-        st.xlast = arrival > st.xlast ? arrival : st.xlast;
-        if (!to_task) st.xret = arrival < st.xret ? arrival : st.xret;
-        ++n_steps; atomicAdd(&EL(c, total, 1, 0), 1u);
-        // One loop body serves the updates after the decision (worker.py:74,76) and the updates of every slot start that
-        // follows (worker.py:45-51, :85) -- a single copy of the code in the instruction cache.
-        double2 jinfo = R.info;
-        int jr = to_task ? j : -1; bool slot_start = false; u64 dec = 0; int empty_slots = 0;
-        for (;;) {
-            f_task_update<TW, NW, MCK>(c, st, nodes, now, jr, R, jinfo, slot_start, dec);
-            const int jk = (jr >= 0 && tbit<TW>(st.feas, jr)) ? jr : -1;
-            f_agent_update<TW, NW>(c, st, nodes, now, st.touched, mv, arrival, jk, jinfo);
-            if (pending) break;
-            if (slot_start && ++empty_slots >= 2) { flags |= ENV_DONE | ENV_STUCK; break; }   // see t_advance
-            double t; dec = f_next_decision<TW>(c, st, t);                    // :283-289
-            if (dec == 0) {                                                   // check_finished :368-370
-                now = t;
-                if (t_all_returned_and_finished(c, st)) flags |= ENV_FINISHED;
-            }
-            if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; break; }     // worker.py:45
-            pending = dec; now = t;                                           // worker.py:47-49
-            slot_start = true; jr = -1; mv = 0;
-        }
-        if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
-        else {
-            group = f_current_group<NW>(c, nodes, pending);                   // :291-298
-            const int inj = F.leader_in ? F.leader_in[b] : -1;
-            if (inj >= 0) {
-                if (inj < c.A && ((group >> inj) & 1ull)) leader = inj;
-                else { flags |= ENV_ERR_LEADER; leader = ctz64(group); }
-            } else {
-                const int n = __popcll(group);
-                leader = n == 1 ? ctz64(group) : kth_bit(group, pick(draw_block(rng, episode, n_steps, 0).y, n));   // worker.py:54
-            }
-        }
-        st_state_all(c, st);
-    }
-    if (F.next_leader) F.next_leader[b] = leader;
-    if (F.reward) F.reward[b] = reward_out;
-    if (F.done) F.done[b] = (flags & ENV_DONE) ? 1 : 0;
-    if (F.used_action) F.used_action[b] = action_out;
-    EL(c, now, 1, 0) = now; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = n_steps;
-    EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = flags; EL(c, ended, 1, 0) = (flags & ENV_DONE) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1234,9 +1080,7 @@ static int fail_cuda(cudaError_t e, const char* where) {
 
 struct dcm_env {
     int device; EnvArgs E; DcmLayout L; bool have_instances;
-    bool fast_step;                  // DCM_STEP_FAST=1 at dcm_create: use the experimental register-resident k_step_fast (measured slower)
     bool fused_pass;                 // DCM_PASS_FUSED=1 at dcm_create: the whole pass in the single persistent kernel k_pass (measured slower)
-    int step_lanes;                  // DCM_STEP_LANES=16|8 experiment
     bool serial_pass;                // DCM_PASS_SERIAL=1 at dcm_create: k_step, k_episode, k_obs one after the other on the caller's stream (cross-check)
     PassCtl* d_ctl; unsigned long long* d_queue; unsigned* d_qmask; unsigned epoch; int pass_grid;
     unsigned long long* d_trace; size_t trace_units;   // DCM_PASS_TRACE=1: per-unit globaltimer stamps of the last k_pass (tools/pass_trace.py)
@@ -1279,7 +1123,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!v) return fail(DCM_ERR_NOMEM, "dcm_create: host allocation failed");
     memset(v, 0, sizeof *v);
     v->device = device;
-    { const char* gs = getenv("DCM_STEP_FAST"); v->fast_step = gs && gs[0] == '1'; gs = getenv("DCM_PASS_FUSED"); v->fused_pass = gs && gs[0] == '1' && !v->fast_step; gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; gs = getenv("DCM_STEP_LANES"); v->step_lanes = gs ? atoi(gs) : 0; if (v->step_lanes != 16 && v->step_lanes != 8) v->step_lanes = 0; }
+    { const char* gs = getenv("DCM_PASS_FUSED"); v->fused_pass = gs && gs[0] == '1'; gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; }
     v->L = dcm_make_layout(A, T, M);
     DcmSoa& S = v->E.S;
     S.B = B; S.NT = (B + 31) / 32; S.A = A; S.T = T; S.M = M; S.MC = M; S.TW = T <= 64 ? 1 : (T <= 128 ? 2 : 4);
@@ -1488,15 +1332,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
         v->launches++;
         return DCM_OK;
     }
-    if (v->E.S.MC <= 8 && v->fast_step) {
-        const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
-#define LAUNCH_FAST(tw) do { if (small && v->E.S.MC <= 5) k_step_fast<tw, 4, 5><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else if (small) k_step_fast<tw, 4, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step_fast<tw, 8, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
-        if (TW == 1) LAUNCH_FAST(1); else if (TW == 2) LAUNCH_FAST(2); else LAUNCH_FAST(4);
-#undef LAUNCH_FAST
-    } else if (v->step_lanes) {
-        const int per = 32 / v->step_lanes; const int warps = v->E.S.NT * per; const int grid = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
-        LAUNCH_TW(v, k_step_narrow, grid, STEP_THREADS, s, v->E, F, v->step_lanes);
-    } else {
+    {
         const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
 #define LAUNCH_STEP(tw) do { if (small) k_step<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
         if (TW == 1) LAUNCH_STEP(1); else if (TW == 2) LAUNCH_STEP(2); else LAUNCH_STEP(4);

@@ -35,9 +35,9 @@ struct TC {
 // of 65,536 envs is ~400 MB).  DcmSoa pointers address tile 0.
 #define TB(c, arr) ((decltype(+(c).s.arr))((char*)(c).s.arr + (c).tb))
 // row-major arrays: element (row k) of this thread's env in an array with K rows per tile
-#define EL(c, arr, K, k) (TB(c, arr)[((unsigned)(k) << 5) + (c).l])
+#define EL(c, arr, K, k) (TB(c, arr)[((void)(K), ((unsigned)(k) << 5)) + (c).l])    // K (rows per tile) documents the array's extent
 // lane-contiguous arrays
-#define LANE_ROW(c, K, k) ((size_t)(((unsigned)(k) << 5) + (c).l))
+#define LANE_ROW(c, K, k) ((void)(K), (size_t)(((unsigned)(k) << 5) + (c).l))
 #define SARR(c, j, sl) (TB(c, t_slot_arr)[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
 #define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * (unsigned)(c).s.MCB + (unsigned)(sl)])   // member id of slot s
 #define TINFO(c, j, k) (TB(c, t_info)[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
@@ -168,6 +168,31 @@ __device__ __forceinline__ void node_xy(const TC& c, unsigned node, double& x, d
 }
 __device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double by) { return ax < bx || (ax == bx && ay < by); }
 
+// ---- packed node ids of all agents of one env, in registers ------------------------------------------------------
+template <int NW> struct Nodes { u64 w[NW]; };
+template <int NW> __device__ __forceinline__ void ld_nodes(const TC& c, Nodes<NW>& nd) {
+    const ulonglong2* p = (const ulonglong2*)&ANODE(c, 0);
+#pragma unroll
+    for (int k = 0; k < NW / 2; ++k) {                                        // the line of an env holds ANB = 32 or 64 bytes
+        if (16 * k < c.s.ANB) { const ulonglong2 v = p[k]; nd.w[2 * k] = v.x; nd.w[2 * k + 1] = v.y; }
+        else { nd.w[2 * k] = 0; nd.w[2 * k + 1] = 0; }
+    }
+}
+// the words are pinned to registers with empty asm statements: without them the compiler turns the select chains into a
+// dynamically indexed local-memory array (66 LDL per warp-step, profiles/r01o)
+template <int NW> __device__ __forceinline__ unsigned nget(const Nodes<NW>& nd, int i) {
+    u64 w = nd.w[0];
+#pragma unroll
+    for (int k = 1; k < NW; ++k) { u64 wk = nd.w[k]; asm("" : "+l"(wk)); w = (i >> 3) == k ? wk : w; }
+    return (unsigned)(w >> (8 * (i & 7))) & 0xffu;
+}
+template <int NW> __device__ __forceinline__ void nset(Nodes<NW>& nd, int i, unsigned v) {
+    const int sh = 8 * (i & 7); const u64 m = 0xffull << sh, val = (u64)v << sh;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { u64 wk = nd.w[k]; asm("" : "+l"(wk)); nd.w[k] = (i >> 3) == k ? ((wk & ~m) | val) : wk; }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // task_update (task_env.py:245-281).  newly: optional per-env [T] u8 (plain row-major global) of ids that became feasible.
 //
@@ -178,7 +203,7 @@ __device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double
 // A non-dirty task with members therefore costs one load and one compare; everything else is evaluated exactly as written
 // in the reference, including Q2 (skip after removal) and Q3 (status not refreshed after removals).
 // ---------------------------------------------------------------------------------------------------------------
-// route[-1] of an agent: read from memory here; the fused step passes a functor that reads its register copy (dcm_fast.cuh Nodes)
+// route[-1] of an agent: read from memory here; the fused step passes a functor that reads its register copy (Nodes below)
 struct NodeFromMemory { const TC& c; __device__ __forceinline__ unsigned operator()(int m) const { return ANODE(c, m); } };
 
 template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c, St<TW>& st, unsigned m, int j, const NF& node_of) {
@@ -408,6 +433,18 @@ __device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending) {
     return g;
 }
 
+// get_unique_group (task_env.py:291-298) for the group that acts next.  Agents that stand at the same node have the same
+// location, so when every pending agent stands at one node (always, in every recorded trajectory: SURVEY App. A Q10) the
+// group is the pending set and no coordinate is read; otherwise the coordinates decide (t_current_group).
+template <int NW> __device__ __forceinline__ u64 f_current_group(const TC& c, const Nodes<NW>& nodes, u64 pending) {
+    if ((pending & (pending - 1)) == 0) return pending;
+    const unsigned first = nget<NW>(nodes, ctz64(pending));
+    bool same = true;
+    for (u64 m = pending & (pending - 1); m; m &= m - 1) same = same && nget<NW>(nodes, ctz64(m)) == first;
+    return same ? pending : t_current_group(c, pending);
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // agent_step for one member (task_env.py:300-324).  (d, tt) = distance / travel time to the target from the member's
 // location, (tx, ty) = target coordinate.
@@ -419,7 +456,7 @@ __device__ __forceinline__ void travel(const TC& c, double ax, double ay, double
 }
 template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<TW>& st, double now, int i, int action, double tx, double ty,
                                                               double d, double tt, unsigned& flags) {
-    const int A = c.A, T = c.T;
+    const int T = c.T;
     const u64 bit = 1ull << i;
     const int j = action - 1;
     const bool to_task = action != 0, feas = to_task && tbit<TW>(st.feas, j), nonempty = to_task && tbit<TW>(st.ne, j);

@@ -234,13 +234,12 @@ def test_shard_invariance():
     big.close(); small.close()
 
 
-@pytest.mark.parametrize("variant", ["DCM_PASS_SERIAL", "DCM_PASS_FUSED", "DCM_STEP_FAST"])
+@pytest.mark.parametrize("variant", ["DCM_PASS_SERIAL", "DCM_PASS_FUSED"])
 @pytest.mark.parametrize("shape,policy", [((20, 50), "random"), ((20, 50), "greedy"), ((10, 20), "random"), ((50, 200), "random"), ((30, 100), "greedy")])
 def test_fused_pass_equals_split_kernels(shape, policy, variant, monkeypatch):
     """The default pass (k_step, then k_episode on a side stream writing the restarted envs' observations from registers
-    beside k_obs) against (a) the three kernels one after the other with k_obs building every observation from memory,
-    (b) the single persistent kernel k_pass (tile completion queue) and (c) the experimental register-resident k_step_fast:
-    raw records (every field, bookkeeping bits included), observations, rewards, leaders and metrics identical on a batch
+    beside k_obs) against (a) the three kernels one after the other with k_obs building every observation from memory and
+    (b) the single persistent kernel k_pass (tile completion queue): raw records (every field, bookkeeping bits included), observations, rewards, leaders and metrics identical on a batch
     that is not a multiple of the tile size."""
     from dcmrta_b200 import BatchedTaskEnv
     A, T = shape

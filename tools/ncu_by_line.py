@@ -61,7 +61,7 @@ def func_table(path):
     except OSError:
         pass
     return tab
-tabs = {f: func_table(os.path.join("dcmrta_b200/csrc", f)) for f in ("dcm_thread.cuh", "dcm_fast.cuh", "dcm_kernels.cu")}
+tabs = {f: func_table(os.path.join("dcmrta_b200/csrc", f)) for f in ("dcm_thread.cuh", "dcm_kernels.cu")}
 fagg = collections.defaultdict(collections.Counter)
 for (f, ln), c in agg.items():
     name = f
