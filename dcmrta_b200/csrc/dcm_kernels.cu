@@ -44,6 +44,7 @@ struct EnvArgs {
 struct StepArgs {
     const int* action; const int* followers; int fstride; const int* leader_in; int policy;
     int* next_leader; float* reward; unsigned char* done; int* used_action;
+    unsigned* elist; unsigned* ecount; unsigned* ecount_next;   // ended-env list of this pass (k_episode_list), its counter, and the next pass's counter to clear
 };
 
 struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask;
@@ -257,8 +258,19 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
 template <int TW, int NW>
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (b >= E.S.B) return;
-    step_env<TW, NW>(E, F, b);
+    unsigned flags = 0;
+    if (b < E.S.B) flags = step_env<TW, NW>(E, F, b);
+    if (F.elist) {                                                            // envs whose episode just ended: one warp-aggregated append per warp that has any
+        const bool need = (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
+        const unsigned m = __ballot_sync(0xffffffffu, need), lane = threadIdx.x & 31u;
+        if (m) {
+            unsigned base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(F.ecount, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (need) F.elist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)b;
+        }
+        if (b == 0) *F.ecount_next = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -600,6 +612,19 @@ __global__ void __launch_bounds__(32, 16) k_episode(const __grid_constant__ EnvA
         if ((k % EPI_WARPS) != r) continue;
         episode_env<TW>(E, P, (int)(tile * 32 + (__ffs(todo) - 1)), lane, scratch, P.write_obs ? &P.obs : nullptr);
     }
+}
+
+// The step path's variant: k_step appended the envs whose episode just ended to a list (about 1 env in 150 per pass), so the
+// grid is a few blocks per SM instead of EPI_WARPS blocks per tile -- dispatching 8,192 mostly empty blocks cost ~25 us beside
+// k_obs (profiles/r03a_timeline.txt).  Envs are independent: the order of the list does not matter.
+template <int TW>
+__global__ void __launch_bounds__(32, 16) k_episode_list(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P, const unsigned* elist, const unsigned* ecount) {
+    extern __shared__ __align__(16) unsigned char epi_smem[];
+    const unsigned n = *ecount;
+    if (blockIdx.x >= n) return;
+    const EpiScratch scratch = epi_scratch(epi_smem, E.S.A, E.S.T, E.S.MC);
+    for (unsigned k = blockIdx.x; k < n; k += gridDim.x)
+        episode_env<TW>(E, P, (int)elist[k], threadIdx.x, scratch, P.write_obs ? &P.obs : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1093,6 +1118,7 @@ struct dcm_env {
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
     cudaStream_t hstream;
     cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // k_episode runs beside k_obs
+    unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
     uint64_t launches;
 };
 
@@ -1156,6 +1182,10 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&v->side, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_elist, (size_t)B * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_ecount, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(v->d_ecount, 0, 2 * sizeof(unsigned));
+    { const char* gs = getenv("DCM_EPISODE_DENSE"); v->dense_episode = gs && gs[0] == '1'; }
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_ctl, sizeof(PassCtl));
     if (e == cudaSuccess) e = cudaMemset(v->d_ctl, 0, sizeof(PassCtl));
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_queue, (size_t)NT * sizeof(unsigned long long));
@@ -1186,7 +1216,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
 int dcm_destroy(dcm_env* v) {
     if (!v) return DCM_OK;
     DeviceGuard g(v->device);
-    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_ctl); cudaFree(v->d_queue); cudaFree(v->d_qmask); cudaFree(v->d_trace); cudaFree(v->d_cursor); cudaFree(v->d_record);
+    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_ctl); cudaFree(v->d_queue); cudaFree(v->d_qmask); cudaFree(v->d_trace); cudaFree(v->d_cursor); cudaFree(v->d_record); cudaFree(v->d_elist); cudaFree(v->d_ecount);
     cudaFree(v->d_action); cudaFree(v->d_agent); cudaFree(v->d_task); cudaFree(v->d_mask); cudaFree(v->d_leader); cudaFree(v->d_reward); cudaFree(v->d_done);
     if (v->hstream) cudaStreamDestroy(v->hstream);
     if (v->side) cudaStreamDestroy(v->side);
@@ -1269,6 +1299,17 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
     return DCM_OK;
 }
 
+static int launch_episode_list(dcm_env* v, const EpiArgs& P, const unsigned* ecount, cudaStream_t s) {
+    const size_t smem = epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
+    int grid = 148 * 8; if (grid > v->E.S.B) grid = v->E.S.B;
+    if (v->E.S.TW == 1) k_episode_list<1><<<grid, 32, smem, s>>>(v->E, P, v->d_elist, ecount);
+    else if (v->E.S.TW == 2) k_episode_list<2><<<grid, 32, smem, s>>>(v->E, P, v->d_elist, ecount);
+    else k_episode_list<4><<<grid, 32, smem, s>>>(v->E, P, v->d_elist, ecount);
+    CK(cudaGetLastError());
+    v->launches++;
+    return DCM_OK;
+}
+
 static int launch_episode(dcm_env* v, const EpiArgs& P, cudaStream_t s) {
     const size_t smem = epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
     const int grid = v->E.S.NT * EPI_WARPS;
@@ -1332,6 +1373,9 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
         v->launches++;
         return DCM_OK;
     }
+    const bool use_list = !v->dense_episode;
+    unsigned* ecount = nullptr;
+    if (use_list) { const unsigned p = v->pass_no++ & 1u; ecount = v->d_ecount + p; F.elist = v->d_elist; F.ecount = ecount; F.ecount_next = v->d_ecount + (p ^ 1u); }
     {
         const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
 #define LAUNCH_STEP(tw) do { if (small) k_step<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
@@ -1345,7 +1389,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     // chains (~30 us) and k_obs is bandwidth-bound (~60 us): they run side by side.  k_obs leaves out the envs k_step marked
     // `ended`; k_episode writes the observation of the envs it restarts from registers (episode_env).
     if (v->serial_pass || !want_obs) {
-        int rc = launch_episode(v, P, s);
+        int rc = use_list ? launch_episode_list(v, P, ecount, s) : launch_episode(v, P, s);
         if (rc) return rc;
         if (want_obs) return launch_obs(v, O, s);
         return DCM_OK;
@@ -1353,7 +1397,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     CK(cudaEventRecord(v->ev_fork, s));
     CK(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
     P.obs = O; P.write_obs = (v->E.cflags & DCM_FLAG_AUTO_RESET) ? 1 : 0;
-    int rc = launch_episode(v, P, v->side);
+    int rc = use_list ? launch_episode_list(v, P, ecount, v->side) : launch_episode(v, P, v->side);
     if (rc) return rc;
     CK(cudaEventRecord(v->ev_join, v->side));
     O.skip_ended = 1;
