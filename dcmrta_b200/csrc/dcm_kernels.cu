@@ -76,7 +76,8 @@ __device__ __noinline__ void t_generate(const TC& c, u64 seed, u64 gid, unsigned
         const uint4 b = philox(g0, g1, instance, 0x80000001u + 2u * j, k0, k1);
         EL(c, s_tx, c.T, j) = u01(a.x, a.y); EL(c, s_ty, c.T, j) = u01(a.z, a.w);          // task_env.py:69
         EL(c, s_req, c.T, j) = (unsigned char)(1 + pick(b.x, c.s.M));                      // :71
-        EL(c, s_dur, c.T, j) = random_duration ? u01(b.y, b.z) * max_duration : max_duration;   // :70
+        const double du = random_duration ? u01(b.y, b.z) * max_duration : max_duration;       // :70
+        EL(c, s_dur, c.T, j) = du; EL(c, s_dur32, c.T, j) = __double2float_rn(du);
     }
     const uint4 a = philox(g0, g1, instance, 0xFFFFFFFFu, k0, k1);
     EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w);                // :67
@@ -162,6 +163,9 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         const unsigned target = to_task ? (unsigned)j : DCM_NODE_DEPOT;
         double tx, ty; node_xy(c, target, tx, ty);
         const double2 Lp = AREC2(c, leader, 0);
+        // observation cache of the movers (AOBS2, dcm_thread.cuh): what their agent row shows of the task they now stand at
+        double2 aobs = make_double2(0.0, 0.0);
+        if (to_task) { if (tbit<TW>(st.feas, j)) aobs = TINFO2(c, j); else aobs.y = 0.0 + EL(c, s_dur, c.T, j); }
         // the task's membership is read ONCE and then kept in registers while the members join (the reference re-reads its
         // lists per agent_step; every load here would be another dependent round trip)
         const bool feas_j = to_task && tbit<TW>(st.feas, j), ne_j = to_task && tbit<TW>(st.ne, j);
@@ -185,7 +189,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
             st.route |= bit; st.touched |= bit; pending &= ~bit;
             if (!to_task) { st.depot |= bit; st.member &= ~bit; }
             else {
-                st.depot &= ~bit;
+                st.depot &= ~bit; AOBS2(c, i) = aobs;
                 int pos = -1;                                                 // :321-322
                 for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
                 if (pos >= 0) {                                               // re-visit by a current member (Q8): last arrival wins
@@ -538,7 +542,7 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
             tx = u01(a.x, a.y); ty = u01(a.z, a.w);                            // task_env.py:69
             rq = 1u + (unsigned)pick(b2.x, E.S.M);                            // :71
             du = E.gen_random_duration ? u01(b2.y, b2.z) * E.gen_max_duration : E.gen_max_duration;   // :70
-            EL(c, s_tx, T, j) = tx; EL(c, s_ty, T, j) = ty; EL(c, s_req, T, j) = (unsigned char)rq; EL(c, s_dur, T, j) = du;
+            EL(c, s_tx, T, j) = tx; EL(c, s_ty, T, j) = ty; EL(c, s_req, T, j) = (unsigned char)rq; EL(c, s_dur, T, j) = du; EL(c, s_dur32, T, j) = __double2float_rn(du);
         } else { rq = EL(c, s_req, T, j); if (obs) { tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j); du = EL(c, s_dur, T, j); } }
         EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)rq; EL(c, t_nab, T, j) = 0;
         if (obs) {
@@ -758,6 +762,191 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_obs_tile: the observation builder of the step path.  ONE BLOCK PER TILE of 32 envs, two blocks per SM, and the TMA
+// engine moves the bytes in both directions:
+//   in   one thread issues cp.async.bulk global -> shared for the tile's rows of s_tx, s_ty, t_status, s_req, the agent
+//        records and the observation cache a_obs (each is one contiguous span of the tile-major arena) against an mbarrier;
+//        nothing is held in registers while they fly.  Meanwhile every warp loads the per-env scalars of its role (leader,
+//        masks, clock; the fp32 durations of its rows).  No load depends on another: the block waits ONE round trip.
+//        (The cache a_obs is what makes that possible: the agent rows need time_start / time_finish of the task an agent
+//        stands at, a gather that depends on the node ids; the step keeps its result per agent instead.)
+//   rows warp <-> row chunk, lane <-> env, operands from shared memory, rows written in place into the staged output:
+//        agent rows [32][6A], task rows [32][5(T+1)] floats and mask [32][T+1] bytes are exactly the three contiguous
+//        spans of the policy tensors that belong to the tile.
+//   out  one thread hands each span to cp.async.bulk shared -> global: no flush loop and no store instructions.
+// A tile with an env that is left out (its episode ended: k_episode_list writes its observation meanwhile; no leader; past
+// B) or a destination that is not 16-byte aligned is copied warp by warp, env by env, instead.  Shapes whose tile does not
+// fit twice in an SM's shared memory use k_obs.
+// ---------------------------------------------------------------------------------------------------------------
+#define OBS_TILE_MAX_WARPS 8
+struct ObsTileSmem { unsigned oA, oT, oM, iX, iY, iR, iO, iS, iQ, bar, total; };
+__host__ __device__ inline ObsTileSmem obs_tile_smem(int A, int T) {
+    ObsTileSmem L; unsigned o = 0;
+    auto take = [&](unsigned bytes) { const unsigned at = o; o += (bytes + 15u) & ~15u; return at; };
+    L.oA = take(32u * 6 * A * 4); L.oT = take(32u * 5 * (T + 1) * 4); L.oM = take(32u * (T + 1));
+    L.iX = take(256u * T); L.iY = take(256u * T); L.iR = take(1024u * A); L.iO = take(512u * A); L.iS = take(32u * T); L.iQ = take(32u * T);
+    L.bar = take(8); L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+template <int TW>
+__global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 2) k_obs_tile(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O, int use_bulk, unsigned long long* trace) {
+    extern __shared__ __align__(128) unsigned char obs_smem[];
+    const int B = E.S.B, A = E.S.A, T = E.S.T;
+    const unsigned tile_id = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const ObsTileSmem L = obs_tile_smem(A, T);
+    float* sA = (float*)(obs_smem + L.oA); float* sT = (float*)(obs_smem + L.oT); unsigned char* sM = obs_smem + L.oM;
+    const double* iX = (const double*)(obs_smem + L.iX); const double* iY = (const double*)(obs_smem + L.iY);
+    const double2* iR = (const double2*)(obs_smem + L.iR); const double2* iO = (const double2*)(obs_smem + L.iO);
+    const signed char* iS = (const signed char*)(obs_smem + L.iS); const unsigned char* iQ = obs_smem + L.iQ;
+    const unsigned bar = smem_u32(obs_smem + L.bar);
+    const int b = (int)(tile_id * 32 + lane);
+    const TC c = make_tc(E, b < B ? b : B - 1);
+    auto stamp = [&](int k) { if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)tile_id * 8 + k] = t; } };
+    stamp(0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                                   // the tile's rows: one contiguous span per array
+        const TC c0 = make_tc(E, (int)(tile_id * 32));                        // lane 0 of the tile
+        const unsigned bytes = 256u * T * 2 + 1024u * A + 512u * A + 32u * T * 2;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        bulk_load(obs_smem + L.iR, &AREC2(c0, 0, 0), 1024u * A, bar);
+        bulk_load(obs_smem + L.iO, &AOBS2(c0, 0), 512u * A, bar);
+        bulk_load(obs_smem + L.iX, &EL(c0, s_tx, T, 0), 256u * T, bar);
+        bulk_load(obs_smem + L.iY, &EL(c0, s_ty, T, 0), 256u * T, bar);
+        bulk_load(obs_smem + L.iS, &EL(c0, t_status, T, 0), 32u * T, bar);
+        bulk_load(obs_smem + L.iQ, &EL(c0, s_req, T, 0), 32u * T, bar);
+    }
+    // per-env scalars of the warp's first chunk, all issued at once and before the leader is known
+    const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
+    int leader = -1; unsigned ended = 0;
+    if (b < B) { leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0); if (O.skip_ended) ended = EL(c, ended, 1, 0); }
+    u64 open[TW]; u64 route = 0, depot = 0, assigned = 0; double now = 0.0, dpx = 0.0, dpy = 0.0; float dq[OBS_ROWS_PER_CHUNK];
+    auto agent_scalars = [&]() { route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); now = EL(c, now, 1, 0); };
+    auto task_scalars = [&](int chunk) {
+        const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
+#pragma unroll
+        for (int w = 0; w < TW; ++w) open[w] = EL(c, m_open, TW, w);
+        if (r0 == 0) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
+#pragma unroll
+        for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) { const int jj = r0 + q; dq[q] = EL(c, s_dur32, T, (jj > 0 && jj <= T) ? jj - 1 : 0); }
+    };
+    if ((int)warp < NA) agent_scalars(); else if ((int)warp < NA + NR) task_scalars((int)warp);
+    if (ended) leader = -1;
+    const bool ok = leader >= 0 && leader < A;
+    const unsigned valid = __ballot_sync(0xffffffffu, ok);                    // the same in every warp of the block
+    stamp(1);
+    mbar_wait(bar, 0);                                                        // (also: never leave with copies in flight into this block's shared memory)
+    stamp(4);
+    if (!valid) return;
+    for (int chunk = (int)warp; chunk < NA + NR; chunk += (int)nwarps) {
+        if (chunk < NA) {                                                     // ---- agent rows (:165-180)
+            if (!O.agent_obs) continue;
+            if (chunk != (int)warp) agent_scalars();
+            if (!ok) continue;
+            const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
+            const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
+            const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+            float* mine = sA + lane * 6 * A + 6 * c0;
+#pragma unroll 5
+            for (int q = 0; q < na; ++q) {
+                const int i = c0 + q; const u64 bit = 1ull << i; const unsigned at = ((unsigned)i << 5) + lane;
+                const double2 xy = iR[at << 1];
+                double travel_t = 0.0, wait = 0.0, remain = 0.0;
+                if ((route & bit) && !(depot & bit)) {                        // :168
+                    const double arr = iR[(at << 1) + 1].x;
+                    const double2 tt = iO[at];                                // {time_start or 0 (Q6), fl(time_start + time)}
+                    const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;                         // :169
+                    if (now <= tt.x) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }     // :170
+                    if (now >= tt.x) { const double qv = tt.y - now; remain = qv < 0.0 ? 0.0 : qv; }  // :171
+                }
+                float2* r = (float2*)(mine + 6 * q);                          // :176-177 (8-byte aligned: even offsets)
+                r[0] = make_float2(__double2float_rn(travel_t), __double2float_rn(remain));
+                r[1] = make_float2(__double2float_rn(wait), __double2float_rn(Lp.x - xy.x));
+                r[2] = make_float2(__double2float_rn(Lp.y - xy.y), (assigned & bit) ? 1.0f : 0.0f);
+            }
+            continue;
+        }
+        // ---- task rows (:182-190; row 0 = depot) + mask bytes
+        if (chunk != (int)warp) task_scalars(chunk);
+        if (!ok) continue;
+        const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
+        const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
+        bool any_open = false;
+#pragma unroll
+        for (int w = 0; w < TW; ++w) any_open = any_open || open[w] != 0;
+        const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+        float* mine = sT + lane * 5 * (T + 1) + 5 * r0;
+        unsigned char* mm = sM + lane * (T + 1) + r0;
+#pragma unroll
+        for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) if (q < nr) {
+            const int jj = r0 + q; const unsigned at = ((unsigned)(jj > 0 ? jj - 1 : 0) << 5) + lane;
+            float* r = mine + 5 * q;
+            if (O.task_obs) {
+                if (jj == 0) { r[0] = 0.f; r[1] = 0.f; r[2] = 0.f; r[3] = __double2float_rn(dpx - Lp.x); r[4] = __double2float_rn(dpy - Lp.y); }   // :188 depot row
+                else {
+                    r[0] = (float)(int)iS[at]; r[1] = (float)(int)iQ[at]; r[2] = dq[q];                           // :185 (s_dur32 = fp32(time))
+                    r[3] = __double2float_rn(iX[at] - Lp.x); r[4] = __double2float_rn(iY[at] - Lp.y);             // :186
+                }
+            }
+            // :199 task bit: forbidden unless open;  worker.py:58-61 depot bit: allowed only when nothing is open
+            mm[q] = jj == 0 ? (any_open ? 1 : 0) : (tbit<TW>(open, jj - 1) ? 0 : 1);
+        }
+    }
+    const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
+    const bool whole = use_bulk && ne == 32 && valid == 0xffffffffu;
+    if (whole) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staged rows must be visible to the TMA engine
+    __syncthreads();
+    stamp(2);
+    const unsigned nA = 6u * A, nT = 5u * (T + 1), nM = (unsigned)(T + 1);
+    if (whole) {
+        if (threadIdx.x == 0) {
+            if (O.agent_obs) bulk_store(O.agent_obs + (size_t)tile_id * 32 * nA, sA, 32 * nA * 4);
+            if (O.task_obs) bulk_store(O.task_obs + (size_t)tile_id * 32 * nT, sT, 32 * nT * 4);
+            if (O.mask) bulk_store(O.mask + (size_t)tile_id * 32 * nM, sM, 32 * nM);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory is released when the block exits
+            stamp(3);
+        }
+        return;
+    }
+    for (int e = (int)warp; e < ne; e += (int)nwarps) {                       // warp <-> env, unit-stride stores; the copies of one env are independent
+        if (!((valid >> e) & 1u)) continue;
+        const size_t be = (size_t)tile_id * 32 + e;
+        if (O.task_obs) {
+            const float* src = sT + e * nT; float* dst = O.task_obs + be * nT;
+#pragma unroll 8
+            for (unsigned k = lane; k < nT; k += 32) dst[k] = src[k];
+        }
+        if (O.agent_obs) {
+            const float* src = sA + e * nA; float* dst = O.agent_obs + be * nA;
+#pragma unroll 4
+            for (unsigned k = lane; k < nA; k += 32) dst[k] = src[k];
+        }
+        if (O.mask) for (unsigned k = lane; k < nM; k += 32) O.mask[be * nM + k] = sM[e * nM + k];
+    }
+    if (trace) { __syncthreads(); if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)tile_id * 8 + 3] = t | (1ull << 63); } }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // k_pass: the whole pass (one leader decision of every env + the observation of the next leader) in ONE launch.
 // Persistent warps take work units from a ticket counter:
 //   units [0, NT)            step   : one tile of 32 envs, thread per env (step_env); the tile id and the mask of the envs
@@ -972,7 +1161,7 @@ __global__ void k_pack_static(const __grid_constant__ EnvArgs E, const double* t
     const TC c = make_tc(E, b);
     for (int j = 0; j < c.T; ++j) {
         EL(c, s_tx, c.T, j) = task_xy[((size_t)b * c.T + j) * 2]; EL(c, s_ty, c.T, j) = task_xy[((size_t)b * c.T + j) * 2 + 1];
-        EL(c, s_dur, c.T, j) = dur[(size_t)b * c.T + j];
+        EL(c, s_dur, c.T, j) = dur[(size_t)b * c.T + j]; EL(c, s_dur32, c.T, j) = __double2float_rn(dur[(size_t)b * c.T + j]);
         int r = req[(size_t)b * c.T + j]; r = r < 1 ? 1 : (r > c.s.M ? c.s.M : r);
         EL(c, s_req, c.T, j) = (unsigned char)r;
     }
@@ -1064,6 +1253,10 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
         AREC(c, i, AR_LAST) = ((const double*)(r + L.o_alast))[i]; AREC(c, i, AR_X) = x; AREC(c, i, AR_Y) = y; AREC(c, i, AR_DIST) = ((const double*)(r + L.o_adist))[i];
         EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i];
         EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; ANODE(c, i) = (unsigned char)node;
+        if (node != DCM_NODE_DEPOT) {                                         // observation cache (AOBS2)
+            const double du = EL(c, s_dur, T, node), ts = ((const double*)(r + L.o_tstart))[node];
+            AOBS2(c, i) = ((r + L.o_tflags)[node] & DCM_TF_FEAS) ? make_double2(ts, ts + du) : make_double2(0.0, 0.0 + du);
+        }
         if (af & DCM_AF_ROUTE) st.route |= bit;
         if (af & DCM_AF_ASSIGNED) st.assigned |= bit;
         if (af & DCM_AF_RETURNED) st.returned |= bit;
@@ -1118,6 +1311,7 @@ struct dcm_env {
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
     cudaStream_t hstream;
     cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // k_episode runs beside k_obs
+    bool obs_ready, obs_tile;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs)
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
     uint64_t launches;
 };
@@ -1160,9 +1354,9 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     size_t off = 0;
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(K, elem) + 255) / 256 * 256; return o; };
     const int MCB = M <= 8 ? 8 : 16; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
-    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32),
+    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32), o_a_obs = carve(A, 16),
                  o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_asg = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
-                 o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
+                 o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dur32 = carve(T, 4), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
                  o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
                  o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
                  o_am_touched = carve(1, 8), o_am_watch = carve(1, 8),
@@ -1194,9 +1388,9 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     { const char* tr = getenv("DCM_PASS_TRACE"); if (e == cudaSuccess && tr && tr[0] == '1') { v->trace_units = (size_t)NT * 64; e = cudaMalloc((void**)&v->d_trace, v->trace_units * 4 * sizeof(unsigned long long)); if (e == cudaSuccess) e = cudaMemset(v->d_trace, 0, v->trace_units * 4 * sizeof(unsigned long long)); } }
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
-    S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec);
+    S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec); S.a_obs = (double*)(a + o_a_obs);
     S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_asg = (double*)(a + o_x_asg); S.x_ret = (double*)(a + o_x_ret); S.x_last = (double*)(a + o_x_last); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
-    S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
+    S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dur32 = (float*)(a + o_s_dur32); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
     S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_dirty = (u64*)(a + o_m_dirty);
     S.am_route = (u64*)(a + o_am_route); S.am_assigned = (u64*)(a + o_am_assigned); S.am_returned = (u64*)(a + o_am_returned); S.am_member = (u64*)(a + o_am_member);
     S.am_depot = (u64*)(a + o_am_depot); S.am_touched = (u64*)(a + o_am_touched); S.am_watch = (u64*)(a + o_am_watch);
@@ -1289,7 +1483,42 @@ int dcm_get_instances(dcm_env* v, double* task_xy, double* depot_xy, int32_t* re
     return DCM_OK;
 }
 
+// the step path's observation builder: k_obs_tile when two tiles fit in an SM's shared memory, else (or with DCM_OBS_CHUNKED=1) k_obs
+static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
+    const int A = v->E.S.A, T = v->E.S.T;
+    const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
+    const int warps = NA + NR < OBS_TILE_MAX_WARPS ? NA + NR : OBS_TILE_MAX_WARPS;
+    const size_t smem = obs_tile_smem(A, T).total;
+    const int use_bulk = (((uintptr_t)O.agent_obs | (uintptr_t)O.task_obs | (uintptr_t)O.mask) & 15u) == 0;
+    if (v->E.S.TW == 1) k_obs_tile<1><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    else if (v->E.S.TW == 2) k_obs_tile<2><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    else k_obs_tile<4><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    CK(cudaGetLastError());
+    v->launches++;
+    return DCM_OK;
+}
+
+// decide once per handle whether the tile kernel applies, and opt in to the shared memory it needs
+static int prepare_obs(dcm_env* v) {
+    if (v->obs_ready) return DCM_OK;
+    v->obs_ready = true; v->obs_tile = false;
+    const char* gs = getenv("DCM_OBS_CHUNKED");
+    if (gs && gs[0] == '1') return DCM_OK;
+    int optin = 0, per_sm = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, v->device));
+    CK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, v->device));
+    const size_t smem = obs_tile_smem(v->E.S.A, v->E.S.T).total;
+    if (smem > (size_t)optin || 2 * (smem + 1024) > (size_t)per_sm) return DCM_OK;
+    const void* fn = v->E.S.TW == 1 ? (const void*)k_obs_tile<1> : v->E.S.TW == 2 ? (const void*)k_obs_tile<2> : (const void*)k_obs_tile<4>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));   // per function, not per handle: the device maximum
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    v->obs_tile = true;
+    return DCM_OK;
+}
+
 static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
+    { const int rc = prepare_obs(v); if (rc) return rc; }
+    if (v->obs_tile) return launch_obs_tile(v, O, s);
     const int tiles_per_block = OBS_THREADS / 32;
     const int NA = (v->E.S.A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (v->E.S.T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
     const dim3 grid((v->E.S.NT + tiles_per_block - 1) / tiles_per_block, NA + NR);

@@ -43,6 +43,8 @@ struct DcmSoa {
     unsigned long long* m_dirty;   // len(members) changed since status was computed (join, or removal: Q3)
     // ---- per agent ----
     double* a_rec;             // [A][32][4]   {arrival_time[-1], x, y, travel_dist}   (one 32-byte sector)
+    double* a_obs;             // [A][32][2]   observation cache: {time_start, time_finish} of the task the agent stands at if it is feasible,
+                               //              else {0, 0 + time} -- the operands of task_env.py:170-171, kept current by agent_step and task_update
     double* a_nd;              // [A]   next_decision
     double* a_ts;              // [A]   time_start of the feasible task the agent is a member of (valid with the watch bit)
     unsigned char* a_node;     // [32 lanes][ANB]  route[-1] or DCM_NODE_DEPOT, per-env contiguous (ANB = 32 for A <= 32, else 64)
@@ -67,6 +69,7 @@ struct DcmSoa {
     // ---- static instance (rows: T, depot: 2) ----
     double* s_tx; double* s_ty; double* s_dur; double* s_dep;
     unsigned char* s_req;
+    float* s_dur32;           // [T] fp32(time): the value the task rows of the observation carry (k_obs_tile copies it with the TMA engine)
     // ---- scratch ----
     double* w_agent;          // [A] per-agent waiting-time accumulator (thread-per-env episode accounting)
 };

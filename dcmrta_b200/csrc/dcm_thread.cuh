@@ -44,6 +44,7 @@ struct TC {
 #define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // {x, y, last arrival, travel_dist}
 enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
 #define AREC2(c, i, h) (((double2*)TB(c, a_rec))[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
+#define AOBS2(c, i) (((double2*)TB(c, a_obs))[LANE_ROW(c, (c).A, i)])                                    // observation cache, see dcm_soa.h
 #define TINFO2(c, j) (((double2*)TB(c, t_info))[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
 // route[-1] of the agents of one env, packed: one 32- or 64-byte line per env so that a step can hold them all in registers
 #define ANODE(c, i) (TB(c, a_node)[(size_t)(c).l * (unsigned)(c).s.ANB + (unsigned)(i)])
@@ -226,6 +227,8 @@ template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC
             st.xfin = tf < st.xfin ? tf : st.xfin;
             feas = bit; open = 0;                                             // :258
             if (newly) newly[j] = 1;
+            for (int i = 0; i < c.A; ++i)                                     // everybody who stands here (member or not, :166-171) now sees a feasible task
+                if (node_of(i) == (unsigned)j) AOBS2(c, i) = make_double2(mx, tf);
             for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
                 const unsigned m = SMEM(c, j, s);
                 if (node_of((int)m) == (unsigned)j) st.touched |= 1ull << m;
@@ -462,6 +465,8 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     const bool to_task = action != 0, feas = to_task && tbit<TW>(st.feas, j), nonempty = to_task && tbit<TW>(st.ne, j);
     // ---- every load first (nothing below can be hoisted above a byte store by the compiler)
     const double2 ld = AREC2(c, i, 1);                                        // {last arrival, travel_dist}
+    double2 aobs = make_double2(0.0, 0.0);                                    // observation cache (AOBS2)
+    if (to_task) { if (feas) aobs = TINFO2(c, j); else aobs.y = 0.0 + EL(c, s_dur, T, j); }
     int n = 0; u64 ids0 = 0, ids1 = 0; double amin = CUDART_INF;
     if (nonempty) {
         n = EL(c, t_nmem, T, j);
@@ -476,7 +481,7 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     st.route |= bit; st.touched |= bit;
     st.xlast = arrival > st.xlast ? arrival : st.xlast;
     if (!to_task) { st.depot |= bit; st.member &= ~bit; st.xret = arrival < st.xret ? arrival : st.xret; return; }
-    st.depot &= ~bit;
+    st.depot &= ~bit; AOBS2(c, i) = aobs;
     int pos = -1;                                                             // :321-322
     for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
     if (pos >= 0) {                                                           // re-visit by a current member (Q8): last arrival wins
