@@ -226,7 +226,16 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         else {
             if (n != n0) { EL(c, t_nmem, c.T, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
             if (!feas_j) {                                                    // earliest member arrival of a waiting coalition
-                if (revisit) { amin = CUDART_INF; for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); amin = a < amin ? a : amin; } amin_new = true; }
+                if (revisit) {                                                // the slots again, in one batch (a loop of dependent loads otherwise)
+                    double v8[8];
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl) v8[sl] = sl < c.MC ? SARR(c, j, sl) : 0.0;
+                    amin = CUDART_INF;
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl) if (sl < n) amin = v8[sl] < amin ? v8[sl] : amin;
+                    for (int sl = 8; sl < n; ++sl) { const double a = SARR(c, j, sl); amin = a < amin ? a : amin; }
+                    amin_new = true;
+                }
                 if (amin_new) { TINFO(c, j, 0) = amin; st.xamin = amin < st.xamin ? amin : st.xamin; }
             }
         }
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant_
 //   mode 1: dcm_reset (every env, or those selected by `which`)
 // ---------------------------------------------------------------------------------------------------------------
 #define EPI_WARPS 4
+#define EPI_LIST_MAX_WARPS 4
 struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int* next_leader; double* metrics;
                  ObsArgs obs; int write_obs; /* mode 0 + auto-reset: write the restarted env's observation (k_obs runs beside this kernel and skips it) */ };
 
@@ -301,13 +311,16 @@ struct EpiScratch {
     unsigned char* sn;     // [32]      member count | feasible << 7
     int MC;
 };
+// handles with at most 8 member slots (w_episode_metrics8) keep the member data in registers and only stage the four vectors that are summed
 __host__ __device__ inline size_t epi_scratch_bytes(int A, int T, int MC) {
+    if (MC <= 8) return (size_t)8 * (2 * T + 2 * A);
     return (size_t)8 * (32 * MC + 32 + 2 * T + 2 * A) + (((size_t)32 * MC + 32 + 7) / 8) * 8;
 }
 __device__ __forceinline__ EpiScratch epi_scratch(unsigned char* base, int A, int T, int MC) {
     EpiScratch S; double* d = (double*)base;
-    S.sa = d; d += 32 * MC; S.smx = d; d += 32; S.s_task = d; d += T; S.s_ts = d; d += T; S.s_agent = d; d += A; S.s_dist = d; d += A;
-    S.sm = (unsigned char*)d; S.sn = S.sm + 32 * MC; S.MC = MC;
+    S.s_task = d; d += T; S.s_ts = d; d += T; S.s_agent = d; d += A; S.s_dist = d; d += A;
+    S.sa = d; S.smx = d; S.sm = (unsigned char*)d; S.sn = S.sm; S.MC = MC;
+    if (MC > 8) { d += 32 * MC; S.smx = d; d += 32; S.sm = (unsigned char*)d; S.sn = S.sm + 32 * MC; }
     return S;
 }
 
@@ -435,8 +448,7 @@ __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& 
         const int j = j0 + (int)lane; const int n = cur.n; const bool feas = cur.feas;
         double mx = 0.0;
 #pragma unroll
-        for (int s2 = 0; s2 < 8; ++s2) if (s2 < n) { S.sa[lane * S.MC + s2] = cur.a[s2]; mx = (s2 == 0 || cur.a[s2] > mx) ? cur.a[s2] : mx; S.sm[lane * S.MC + s2] = (unsigned char)((cur.ids >> (8 * s2)) & 0xffu); }
-        S.sn[lane] = (unsigned char)(n | (feas ? 0x80 : 0)); S.smx[lane] = mx;
+        for (int s2 = 0; s2 < 8; ++s2) if (s2 < n) mx = (s2 == 0 || cur.a[s2] > mx) ? cur.a[s2] : mx;
         if (j < T) {                                                          // task['sum_waiting_time'] :349-357
             const double w_ab = (double)cur.nab * c.W;
             double v = w_ab;
@@ -449,20 +461,22 @@ __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& 
             S.s_task[j] = v;
             S.s_ts[j] = feas ? cur.ts : 0.0;
         }
-        __syncwarp();
-        const int nt = T - j0 < 32 ? T - j0 : 32;
-        for (int t = 0; t < nt; ++t) {                                        // reference order: tasks ascending, members in list order (:358-362)
-            const int cnt = S.sn[t] & 0x7f;
-            if (!cnt) continue;
-            const bool ft = S.sn[t] & 0x80; const double mxt = S.smx[t];
-            for (int s2 = 0; s2 < cnt; ++s2) {
-                const unsigned m = S.sm[t * S.MC + s2]; const double a = S.sa[t * S.MC + s2];
+        // agent['sum_waiting_time'] in the reference order: tasks ascending, members in list order (:358-362).  The task's count,
+        // latest arrival, ids and arrivals are broadcast from the lane that holds them (no staging in shared memory: the scratch
+        // of a block stays small enough for four of these blocks beside two k_obs_tile blocks on an SM)
+        for (unsigned tm = __ballot_sync(0xffffffffu, n > 0); tm; tm &= tm - 1) {
+            const int t = __ffs(tm) - 1;
+            const int cnt = __shfl_sync(0xffffffffu, n, t); const bool ft = __shfl_sync(0xffffffffu, (int)feas, t) != 0;
+            const double mxt = __shfl_sync(0xffffffffu, mx, t); const u64 idt = __shfl_sync(0xffffffffu, cur.ids, t);
+#pragma unroll
+            for (int s2 = 0; s2 < 8; ++s2) if (s2 < cnt) {                    // cnt is warp-uniform
+                const double a = __shfl_sync(0xffffffffu, cur.a[s2], t);
+                const unsigned m = (unsigned)(idt >> (8 * s2)) & 0xffu;
                 double add;
                 if (ft) add = mxt - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }     // :360 / :362
                 if (lane == (m & 31u)) { if (m < 32u) acc0 += add; else acc1 += add; }
             }
         }
-        __syncwarp();
         cur = nxt;
     }
 #pragma unroll
@@ -621,14 +635,27 @@ __global__ void __launch_bounds__(32, 16) k_episode(const __grid_constant__ EnvA
 // The step path's variant: k_step appended the envs whose episode just ended to a list (about 1 env in 150 per pass), so the
 // grid is a few blocks per SM instead of EPI_WARPS blocks per tile -- dispatching 8,192 mostly empty blocks cost ~25 us beside
 // k_obs (profiles/r03a_timeline.txt).  Envs are independent: the order of the list does not matter.
+// Shared-memory footprint matters more than anything else here.  Two k_obs_tile blocks leave a 13 kB hole at the top of an
+// SM's shared memory; episode blocks that fit into it run beside them for free, but a block that does not is placed -- it has
+// priority -- at the BOTTOM of the 110 kB an exiting k_obs_tile block frees, after which no second k_obs_tile block fits on that SM
+// until it is gone (30-50 us; measured with tools/obs_trace.py: most SMs ran ONE obs block, profiles/r04_pass_trace.txt).  Hence:
+// member data in registers (1.1 kB of scratch per env), several envs (warps) per block to share the 1 kB the hardware reserves per
+// block, and at most ~100 registers.
 template <int TW>
-__global__ void __launch_bounds__(32, 16) k_episode_list(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P, const unsigned* elist, const unsigned* ecount) {
+__global__ void __launch_bounds__(32 * EPI_LIST_MAX_WARPS, 5) k_episode_list(const __grid_constant__ EnvArgs E, const __grid_constant__ EpiArgs P, const unsigned* elist, const unsigned* ecount,
+                                                                         unsigned long long* trace) {
     extern __shared__ __align__(16) unsigned char epi_smem[];
-    const unsigned n = *ecount;
-    if (blockIdx.x >= n) return;
-    const EpiScratch scratch = epi_scratch(epi_smem, E.S.A, E.S.T, E.S.MC);
-    for (unsigned k = blockIdx.x; k < n; k += gridDim.x)
-        episode_env<TW>(E, P, (int)elist[k], threadIdx.x, scratch, P.write_obs ? &P.obs : nullptr);
+    const unsigned n = *ecount, nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned first = blockIdx.x * nw + warp;
+    if (first >= n) return;
+    auto stamp = [&](int k) { if (trace && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)E.S.NT * 8 + 4 * first + k] = t; } };
+    if (trace && lane == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); trace[(size_t)E.S.NT * 8 + 4 * first + 2] = sm; }
+    stamp(0);                                                                 // DCM_PASS_TRACE=1 (tools/obs_trace.py): warp entry / exit / SM, after the obs tiles' stamps
+    const size_t per_warp = (epi_scratch_bytes(E.S.A, E.S.T, E.S.MC) + 15) / 16 * 16;
+    const EpiScratch scratch = epi_scratch(epi_smem + warp * per_warp, E.S.A, E.S.T, E.S.MC);
+    for (unsigned k = first; k < n; k += gridDim.x * nw)
+        episode_env<TW>(E, P, (int)elist[k], lane, scratch, P.write_obs ? &P.obs : nullptr);
+    stamp(1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -805,7 +832,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 }
 
 template <int TW>
-__global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 2) k_obs_tile(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O, int use_bulk, unsigned long long* trace) {
+__global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O, int use_bulk, unsigned long long* trace) {
     extern __shared__ __align__(128) unsigned char obs_smem[];
     const int B = E.S.B, A = E.S.A, T = E.S.T;
     const unsigned tile_id = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -819,6 +846,7 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 2) k_obs_tile(const _
     const TC c = make_tc(E, b < B ? b : B - 1);
     auto stamp = [&](int k) { if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)tile_id * 8 + k] = t; } };
     stamp(0);
+    if (trace && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); trace[(size_t)tile_id * 8 + 5] = sm; }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1373,6 +1401,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     int prio_lo = 0, prio_hi = 0;
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     // highest priority: the few long episode chains must get their blocks in before the six waves of k_obs that run beside them
+    { const char* gp = getenv("DCM_EPISODE_PRIO"); if (gp && gp[0] == '0') prio_hi = prio_lo; }                       // experiment switch: side stream at normal priority
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&v->side, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_join, cudaEventDisableTiming);
@@ -1512,6 +1541,16 @@ static int prepare_obs(dcm_env* v) {
     const void* fn = v->E.S.TW == 1 ? (const void*)k_obs_tile<1> : v->E.S.TW == 2 ? (const void*)k_obs_tile<2> : (const void*)k_obs_tile<4>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));   // per function, not per handle: the device maximum
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // The episode kernel runs BESIDE this one and has to share SMs with it: blocks of kernels that ask for different L1 /
+    // shared-memory splits do not become co-resident on an SM (measured: side by side the two kernels took as long as one
+    // after the other, profiles/r03_timeline.txt), so it asks for the same split.
+    const void* fe = v->E.S.TW == 1 ? (const void*)k_episode_list<1> : v->E.S.TW == 2 ? (const void*)k_episode_list<2> : (const void*)k_episode_list<4>;
+    const void* fd = v->E.S.TW == 1 ? (const void*)k_episode<1> : v->E.S.TW == 2 ? (const void*)k_episode<2> : (const void*)k_episode<4>;
+    { const char* gc = getenv("DCM_EPISODE_CARVEOUT_DEFAULT");
+      if (!(gc && gc[0] == '1')) {
+          CK(cudaFuncSetAttribute(fe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CK(cudaFuncSetAttribute(fd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      } }
     v->obs_tile = true;
     return DCM_OK;
 }
@@ -1529,11 +1568,14 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 }
 
 static int launch_episode_list(dcm_env* v, const EpiArgs& P, const unsigned* ecount, cudaStream_t s) {
-    const size_t smem = epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC);
-    int grid = 148 * 8; if (grid > v->E.S.B) grid = v->E.S.B;
-    if (v->E.S.TW == 1) k_episode_list<1><<<grid, 32, smem, s>>>(v->E, P, v->d_elist, ecount);
-    else if (v->E.S.TW == 2) k_episode_list<2><<<grid, 32, smem, s>>>(v->E, P, v->d_elist, ecount);
-    else k_episode_list<4><<<grid, 32, smem, s>>>(v->E, P, v->d_elist, ecount);
+    int nw = 2; { const char* gw = getenv("DCM_EPISODE_WARPS"); if (gw && atoi(gw) >= 1 && atoi(gw) <= EPI_LIST_MAX_WARPS) nw = atoi(gw); }   // envs (warps) per block
+    const size_t smem = nw * ((epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC) + 15) / 16 * 16);
+    int per_sm = 8; { const char* gg = getenv("DCM_EPISODE_GRID"); if (gg && atoi(gg) > 0) per_sm = atoi(gg); }              // experiment switch: warps per SM
+    int grid = (148 * per_sm + nw - 1) / nw; if (grid > v->E.S.B) grid = v->E.S.B;
+    if (v->d_trace) CK(cudaMemsetAsync(v->d_trace + (size_t)v->E.S.NT * 8, 0, (size_t)grid * nw * 4 * sizeof(unsigned long long), s));
+    if (v->E.S.TW == 1) k_episode_list<1><<<grid, 32 * nw, smem, s>>>(v->E, P, v->d_elist, ecount, v->d_trace);
+    else if (v->E.S.TW == 2) k_episode_list<2><<<grid, 32 * nw, smem, s>>>(v->E, P, v->d_elist, ecount, v->d_trace);
+    else k_episode_list<4><<<grid, 32 * nw, smem, s>>>(v->E, P, v->d_elist, ecount, v->d_trace);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;

@@ -207,20 +207,40 @@ template <int NW> __device__ __forceinline__ void nset(Nodes<NW>& nd, int i, uns
 // route[-1] of an agent: read from memory here; the fused step passes a functor that reads its register copy (Nodes below)
 struct NodeFromMemory { const TC& c; __device__ __forceinline__ unsigned operator()(int m) const { return ANODE(c, m); } };
 
+// counters of abandonments (u16 per agent / per task, rows of 32 lanes): bumped with a 32-bit reduction on the word that
+// holds the counter of this lane and of its neighbour -- fire-and-forget, where load + add + store would make the warp wait a
+// DRAM round trip for a value nothing in the step reads (only the episode accounting does; the counts stay far below 65,536)
+__device__ __forceinline__ void bump_u16(unsigned short* p, unsigned by) {
+    const size_t a = (size_t)p;
+    atomicAdd((unsigned*)(a & ~(size_t)3), by << (8u * (unsigned)(a & 2)));
+}
+
 template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c, St<TW>& st, unsigned m, int j, const NF& node_of) {
-    EL(c, a_nab, c.A, m) = (unsigned short)(EL(c, a_nab, c.A, m) + 1);
+    bump_u16(&EL(c, a_nab, c.A, m), 1u);
     if (node_of((int)m) == (unsigned)j) st.member &= ~(1ull << m);           // it no longer belongs to the task it stands at
 }
 
+// The member slots of the task are read in ONE batch together with the count (the first eight arrivals and the id word do not
+// depend on it; slots past the count hold stale values that are never used), so the common outcomes -- the coalition becomes
+// feasible, or it is still short and nobody gives up -- cost one round trip instead of one per member (profiles/r03_k_step_by_line).
+// Handles with more than eight slots per task keep the slot-by-slot loops for the tasks that hold more than eight members.
 template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of) {
     const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
     const int n = EL(c, t_nmem, T, j);                                        // :250
+    double a8[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) a8[s] = s < c.MC ? SARR(c, j, s) : 0.0;
+    const u64 ids = *(const u64*)&SMEM(c, j, 0);
+    auto idb = [&](int s) -> unsigned { return (unsigned)(ids >> (8 * s)) & 0xffu; };
+    const bool small = n <= 8;
     const int stt = (int)EL(c, s_req, T, j) - n;                              // :252 (not refreshed after removals: Q3)
     if (stt != (int)EL(c, t_status, T, j)) EL(c, t_status, T, j) = (signed char)stt;
     u64 open = stt > 0 ? bit : 0, feas = 0, ne = bit, dirty = 0;
     if (stt <= 0) {                                                           // :254
-        double mx = SARR(c, j, 0), mn = mx;
-        for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; mn = a < mn ? a : mn; }
+        double mx = a8[0], mn = mx;
+#pragma unroll
+        for (int s = 1; s < 8; ++s) if (s < n) { mx = a8[s] > mx ? a8[s] : mx; mn = a8[s] < mn ? a8[s] : mn; }
+        for (int s = 8; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; mn = a < mn ? a : mn; }
         if (mx - mn <= c.W) {                                                 // :255
             const double tf = mx + EL(c, s_dur, T, j);
             TINFO(c, j, 0) = mx; TINFO(c, j, 1) = tf;                         // :256-257 time_start, time_finish
@@ -230,40 +250,51 @@ template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC
             for (int i = 0; i < c.A; ++i)                                     // everybody who stands here (member or not, :166-171) now sees a feasible task
                 if (node_of(i) == (unsigned)j) AOBS2(c, i) = make_double2(mx, tf);
             for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
-                const unsigned m = SMEM(c, j, s);
+                const unsigned m = s < 8 ? idb(s) : (unsigned)SMEM(c, j, s);
                 if (node_of((int)m) == (unsigned)j) st.touched |= 1ull << m;
             }
         } else {                                                              // :260-265 (iterates a copy: no skipping, Q4)
             const double thr = mx - c.W;
             int wv = 0, nab = 0; double amin = CUDART_INF;
-            for (int s = 0; s < n; ++s) {
-                const double a = SARR(c, j, s); const unsigned m = SMEM(c, j, s);
+            auto one = [&](int s, double a, unsigned m) {
                 if (a <= thr) { ++nab; abandon(c, st, m, j, node_of); }
                 else { if (wv != s) { SARR(c, j, wv) = a; SMEM(c, j, wv) = (unsigned char)m; } ++wv; amin = a < amin ? a : amin; }
-            }
-            EL(c, t_nmem, T, j) = (unsigned char)wv; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
+            };
+#pragma unroll
+            for (int s = 0; s < 8; ++s) if (s < n) one(s, a8[s], idb(s));
+            for (int s = 8; s < n; ++s) one(s, SARR(c, j, s), SMEM(c, j, s));
+            EL(c, t_nmem, T, j) = (unsigned char)wv; bump_u16(&EL(c, t_nab, T, j), (unsigned)nab);
             TINFO(c, j, 0) = amin;
             if (wv == 0) ne = 0;
             dirty = bit;
         }
     } else {                                                                  // :266-271 (mutates while iterating: Q2)
-        int i = 0, nn = n, nab = 0;
-        while (i < nn) {
-            const double a = SARR(c, j, i);
-            if (now - a >= c.W) {                                             // :269 (Q1: false when fl(arr+W) rounded down)
-                abandon(c, st, SMEM(c, j, i), j, node_of);
-                for (int k = i; k < nn - 1; ++k) { SARR(c, j, k) = SARR(c, j, k + 1); SMEM(c, j, k) = SMEM(c, j, k + 1); }
-                --nn; ++nab;                                                  // the element that moved into slot i is skipped
+        bool any = !small;                                                    // does anybody give up?  (:269 on the batch; Q1: false when fl(arr+W) rounded down)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) any = any || (s < n && now - a8[s] >= c.W);
+        if (any) {
+            int i = 0, nn = n, nab = 0;
+            while (i < nn) {
+                const double a = SARR(c, j, i);
+                if (now - a >= c.W) {                                         // :269
+                    abandon(c, st, SMEM(c, j, i), j, node_of);
+                    for (int k = i; k < nn - 1; ++k) { SARR(c, j, k) = SARR(c, j, k + 1); SMEM(c, j, k) = SMEM(c, j, k + 1); }
+                    --nn; ++nab;                                              // the element that moved into slot i is skipped
+                }
+                ++i;
             }
-            ++i;
-        }
-        if (nab) {
-            EL(c, t_nmem, T, j) = (unsigned char)nn; EL(c, t_nab, T, j) = (unsigned short)(EL(c, t_nab, T, j) + nab);
-            double amin = CUDART_INF;
-            for (int s = 0; s < nn; ++s) { const double a = SARR(c, j, s); amin = a < amin ? a : amin; }
-            TINFO(c, j, 0) = amin;
-            if (nn == 0) ne = 0;
-            dirty = bit;
+            if (nab) {
+                EL(c, t_nmem, T, j) = (unsigned char)nn; bump_u16(&EL(c, t_nab, T, j), (unsigned)nab);
+                double v8[8], amin = CUDART_INF;                              // the survivors, again in one batch
+#pragma unroll
+                for (int s = 0; s < 8; ++s) v8[s] = s < c.MC ? SARR(c, j, s) : 0.0;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) if (s < nn) amin = v8[s] < amin ? v8[s] : amin;
+                for (int s = 8; s < nn; ++s) { const double a = SARR(c, j, s); amin = a < amin ? a : amin; }
+                TINFO(c, j, 0) = amin;
+                if (nn == 0) ne = 0;
+                dirty = bit;
+            }
         }
     }
 #pragma unroll

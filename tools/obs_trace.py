@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""tools/obs_trace.py [B] -- per-tile phase stamps of one steady-state k_obs_tile (DCM_PASS_TRACE=1): entry, input copies landed,
-rows staged, output copies read."""
+"""tools/obs_trace.py [B] [passes] -- globaltimer stamps of steady-state passes (DCM_PASS_TRACE=1): per k_obs_tile block
+entry, scalars landed, input copies landed, rows staged, output copies read, and the SM it ran on; per k_episode_list block
+entry, exit and SM.  Prints the phase percentiles of the last pass and, per pass, how long both kernels took and how many obs
+blocks each SM had resident while episode blocks were alive."""
 import os, sys
 os.environ["DCM_PASS_TRACE"] = "1"
 import ctypes as C
@@ -9,20 +11,38 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dcmrta_b200 import BatchedTaskEnv
 from dcmrta_b200._lib import lib, check
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+PASSES = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 env = BatchedTaskEnv(B, 20, 50, auto_reset=True, seed=1234)
 env.generate(); env.reset()
 for _ in range(700): env.step(policy="random")
 torch.cuda.synchronize()
 NT = (B + 31) // 32
-buf = np.zeros(NT * 8, np.uint64)
-check(lib().dcm_debug_pass_trace(env._h, buf.ctypes.data_as(C.c_void_p), buf.size))
-tr = buf.reshape(NT, 8)
-slow = (tr[:, 3] >> np.uint64(63)).astype(bool)
-tr = (tr & np.uint64((1 << 63) - 1)).astype(np.int64)
-t0 = tr[:, 0].min()
-t = (tr - t0) / 1e3
+EB = 148 * int(os.environ.get("DCM_EPISODE_GRID", "8")) + 8   # warps of k_episode_list (one env each)
 pc = lambda x: np.percentile(x, [0, 10, 50, 90, 99, 100]).round(2)
-print("B", B, "tiles", NT, "span us", round(t[:, 3].max(), 1), "tiles copied env by env:", int(slow.sum()))
+for p in range(PASSES):
+    env.step(policy="random"); torch.cuda.synchronize()
+    buf = np.zeros(NT * 8 + 4 * EB, np.uint64)
+    check(lib().dcm_debug_pass_trace(env._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+    tr = buf[:NT * 8].reshape(NT, 8)
+    ep = buf[NT * 8:].reshape(EB, 4).astype(np.int64)
+    ep = ep[ep[:, 0] > 0]
+    slow = (tr[:, 3] >> np.uint64(63)).astype(bool)
+    sm = tr[:, 5].astype(np.int64)
+    tr = (tr & np.uint64((1 << 63) - 1)).astype(np.int64)
+    t0 = tr[:, 0].min()
+    t = (tr - t0) / 1e3
+    line = "pass %d: k_obs_tile span %.1f us (%d of %d tiles copied env by env)" % (p, t[:, 3].max(), int(slow.sum()), NT)
+    if len(ep):
+        e0, e1 = (ep[:, 0] - t0) / 1e3, (ep[:, 1] - t0) / 1e3
+        per_sm = np.bincount(ep[:, 2], minlength=148)
+        line += "; k_episode_list %d blocks with work, enter %.1f, last exit %.1f us, per SM min/median/max %d/%d/%d" % (
+            len(ep), e0.min(), e1.max(), per_sm.min(), int(np.median(per_sm)), per_sm.max())
+        # obs blocks resident per SM at the middle of the episode kernel's life
+        mid = 0.5 * (e0.min() + e1.max())
+        res = np.bincount(sm[(t[:, 0] <= mid) & (t[:, 3] > mid)], minlength=148)
+        line += "; obs blocks resident per SM at t=%.0f us: %s" % (mid, dict(zip(*np.unique(res, return_counts=True))))
+    print(line)
+print("B", B, "tiles", NT, "last pass:")
 print("entry                 p0/10/50/90/99/100", pc(t[:, 0]))
 print("scalars landed - entry                  ", pc(t[:, 1] - t[:, 0]))
 print("copies landed - entry                   ", pc(t[:, 4] - t[:, 0]))
@@ -30,3 +50,5 @@ print("rows staged - entry                     ", pc(t[:, 2] - t[:, 0]))
 print("outputs read - rows staged  (bulk)      ", pc((t[:, 3] - t[:, 2])[~slow]))
 if slow.any(): print("outputs written - rows staged (by env)  ", pc((t[:, 3] - t[:, 2])[slow]))
 print("block lifetime                          ", pc(t[:, 3] - t[:, 0]))
+if len(ep):
+    print("episode block lifetime                  ", pc(e1 - e0))
