@@ -48,7 +48,10 @@ struct StepArgs {
 };
 
 struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask;
-                 int skip_ended; /* leave out the envs whose episode ended in this step: the episode kernel, running beside k_obs, writes theirs */ };
+                 int skip_ended; /* envs whose episode ended in this step: 1 = leave them out (the episode kernel, running beside k_obs, writes
+                                    theirs); 2 = k_obs_tile writes the observation of the restarted episode itself -- every agent at the depot, no route,
+                                    status = requirements, only the depot masked: a function of the static instance alone, which the episode kernel
+                                    does not touch unless it regenerates instances */ };
 
 enum GranOp { OP_NEXT_DECISION = 1, OP_UNIQUE_GROUP, OP_SET_CLOCK, OP_GET_CLOCK, OP_TASK_UPDATE, OP_AGENT_UPDATE, OP_APPLY_MEMBERS,
               OP_CHECK_FINISHED, OP_COMPUTE_METRICS, OP_ENV_FLAGS };
@@ -464,16 +467,17 @@ __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& 
         // agent['sum_waiting_time'] in the reference order: tasks ascending, members in list order (:358-362).  The task's count,
         // latest arrival, ids and arrivals are broadcast from the lane that holds them (no staging in shared memory: the scratch
         // of a block stays small enough for four of these blocks beside two k_obs_tile blocks on an SM)
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) {                                      // in place: what each member of this lane's task waited, :360 / :362
+            const double wv = now - cur.a[s2]; cur.a[s2] = feas ? mx - cur.a[s2] : (wv > 0.0 ? wv : 0.0);
+        }
         for (unsigned tm = __ballot_sync(0xffffffffu, n > 0); tm; tm &= tm - 1) {
             const int t = __ffs(tm) - 1;
-            const int cnt = __shfl_sync(0xffffffffu, n, t); const bool ft = __shfl_sync(0xffffffffu, (int)feas, t) != 0;
-            const double mxt = __shfl_sync(0xffffffffu, mx, t); const u64 idt = __shfl_sync(0xffffffffu, cur.ids, t);
+            const int cnt = __shfl_sync(0xffffffffu, n, t); const u64 idt = __shfl_sync(0xffffffffu, cur.ids, t);
 #pragma unroll
             for (int s2 = 0; s2 < 8; ++s2) if (s2 < cnt) {                    // cnt is warp-uniform
-                const double a = __shfl_sync(0xffffffffu, cur.a[s2], t);
+                const double add = __shfl_sync(0xffffffffu, cur.a[s2], t);
                 const unsigned m = (unsigned)(idt >> (8 * s2)) & 0xffu;
-                double add;
-                if (ft) add = mxt - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }     // :360 / :362
                 if (lane == (m & 31u)) { if (m < 32u) acc0 += add; else acc1 += add; }
             }
         }
@@ -873,12 +877,13 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
         const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
 #pragma unroll
         for (int w = 0; w < TW; ++w) open[w] = EL(c, m_open, TW, w);
-        if (r0 == 0) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
+        if (r0 == 0 || O.skip_ended == 2) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
 #pragma unroll
         for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) { const int jj = r0 + q; dq[q] = EL(c, s_dur32, T, (jj > 0 && jj <= T) ? jj - 1 : 0); }
     };
     if ((int)warp < NA) agent_scalars(); else if ((int)warp < NA + NR) task_scalars((int)warp);
-    if (ended) leader = -1;
+    const bool fresh = ended && O.skip_ended == 2;                            // the restarted episode's first observation (see ObsArgs)
+    if (ended) leader = fresh ? 0 : -1;
     const bool ok = leader >= 0 && leader < A;
     const unsigned valid = __ballot_sync(0xffffffffu, ok);                    // the same in every warp of the block
     stamp(1);
@@ -899,6 +904,7 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
                 const int i = c0 + q; const u64 bit = 1ull << i; const unsigned at = ((unsigned)i << 5) + lane;
                 const double2 xy = iR[at << 1];
                 double travel_t = 0.0, wait = 0.0, remain = 0.0;
+                if (fresh) { float2* r = (float2*)(mine + 6 * q); r[0] = r[1] = r[2] = make_float2(0.f, 0.f); continue; }
                 if ((route & bit) && !(depot & bit)) {                        // :168
                     const double arr = iR[(at << 1) + 1].x;
                     const double2 tt = iO[at];                                // {time_start or 0 (Q6), fl(time_start + time)}
@@ -921,7 +927,8 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
         bool any_open = false;
 #pragma unroll
         for (int w = 0; w < TW; ++w) any_open = any_open || open[w] != 0;
-        const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+        double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+        if (fresh) { Lp = make_double2(dpx, dpy); any_open = true; }           // everybody stands at the depot, every task is open
         float* mine = sT + lane * 5 * (T + 1) + 5 * r0;
         unsigned char* mm = sM + lane * (T + 1) + r0;
 #pragma unroll
@@ -931,12 +938,12 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
             if (O.task_obs) {
                 if (jj == 0) { r[0] = 0.f; r[1] = 0.f; r[2] = 0.f; r[3] = __double2float_rn(dpx - Lp.x); r[4] = __double2float_rn(dpy - Lp.y); }   // :188 depot row
                 else {
-                    r[0] = (float)(int)iS[at]; r[1] = (float)(int)iQ[at]; r[2] = dq[q];                           // :185 (s_dur32 = fp32(time))
+                    r[0] = (float)(int)(fresh ? (int)iQ[at] : (int)iS[at]); r[1] = (float)(int)iQ[at]; r[2] = dq[q];   // :185 (s_dur32 = fp32(time)); status = requirements after clear_decisions
                     r[3] = __double2float_rn(iX[at] - Lp.x); r[4] = __double2float_rn(iY[at] - Lp.y);             // :186
                 }
             }
             // :199 task bit: forbidden unless open;  worker.py:58-61 depot bit: allowed only when nothing is open
-            mm[q] = jj == 0 ? (any_open ? 1 : 0) : (tbit<TW>(open, jj - 1) ? 0 : 1);
+            mm[q] = jj == 0 ? (any_open ? 1 : 0) : ((fresh || tbit<TW>(open, jj - 1)) ? 0 : 1);
         }
     }
     const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
@@ -1339,7 +1346,7 @@ struct dcm_env {
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
     cudaStream_t hstream;
     cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // k_episode runs beside k_obs
-    bool obs_ready, obs_tile;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs)
+    bool obs_ready, obs_tile, obs_resets;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs); it also writes restarted envs' observations
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
     uint64_t launches;
 };
@@ -1531,6 +1538,7 @@ static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 static int prepare_obs(dcm_env* v) {
     if (v->obs_ready) return DCM_OK;
     v->obs_ready = true; v->obs_tile = false;
+    { const char* gr = getenv("DCM_OBS_RESET_BY_EPISODE"); v->obs_resets = !(gr && gr[0] == '1'); }
     const char* gs = getenv("DCM_OBS_CHUNKED");
     if (gs && gs[0] == '1') return DCM_OK;
     int optin = 0, per_sm = 0;
@@ -1667,11 +1675,16 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     }
     CK(cudaEventRecord(v->ev_fork, s));
     CK(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
-    P.obs = O; P.write_obs = (v->E.cflags & DCM_FLAG_AUTO_RESET) ? 1 : 0;
+    { const int rc0 = prepare_obs(v); if (rc0) return rc0; }
+    // the restarted envs' observation: by k_obs_tile itself when it only depends on the static instance (auto-reset without
+    // regeneration; DCM_OBS_RESET_BY_EPISODE=1 switches back), else by the episode kernel, from the registers that hold the new instance
+    const bool auto_reset = (v->E.cflags & DCM_FLAG_AUTO_RESET) != 0;
+    const bool obs_resets = auto_reset && v->obs_tile && v->obs_resets && !(v->E.cflags & DCM_FLAG_REGENERATE) && v->E.max_time > 0.0;
+    P.obs = O; P.write_obs = (auto_reset && !obs_resets) ? 1 : 0;
     int rc = use_list ? launch_episode_list(v, P, ecount, v->side) : launch_episode(v, P, v->side);
     if (rc) return rc;
     CK(cudaEventRecord(v->ev_join, v->side));
-    O.skip_ended = 1;
+    O.skip_ended = obs_resets ? 2 : 1;
     rc = launch_obs(v, O, s);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(s, v->ev_join, 0));
