@@ -261,7 +261,17 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
             }
         }
     }
-    if (F.next_leader) F.next_leader[b] = leader;
+    int leader_out = leader;
+    if ((flags & ENV_DONE) && (E.cflags & DCM_FLAG_AUTO_RESET) && 0.0 < E.max_time) {
+        // The episode kernel restarts this env; the first leader of the new episode (episode_env, worker.py:54) is a function of the
+        // RNG contract alone, so the OUTPUT carries it already: next_leader, reward and done are then final when k_step ends and
+        // dcm_step_host sends them to the host while the episode and observation kernels run.  (The stored leader stays -1.)
+        const int inj = F.leader_in ? F.leader_in[b] : -1;
+        if (inj >= 0) leader_out = inj < c.A ? inj : 0;
+        else if (c.A == 1) leader_out = 0;
+        else leader_out = kth_bit(c.A >= 64 ? ~0ull : ((1ull << c.A) - 1), pick(draw_block(rng, episode + 1, 0, 0).y, c.A));
+    }
+    if (F.next_leader) F.next_leader[b] = leader_out;
     if (F.reward) F.reward[b] = reward_out;
     if (F.done) F.done[b] = (flags & ENV_DONE) ? 1 : 0;
     if (F.used_action) F.used_action[b] = action_out;
@@ -1344,7 +1354,7 @@ struct dcm_env {
     unsigned char* d_record;         // [B,dyn_bytes] export staging
     // dcm_step_host staging
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
-    cudaStream_t hstream;
+    cudaStream_t hstream, hcopy; bool forked;   // dcm_step_host: its stream; a second one for the results k_step alone produces; the last dcm_step recorded ev_fork
     cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // k_episode runs beside k_obs
     bool obs_ready, obs_tile, obs_resets;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs); it also writes restarted envs' observations
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
@@ -1449,6 +1459,7 @@ int dcm_destroy(dcm_env* v) {
     cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_ctl); cudaFree(v->d_queue); cudaFree(v->d_qmask); cudaFree(v->d_trace); cudaFree(v->d_cursor); cudaFree(v->d_record); cudaFree(v->d_elist); cudaFree(v->d_ecount);
     cudaFree(v->d_action); cudaFree(v->d_agent); cudaFree(v->d_task); cudaFree(v->d_mask); cudaFree(v->d_leader); cudaFree(v->d_reward); cudaFree(v->d_done);
     if (v->hstream) cudaStreamDestroy(v->hstream);
+    if (v->hcopy) cudaStreamDestroy(v->hcopy);
     if (v->side) cudaStreamDestroy(v->side);
     if (v->ev_fork) cudaEventDestroy(v->ev_fork);
     if (v->ev_join) cudaEventDestroy(v->ev_join);
@@ -1674,6 +1685,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
         return DCM_OK;
     }
     CK(cudaEventRecord(v->ev_fork, s));
+    v->forked = true;
     CK(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
     { const int rc0 = prepare_obs(v); if (rc0) return rc0; }
     // the restarted envs' observation: by k_obs_tile itself when it only depends on the static instance (auto-reset without
@@ -1697,6 +1709,7 @@ static int ensure_host_staging(dcm_env* v) {
     CK(cudaMalloc(&v->d_action, B * 4)); CK(cudaMalloc(&v->d_agent, B * A * 6 * 4)); CK(cudaMalloc(&v->d_task, B * (T + 1) * 5 * 4));
     CK(cudaMalloc(&v->d_mask, B * (T + 1))); CK(cudaMalloc(&v->d_leader, B * 4)); CK(cudaMalloc(&v->d_reward, B * 4)); CK(cudaMalloc(&v->d_done, B));
     CK(cudaStreamCreateWithFlags(&v->hstream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&v->hcopy, cudaStreamNonBlocking));
     return DCM_OK;
 }
 
@@ -1710,8 +1723,18 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
     const size_t B = v->E.S.B, A = v->E.S.A, T = v->E.S.T;
     cudaStream_t s = v->hstream;
     if (action) CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
+    v->forked = false;
     rc = dcm_step(v, v->d_action, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
     if (rc) return rc;
+    // next_leader, reward and done are final when k_step ends (ev_fork; k_step also knows the first leader of an episode the
+    // episode kernel is about to restart): they travel to the host while the episode and observation kernels run
+    if (v->forked && (reward || done || next_leader)) {
+        CK(cudaStreamWaitEvent(v->hcopy, v->ev_fork, 0));
+        if (next_leader) CK(cudaMemcpyAsync(next_leader, v->d_leader, B * 4, cudaMemcpyDeviceToHost, v->hcopy));
+        if (reward) CK(cudaMemcpyAsync(reward, v->d_reward, B * 4, cudaMemcpyDeviceToHost, v->hcopy));
+        if (done) CK(cudaMemcpyAsync(done, v->d_done, B, cudaMemcpyDeviceToHost, v->hcopy));
+        reward = nullptr; done = nullptr; next_leader = nullptr;
+    }
     if (agent_obs) CK(cudaMemcpyAsync(agent_obs, v->d_agent, B * A * 6 * 4, cudaMemcpyDeviceToHost, s));
     if (task_obs) CK(cudaMemcpyAsync(task_obs, v->d_task, B * (T + 1) * 5 * 4, cudaMemcpyDeviceToHost, s));
     if (mask) CK(cudaMemcpyAsync(mask, v->d_mask, B * (T + 1), cudaMemcpyDeviceToHost, s));
@@ -1719,6 +1742,7 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
     if (reward) CK(cudaMemcpyAsync(reward, v->d_reward, B * 4, cudaMemcpyDeviceToHost, s));
     if (done) CK(cudaMemcpyAsync(done, v->d_done, B, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (v->forked) CK(cudaStreamSynchronize(v->hcopy));
     return DCM_OK;
 }
 
