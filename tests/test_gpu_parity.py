@@ -274,3 +274,41 @@ def test_fused_pass_equals_split_kernels(shape, policy, variant, monkeypatch):
     assert np.array_equal(ma, mb)
     assert fused.total_steps() == other.total_steps() == B * 600
     fused.close(); other.close()
+
+
+@pytest.mark.parametrize("variant", [None, "DCM_OBS_RESET_BY_EPISODE", "DCM_OBS_CHUNKED"])
+def test_step_host_matches_device_step(variant, monkeypatch):
+    """dcm_step_host (host buffers; next_leader / reward / done leave for the host when k_step ends, beside the episode and
+    observation kernels) against dcm_step with device buffers replaying the same actions: every output of every decision,
+    restarts included (the first leader and the first observation of a restarted episode come from k_step / k_obs_tile in the
+    default pass and from the episode kernel in the variants)."""
+    from dcmrta_b200 import BatchedTaskEnv
+    B, A, T = 1003, 20, 50
+    dev = BatchedTaskEnv(B, A, T, auto_reset=True, seed=21, first_gid=3)
+    dev.generate(max_duration=5.0)
+    dev.reset()
+    if variant:                                                                # read when the handle launches its first observation kernel
+        monkeypatch.setenv(variant, "1")
+    host = BatchedTaskEnv(B, A, T, auto_reset=True, seed=21, first_gid=3)
+    host.generate(max_duration=5.0)
+    host.reset()
+    if variant:
+        monkeypatch.delenv(variant)
+    out = {"next_leader": np.empty(B, np.int32), "reward": np.empty(B, np.float32), "done": np.empty(B, np.uint8),
+           "agent_obs": np.empty((B, A, 6), np.float32), "task_obs": np.empty((B, T + 1, 5), np.float32), "mask": np.empty((B, T + 1), np.uint8)}
+    restarts = 0
+    for k in range(450):
+        dev.step(policy="random")
+        acts = np.ascontiguousarray(dev.used_action.cpu().numpy().astype(np.int32))
+        host.step_host(acts, out)
+        assert np.array_equal(out["next_leader"], dev.leader.cpu().numpy()), k
+        assert np.array_equal(out["reward"], dev.reward.cpu().numpy()), k
+        assert np.array_equal(out["done"], dev.done_u8.cpu().numpy()), k
+        assert np.array_equal(out["agent_obs"], dev.agent_obs.cpu().numpy()), k
+        assert np.array_equal(out["task_obs"], dev.task_obs.cpu().numpy()), k
+        assert np.array_equal(out["mask"], dev.mask_u8.cpu().numpy()), k
+        restarts += int(out["done"].sum())
+        assert (out["next_leader"] >= 0).all(), k                              # auto-reset: every env has a leader after every decision
+    assert restarts > B                                                        # the restart path was exercised
+    assert np.array_equal(dev.export_raw(), host.export_raw())
+    dev.close(); host.close()
