@@ -14,8 +14,8 @@ uniform-random policy over unmasked actions (in-kernel Philox), auto-reset, fp64
   e2e          same metric through the host-buffer C-ABI call (dcm_step_host): actions H2D from pinned memory,
                reward/done/next-leader D2H every step, observations written to the device-resident policy buffers
   e2e_full_obs as e2e but the observations and mask are also copied to pinned host memory every step (PCIe-bound)
-  roofline     HBM: algorithmic bytes/step (w=8) x B / average duration of one pass (k_step, then k_episode on a
-               side stream beside k_obs; CUDA events on the launching stream, which joins the side stream before the next pass)
+  roofline     HBM: algorithmic bytes/step (w=8) x B / average duration of one pass (k_step, then k_episode_list on a
+               side stream beside k_obs_tile; CUDA events on the launching stream, which joins the side stream before the next pass)
                vs MEASURED_PEAKS.json; traffic = ncu DRAM bytes of the same pass
   cpu_baseline the C oracle port of the reference TaskEnv on the host cores, bounded sample of the same workload
 """
@@ -312,7 +312,7 @@ def run_ours(args):
                          "what": "as e2e plus agent_obs/task_obs/mask copied to pinned host memory every step"},
         "gpu_launches": launched, "env_steps_timed": total_steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "one pass = k_step, then k_episode (priority side stream) beside k_obs", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
+                     "kernel": "one pass = k_step, then k_episode_list (priority side stream) beside k_obs_tile", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
                      "launch_us": per_launch_s * 1e6},
         "clocks": clocks,
     }
