@@ -312,3 +312,50 @@ def test_step_host_matches_device_step(variant, monkeypatch):
     assert restarts > B                                                        # the restart path was exercised
     assert np.array_equal(dev.export_raw(), host.export_raw())
     dev.close(); host.close()
+
+
+def test_regenerate_restarts_on_fresh_instances(monkeypatch):
+    """DCM_FLAG_REGENERATE: an env whose episode ended restarts on a NEW instance drawn in the episode kernel's registers (same
+    Philox streams as dcm_generate, instance counter + 1), and that kernel writes the first observation of the new episode
+    beside k_obs_tile.  Checked against (a) the serial pass, where k_obs builds that observation from memory after the
+    restart, and (b) the closed form of a reset observation on the instance read back from the device."""
+    from dcmrta_b200 import BatchedTaskEnv
+    B, A, T = 1003, 20, 50
+    env = BatchedTaskEnv(B, A, T, auto_reset=True, regenerate=True, seed=31, first_gid=9)
+    monkeypatch.setenv("DCM_PASS_SERIAL", "1")
+    ser = BatchedTaskEnv(B, A, T, auto_reset=True, regenerate=True, seed=31, first_gid=9)
+    monkeypatch.delenv("DCM_PASS_SERIAL")
+    for e in (env, ser):
+        e.generate(max_duration=5.0)
+        e.reset()
+    first = {k: v.cpu().numpy().copy() for k, v in env.get_instances().items()}
+    restarted = np.zeros(B, bool)
+    for k in range(450):
+        env.step(policy="random")
+        ser.step(policy="random")
+        done = env.done_u8.cpu().numpy().astype(bool)
+        assert np.array_equal(done, ser.done_u8.cpu().numpy().astype(bool)), k
+        assert np.array_equal(env.leader.cpu().numpy(), ser.leader.cpu().numpy()), k
+        assert np.array_equal(env.reward.cpu().numpy(), ser.reward.cpu().numpy()), k
+        ag, tk, mk = env.agent_obs.cpu().numpy(), env.task_obs.cpu().numpy(), env.mask_u8.cpu().numpy()
+        assert np.array_equal(ag, ser.agent_obs.cpu().numpy()), k
+        assert np.array_equal(tk, ser.task_obs.cpu().numpy()), k
+        assert np.array_equal(mk, ser.mask_u8.cpu().numpy()), k
+        if done.any():
+            inst = {kk: v.cpu().numpy() for kk, v in env.get_instances().items()}
+            for b in np.flatnonzero(done)[:8]:
+                assert not ag[b].any(), (k, b)                                         # nobody has a route (:165-180)
+                want = np.zeros((T + 1, 5), np.float32)
+                want[1:, 0] = inst["req"][b]; want[1:, 1] = inst["req"][b]; want[1:, 2] = inst["dur"][b].astype(np.float32)
+                want[1:, 3:] = (inst["task_xy"][b] - inst["depot_xy"][b]).astype(np.float32)
+                assert np.array_equal(tk[b], want), (k, b)                              # :182-190 seen from the depot
+                assert mk[b, 0] == 1 and not mk[b, 1:].any(), (k, b)                    # only the depot is masked
+            restarted |= done
+    assert restarted.sum() > B // 2
+    last = {k: v.cpu().numpy() for k, v in env.get_instances().items()}
+    moved = (last["task_xy"] != first["task_xy"]).any(axis=(1, 2))
+    assert np.array_equal(moved, restarted)                                             # new instances exactly where an episode ended
+    assert (last["task_xy"] >= 0).all() and (last["task_xy"] < 1).all() and (last["depot_xy"] >= 0).all() and (last["depot_xy"] < 1).all()
+    assert last["req"].min() >= 1 and last["req"].max() <= 5 and (last["dur"] == 5.0).all()
+    assert np.array_equal(env.export_raw(), ser.export_raw())
+    env.close(); ser.close()
