@@ -849,25 +849,18 @@ template <int TW>
 __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const __grid_constant__ EnvArgs E, const __grid_constant__ ObsArgs O, int use_bulk, unsigned long long* trace) {
     extern __shared__ __align__(128) unsigned char obs_smem[];
     const int B = E.S.B, A = E.S.A, T = E.S.T;
-    const unsigned tile_id = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const unsigned NT = (unsigned)E.S.NT, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const ObsTileSmem L = obs_tile_smem(A, T);
     float* sA = (float*)(obs_smem + L.oA); float* sT = (float*)(obs_smem + L.oT); unsigned char* sM = obs_smem + L.oM;
     const double* iX = (const double*)(obs_smem + L.iX); const double* iY = (const double*)(obs_smem + L.iY);
     const double2* iR = (const double2*)(obs_smem + L.iR); const double2* iO = (const double2*)(obs_smem + L.iO);
     const signed char* iS = (const signed char*)(obs_smem + L.iS); const unsigned char* iQ = obs_smem + L.iQ;
     const unsigned bar = smem_u32(obs_smem + L.bar);
-    const int b = (int)(tile_id * 32 + lane);
-    const TC c = make_tc(E, b < B ? b : B - 1);
-    auto stamp = [&](int k) { if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)tile_id * 8 + k] = t; } };
-    stamp(0);
-    if (trace && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); trace[(size_t)tile_id * 8 + 5] = sm; }
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {                                                   // the tile's rows: one contiguous span per array
-        const TC c0 = make_tc(E, (int)(tile_id * 32));                        // lane 0 of the tile
+    const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
+    const unsigned nA = 6u * A, nT = 5u * (T + 1), nM = (unsigned)(T + 1);
+    auto clock_ns = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    auto issue_loads = [&](unsigned tile) {                                   // thread 0: the tile's rows, one contiguous span per array
+        const TC c0 = make_tc(E, (int)(tile * 32));                           // lane 0 of the tile
         const unsigned bytes = 256u * T * 2 + 1024u * A + 512u * A + 32u * T * 2;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
         bulk_load(obs_smem + L.iR, &AREC2(c0, 0, 0), 1024u * A, bar);
@@ -876,119 +869,146 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
         bulk_load(obs_smem + L.iY, &EL(c0, s_ty, T, 0), 256u * T, bar);
         bulk_load(obs_smem + L.iS, &EL(c0, t_status, T, 0), 32u * T, bar);
         bulk_load(obs_smem + L.iQ, &EL(c0, s_req, T, 0), 32u * T, bar);
-    }
-    // per-env scalars of the warp's first chunk, all issued at once and before the leader is known
-    const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
-    int leader = -1; unsigned ended = 0;
-    if (b < B) { leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0); if (O.skip_ended) ended = EL(c, ended, 1, 0); }
-    u64 open[TW]; u64 route = 0, depot = 0, assigned = 0; double now = 0.0, dpx = 0.0, dpy = 0.0; float dq[OBS_ROWS_PER_CHUNK];
-    auto agent_scalars = [&]() { route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); now = EL(c, now, 1, 0); };
-    auto task_scalars = [&](int chunk) {
-        const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
-#pragma unroll
-        for (int w = 0; w < TW; ++w) open[w] = EL(c, m_open, TW, w);
-        if (r0 == 0 || O.skip_ended == 2) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
-#pragma unroll
-        for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) { const int jj = r0 + q; dq[q] = EL(c, s_dur32, T, (jj > 0 && jj <= T) ? jj - 1 : 0); }
     };
-    if ((int)warp < NA) agent_scalars(); else if ((int)warp < NA + NR) task_scalars((int)warp);
-    const bool fresh = ended && O.skip_ended == 2;                            // the restarted episode's first observation (see ObsArgs)
-    if (ended) leader = fresh ? 0 : -1;
-    const bool ok = leader >= 0 && leader < A;
-    const unsigned valid = __ballot_sync(0xffffffffu, ok);                    // the same in every warp of the block
-    stamp(1);
-    mbar_wait(bar, 0);                                                        // (also: never leave with copies in flight into this block's shared memory)
-    stamp(4);
-    if (!valid) return;
-    for (int chunk = (int)warp; chunk < NA + NR; chunk += (int)nwarps) {
-        if (chunk < NA) {                                                     // ---- agent rows (:165-180)
-            if (!O.agent_obs) continue;
-            if (chunk != (int)warp) agent_scalars();
-            if (!ok) continue;
-            const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
-            const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
-            const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
-            float* mine = sA + lane * 6 * A + 6 * c0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < NT) issue_loads(blockIdx.x);
+    // The block walks tiles blockIdx.x, + gridDim.x, ...  Default grid: one block per tile (a single trip).  With two persistent
+    // blocks per SM (DCM_OBS_PERSISTENT=1) the inputs of tile i + 1 land while the TMA engine still reads the staged output of
+    // tile i; measured 138 vs 135 us per pass: the output drain lengthens to 3 us under the extra traffic and the hardware block
+    // scheduler balances the SMs better than a static tile walk beside the episode warps (profiles/r07_persistent_obs.txt).
+    unsigned parity = 0; bool draining = false; unsigned prev_tile = 0;
+    for (unsigned tile_id = blockIdx.x; tile_id < NT; tile_id += gridDim.x) {
+        const int b = (int)(tile_id * 32 + lane);
+        const TC c = make_tc(E, b < B ? b : B - 1);
+        auto stamp = [&](int k) { if (trace && threadIdx.x == 0) trace[(size_t)tile_id * 8 + k] = clock_ns(); };
+        stamp(0);
+        if (trace && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); trace[(size_t)tile_id * 8 + 5] = sm; }
+        // per-env scalars of the warp's first chunk, all issued at once and before the leader is known
+        int leader = -1; unsigned ended = 0;
+        if (b < B) { leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0); if (O.skip_ended) ended = EL(c, ended, 1, 0); }
+        u64 open[TW]; u64 route = 0, depot = 0, assigned = 0; double now = 0.0, dpx = 0.0, dpy = 0.0; float dq[OBS_ROWS_PER_CHUNK];
+        auto agent_scalars = [&]() { route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); now = EL(c, now, 1, 0); };
+        auto task_scalars = [&](int chunk) {
+            const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
+#pragma unroll
+            for (int w = 0; w < TW; ++w) open[w] = EL(c, m_open, TW, w);
+            if (r0 == 0 || O.skip_ended == 2) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
+#pragma unroll
+            for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) { const int jj = r0 + q; dq[q] = EL(c, s_dur32, T, (jj > 0 && jj <= T) ? jj - 1 : 0); }
+        };
+        if ((int)warp < NA) agent_scalars(); else if ((int)warp < NA + NR) task_scalars((int)warp);
+        const bool fresh = ended && O.skip_ended == 2;                        // the restarted episode's first observation (see ObsArgs)
+        if (ended) leader = fresh ? 0 : -1;
+        const bool ok = leader >= 0 && leader < A;
+        const unsigned valid = __ballot_sync(0xffffffffu, ok);                // the same in every warp of the block
+        stamp(1);
+        mbar_wait(bar, parity); parity ^= 1u;                                 // (also: never leave with copies in flight into this block's shared memory)
+        stamp(4);
+        if (draining) {                                                       // the previous tile's staged rows must have been read before they are overwritten
+            if (threadIdx.x == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); if (trace) trace[(size_t)prev_tile * 8 + 3] = clock_ns(); }
+            __syncthreads();
+            draining = false;
+        }
+        if (valid) for (int chunk = (int)warp; chunk < NA + NR; chunk += (int)nwarps) {
+            if (chunk < NA) {                                                 // ---- agent rows (:165-180)
+                if (!O.agent_obs) continue;
+                if (chunk != (int)warp) agent_scalars();
+                if (!ok) continue;
+                const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
+                const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
+                const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+                float* mine = sA + lane * 6 * A + 6 * c0;
 #pragma unroll 5
-            for (int q = 0; q < na; ++q) {
-                const int i = c0 + q; const u64 bit = 1ull << i; const unsigned at = ((unsigned)i << 5) + lane;
-                const double2 xy = iR[at << 1];
-                double travel_t = 0.0, wait = 0.0, remain = 0.0;
-                if (fresh) { float2* r = (float2*)(mine + 6 * q); r[0] = r[1] = r[2] = make_float2(0.f, 0.f); continue; }
-                if ((route & bit) && !(depot & bit)) {                        // :168
-                    const double arr = iR[(at << 1) + 1].x;
-                    const double2 tt = iO[at];                                // {time_start or 0 (Q6), fl(time_start + time)}
-                    const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;                         // :169
-                    if (now <= tt.x) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }     // :170
-                    if (now >= tt.x) { const double qv = tt.y - now; remain = qv < 0.0 ? 0.0 : qv; }  // :171
+                for (int q = 0; q < na; ++q) {
+                    const int i = c0 + q; const u64 bit = 1ull << i; const unsigned at = ((unsigned)i << 5) + lane;
+                    const double2 xy = iR[at << 1];
+                    double travel_t = 0.0, wait = 0.0, remain = 0.0;
+                    if (fresh) { float2* r = (float2*)(mine + 6 * q); r[0] = r[1] = r[2] = make_float2(0.f, 0.f); continue; }
+                    if ((route & bit) && !(depot & bit)) {                    // :168
+                        const double arr = iR[(at << 1) + 1].x;
+                        const double2 tt = iO[at];                            // {time_start or 0 (Q6), fl(time_start + time)}
+                        const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;                         // :169
+                        if (now <= tt.x) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }     // :170
+                        if (now >= tt.x) { const double qv = tt.y - now; remain = qv < 0.0 ? 0.0 : qv; }  // :171
+                    }
+                    float2* r = (float2*)(mine + 6 * q);                      // :176-177 (8-byte aligned: even offsets)
+                    r[0] = make_float2(__double2float_rn(travel_t), __double2float_rn(remain));
+                    r[1] = make_float2(__double2float_rn(wait), __double2float_rn(Lp.x - xy.x));
+                    r[2] = make_float2(__double2float_rn(Lp.y - xy.y), (assigned & bit) ? 1.0f : 0.0f);
                 }
-                float2* r = (float2*)(mine + 6 * q);                          // :176-177 (8-byte aligned: even offsets)
-                r[0] = make_float2(__double2float_rn(travel_t), __double2float_rn(remain));
-                r[1] = make_float2(__double2float_rn(wait), __double2float_rn(Lp.x - xy.x));
-                r[2] = make_float2(__double2float_rn(Lp.y - xy.y), (assigned & bit) ? 1.0f : 0.0f);
+                continue;
             }
+            // ---- task rows (:182-190; row 0 = depot) + mask bytes
+            if (chunk != (int)warp) task_scalars(chunk);
+            if (!ok) continue;
+            const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
+            const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
+            bool any_open = false;
+#pragma unroll
+            for (int w = 0; w < TW; ++w) any_open = any_open || open[w] != 0;
+            double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+            if (fresh) { Lp = make_double2(dpx, dpy); any_open = true; }       // everybody stands at the depot, every task is open
+            float* mine = sT + lane * 5 * (T + 1) + 5 * r0;
+            unsigned char* mm = sM + lane * (T + 1) + r0;
+#pragma unroll
+            for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) if (q < nr) {
+                const int jj = r0 + q; const unsigned at = ((unsigned)(jj > 0 ? jj - 1 : 0) << 5) + lane;
+                float* r = mine + 5 * q;
+                if (O.task_obs) {
+                    if (jj == 0) { r[0] = 0.f; r[1] = 0.f; r[2] = 0.f; r[3] = __double2float_rn(dpx - Lp.x); r[4] = __double2float_rn(dpy - Lp.y); }   // :188 depot row
+                    else {
+                        r[0] = (float)(int)(fresh ? (int)iQ[at] : (int)iS[at]); r[1] = (float)(int)iQ[at]; r[2] = dq[q];   // :185 (s_dur32 = fp32(time)); status = requirements after clear_decisions
+                        r[3] = __double2float_rn(iX[at] - Lp.x); r[4] = __double2float_rn(iY[at] - Lp.y);             // :186
+                    }
+                }
+                // :199 task bit: forbidden unless open;  worker.py:58-61 depot bit: allowed only when nothing is open
+                mm[q] = jj == 0 ? (any_open ? 1 : 0) : ((fresh || tbit<TW>(open, jj - 1)) ? 0 : 1);
+            }
+        }
+        const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
+        const bool whole = use_bulk && ne == 32 && valid == 0xffffffffu;
+        if (whole) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staged rows must be visible to the TMA engine
+        __syncthreads();                                                      // rows staged; nobody reads the staged inputs any more
+        stamp(2);
+        const unsigned next = tile_id + gridDim.x;
+        if (threadIdx.x == 0 && next < NT) issue_loads(next);
+        if (!valid) continue;
+        if (whole) {
+            if (threadIdx.x == 0) {
+                if (O.agent_obs) bulk_store(O.agent_obs + (size_t)tile_id * 32 * nA, sA, 32 * nA * 4);
+                if (O.task_obs) bulk_store(O.task_obs + (size_t)tile_id * 32 * nT, sT, 32 * nT * 4);
+                if (O.mask) bulk_store(O.mask + (size_t)tile_id * 32 * nM, sM, 32 * nM);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            draining = true; prev_tile = tile_id;
             continue;
         }
-        // ---- task rows (:182-190; row 0 = depot) + mask bytes
-        if (chunk != (int)warp) task_scalars(chunk);
-        if (!ok) continue;
-        const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
-        const int nr = T + 1 - r0 < OBS_ROWS_PER_CHUNK ? T + 1 - r0 : OBS_ROWS_PER_CHUNK;
-        bool any_open = false;
-#pragma unroll
-        for (int w = 0; w < TW; ++w) any_open = any_open || open[w] != 0;
-        double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
-        if (fresh) { Lp = make_double2(dpx, dpy); any_open = true; }           // everybody stands at the depot, every task is open
-        float* mine = sT + lane * 5 * (T + 1) + 5 * r0;
-        unsigned char* mm = sM + lane * (T + 1) + r0;
-#pragma unroll
-        for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) if (q < nr) {
-            const int jj = r0 + q; const unsigned at = ((unsigned)(jj > 0 ? jj - 1 : 0) << 5) + lane;
-            float* r = mine + 5 * q;
+        for (int e = (int)warp; e < ne; e += (int)nwarps) {                   // warp <-> env, unit-stride stores; the copies of one env are independent
+            if (!((valid >> e) & 1u)) continue;
+            const size_t be = (size_t)tile_id * 32 + e;
             if (O.task_obs) {
-                if (jj == 0) { r[0] = 0.f; r[1] = 0.f; r[2] = 0.f; r[3] = __double2float_rn(dpx - Lp.x); r[4] = __double2float_rn(dpy - Lp.y); }   // :188 depot row
-                else {
-                    r[0] = (float)(int)(fresh ? (int)iQ[at] : (int)iS[at]); r[1] = (float)(int)iQ[at]; r[2] = dq[q];   // :185 (s_dur32 = fp32(time)); status = requirements after clear_decisions
-                    r[3] = __double2float_rn(iX[at] - Lp.x); r[4] = __double2float_rn(iY[at] - Lp.y);             // :186
-                }
-            }
-            // :199 task bit: forbidden unless open;  worker.py:58-61 depot bit: allowed only when nothing is open
-            mm[q] = jj == 0 ? (any_open ? 1 : 0) : ((fresh || tbit<TW>(open, jj - 1)) ? 0 : 1);
-        }
-    }
-    const int ne = B - (int)(tile_id * 32) < 32 ? B - (int)(tile_id * 32) : 32;
-    const bool whole = use_bulk && ne == 32 && valid == 0xffffffffu;
-    if (whole) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staged rows must be visible to the TMA engine
-    __syncthreads();
-    stamp(2);
-    const unsigned nA = 6u * A, nT = 5u * (T + 1), nM = (unsigned)(T + 1);
-    if (whole) {
-        if (threadIdx.x == 0) {
-            if (O.agent_obs) bulk_store(O.agent_obs + (size_t)tile_id * 32 * nA, sA, 32 * nA * 4);
-            if (O.task_obs) bulk_store(O.task_obs + (size_t)tile_id * 32 * nT, sT, 32 * nT * 4);
-            if (O.mask) bulk_store(O.mask + (size_t)tile_id * 32 * nM, sM, 32 * nM);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory is released when the block exits
-            stamp(3);
-        }
-        return;
-    }
-    for (int e = (int)warp; e < ne; e += (int)nwarps) {                       // warp <-> env, unit-stride stores; the copies of one env are independent
-        if (!((valid >> e) & 1u)) continue;
-        const size_t be = (size_t)tile_id * 32 + e;
-        if (O.task_obs) {
-            const float* src = sT + e * nT; float* dst = O.task_obs + be * nT;
+                const float* src = sT + e * nT; float* dst = O.task_obs + be * nT;
 #pragma unroll 8
-            for (unsigned k = lane; k < nT; k += 32) dst[k] = src[k];
-        }
-        if (O.agent_obs) {
-            const float* src = sA + e * nA; float* dst = O.agent_obs + be * nA;
+                for (unsigned k = lane; k < nT; k += 32) dst[k] = src[k];
+            }
+            if (O.agent_obs) {
+                const float* src = sA + e * nA; float* dst = O.agent_obs + be * nA;
 #pragma unroll 4
-            for (unsigned k = lane; k < nA; k += 32) dst[k] = src[k];
+                for (unsigned k = lane; k < nA; k += 32) dst[k] = src[k];
+            }
+            if (O.mask) for (unsigned k = lane; k < nM; k += 32) O.mask[be * nM + k] = sM[e * nM + k];
         }
-        if (O.mask) for (unsigned k = lane; k < nM; k += 32) O.mask[be * nM + k] = sM[e * nM + k];
+        __syncthreads();                                                      // the staged rows are free again
+        if (trace && threadIdx.x == 0) trace[(size_t)tile_id * 8 + 3] = clock_ns() | (1ull << 63);
     }
-    if (trace) { __syncthreads(); if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[(size_t)tile_id * 8 + 3] = t | (1ull << 63); } }
+    if (draining && threadIdx.x == 0) {                                       // shared memory is released when the block exits
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (trace) trace[(size_t)prev_tile * 8 + 3] = clock_ns();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1356,6 +1376,7 @@ struct dcm_env {
     int* d_action; float* d_agent; float* d_task; unsigned char* d_mask; int* d_leader; float* d_reward; unsigned char* d_done;
     cudaStream_t hstream, hcopy; bool forked;   // dcm_step_host: its stream; a second one for the results k_step alone produces; the last dcm_step recorded ev_fork
     cudaStream_t side; cudaEvent_t ev_fork, ev_join;   // k_episode runs beside k_obs
+    bool obs_persistent; int sm_count;
     bool obs_ready, obs_tile, obs_resets;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs); it also writes restarted envs' observations
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
     uint64_t launches;
@@ -1537,9 +1558,11 @@ static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
     const int warps = NA + NR < OBS_TILE_MAX_WARPS ? NA + NR : OBS_TILE_MAX_WARPS;
     const size_t smem = obs_tile_smem(A, T).total;
     const int use_bulk = (((uintptr_t)O.agent_obs | (uintptr_t)O.task_obs | (uintptr_t)O.mask) & 15u) == 0;
-    if (v->E.S.TW == 1) k_obs_tile<1><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
-    else if (v->E.S.TW == 2) k_obs_tile<2><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
-    else k_obs_tile<4><<<v->E.S.NT, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    int grid = v->E.S.NT;                                                    // one block per tile (DCM_OBS_PERSISTENT=1: two persistent blocks per SM walk the tiles)
+    if (v->obs_persistent && grid > 2 * v->sm_count) grid = 2 * v->sm_count;
+    if (v->E.S.TW == 1) k_obs_tile<1><<<grid, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    else if (v->E.S.TW == 2) k_obs_tile<2><<<grid, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    else k_obs_tile<4><<<grid, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
@@ -1550,6 +1573,8 @@ static int prepare_obs(dcm_env* v) {
     if (v->obs_ready) return DCM_OK;
     v->obs_ready = true; v->obs_tile = false;
     { const char* gr = getenv("DCM_OBS_RESET_BY_EPISODE"); v->obs_resets = !(gr && gr[0] == '1'); }
+    { const char* gp = getenv("DCM_OBS_PERSISTENT"); v->obs_persistent = gp && gp[0] == '1'; }   // measured slower than one block per tile, DESIGN.md section 4
+    CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device));
     const char* gs = getenv("DCM_OBS_CHUNKED");
     if (gs && gs[0] == '1') return DCM_OK;
     int optin = 0, per_sm = 0;
