@@ -109,7 +109,8 @@ int dcm_reset(dcm_env* env, const uint8_t* which_d, const int32_t* leader_in_d,
  *   followers_d      [B, fstride] i32, -1 padded: the followers random_choice drew (task_env.py:331); NULL = Philox
  *   next_leader_in_d [B] i32 the leader np.random.choice(group) returned for the NEXT decision; NULL = Philox
  *   agent_obs_d [B,A,6] f32   task_obs_d [B,T+1,5] f32   mask_d [B,T+1] u8 (1 = forbidden)
- *   next_leader_d [B] i32 (-1 when done)   reward_d [B] f32 (task_env.py:341)   done_d [B] u8
+ *   next_leader_d [B] i32 (-1 when done; with DCM_FLAG_AUTO_RESET the first leader of the restarted episode)
+ *   reward_d [B] f32 (task_env.py:341)   done_d [B] u8
  *   used_action_d [B] i32 or NULL: the action that was applied (what a built-in policy chose; -1 if the env did not step)
  * Envs already done (and not auto-reset) are left untouched and report done=1. */
 int dcm_step(dcm_env* env, const int32_t* action_d, const int32_t* followers_d, int fstride,
@@ -118,7 +119,8 @@ int dcm_step(dcm_env* env, const int32_t* action_d, const int32_t* followers_d, 
              int32_t* next_leader_d, float* reward_d, uint8_t* done_d, int32_t* used_action_d, void* stream);
 
 /* Same call with HOST buffers (pageable or pinned): actions are copied in, outputs copied out, the call returns when the
- * outputs are valid.  Any output pointer may be NULL (then it is not copied). */
+ * outputs are valid.  Any output pointer may be NULL (then it is not copied).  next_leader, reward and done are final when the
+ * step kernel ends and are copied on a second stream while the episode and observation kernels still run. */
 int dcm_step_host(dcm_env* env, const int32_t* action_h, int policy,
                   float* agent_obs_h, float* task_obs_h, uint8_t* mask_h,
                   int32_t* next_leader_h, float* reward_h, uint8_t* done_h);
