@@ -33,7 +33,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "env-steps/sec at 20A/50T"
+METRIC = "env-steps/sec at 20A/50T"          # the headline shape; other --agents/--tasks name theirs (metric_name)
 UNIT = "env-steps/s"
 FALLBACK_HBM_GBS = 6650.0           # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -44,7 +44,12 @@ def parse():
     p.add_argument("--steps", type=int, default=2000)
     p.add_argument("--warmup", type=int, default=200)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    p.add_argument("--envs", type=int, default=65536, help="envs per GPU (weak scaling)")
+    p.add_argument("--total-envs", type=int, default=0, help="BASELINE configs[3]: this many envs in total, sharded evenly over the GPUs "
+                                                              "(strong scaling; overrides --envs)")
+    p.add_argument("--preroll", type=int, default=400, help="untimed passes after reset and before the warm-up, so that the timed passes see "
+                                                            "the steady state (envs desynchronised, episodes ending every pass) whatever --warmup is")
+    p.add_argument("--no-e2e", action="store_true", help="skip the e2e legs (shape sweeps)")
     p.add_argument("--agents", type=int, default=20)
     p.add_argument("--tasks", type=int, default=50)
     p.add_argument("--policy", default="random", choices=["random", "greedy"])
@@ -57,6 +62,10 @@ def parse():
     p.add_argument("--iters", type=int, default=3, help="--mode rollout/train: timed iterations (one episode per env each)")
     p.add_argument("--amp", action="store_true", help="--mode rollout/train: bf16 autocast for the rollout forward passes")
     return p.parse_args()
+
+
+def metric_name(args):
+    return METRIC if (args.agents, args.tasks) == (20, 50) else f"env-steps/sec at {args.agents}A/{args.tasks}T"
 
 
 def peaks():
@@ -166,7 +175,7 @@ def run_reference(args):
     # threads, i.e. one "step" = total/K decisions spread over the thread pool
     rate, cores, total, dt, rate1 = cpu_rollout(args.agents, args.tasks, args.policy, args.cpu_seconds)
     line = {
-        "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args), "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "impl": "reference",
         "config": {"workload": f"synthetic {args.agents}A/{args.tasks}T TaskEnv, {args.policy} policy, obs+mask built every decision",
@@ -187,7 +196,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from dcmrta_b200 import BatchedTaskEnv
-    from dcmrta_b200.sharding import dist_env, shard_range
+    from dcmrta_b200.sharding import dist_env, reduce_job_totals, shard_range
 
     rank, local, world = dist_env()
     if world != args.gpus and world == 1 and args.gpus > 1:
@@ -205,15 +214,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     A, T = args.agents, args.tasks
-    first_gid, B = shard_range(args.envs * world, rank, world)      # weak scaling: args.envs per GPU, global ids are shard-invariant
+    strong = args.total_envs > 0
+    # weak scaling: args.envs per GPU; strong (--total-envs, BASELINE configs[3]): a fixed job sharded evenly.  Global ids are shard-invariant.
+    first_gid, B = shard_range(args.total_envs if strong else args.envs * world, rank, world)
     env = BatchedTaskEnv(B, A, T, M=5, device=local, auto_reset=True, seed=1234, first_gid=first_gid)
     env.generate(max_duration=5.0)
     env.reset()
+    # Pre-roll to the steady state (">= 200 steps warm-up").  After a synchronised reset every env is in its
+    # first slot and no episode ends for ~130 passes; the workload the metric is quoted on has the envs desynchronised, with ~B/150
+    # episodes ending (accounting + restart) in every pass.  Untimed, ~50 ms.
+    for _ in range(max(args.preroll, 0)):
+        env.step(policy=args.policy)
     launches0 = env.launch_count()
     for _ in range(args.warmup):
         env.step(policy=args.policy)
     barrier()
     steps0 = env.total_steps()
+    episodes0 = env.total_episodes()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -238,12 +255,10 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     env_steps = env.total_steps() - steps0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([env_steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, total_steps = float(t.item()), float(cnt.item())
+    episodes_timed = env.total_episodes() - episodes0
+    total_steps, ms_max = reduce_job_totals(env_steps, ms)          # env-steps summed over the ranks, time = max over the ranks
+    ep_timed_all, _ = reduce_job_totals(episodes_timed, 0.0)
+    ep_before_all, _ = reduce_job_totals(episodes0, 0.0)
     value = total_steps / (ms_max * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call ---------------------------------------------------------------
@@ -279,8 +294,11 @@ def run_ours(args):
         d2h = sum(v.numel() * v.element_size() for v in out.values())
         return world * B * K / float(tt.item()), 4 * B, d2h
 
-    e_val, e_h2d, e_d2h = e2e(False)
-    f_val, f_h2d, f_d2h = e2e(True)
+    if args.no_e2e:
+        e_val = f_val = None; e_h2d = f_h2d = e_d2h = f_d2h = 0
+    else:
+        e_val, e_h2d, e_d2h = e2e(False)
+        f_val, f_h2d, f_d2h = e2e(True)
 
     if rank != 0:
         if world > 1:
@@ -290,20 +308,27 @@ def run_ours(args):
     bytes_step = algorithmic_bytes(A, T)
     per_launch_s = ms_max * 1e-3 / args.steps
     achieved = bytes_step * B / per_launch_s / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.load(open(tf)).get(f"{A}x{T}x{B}")
+            tj = json.load(open(tf))
+            traffic = tj.get(f"{A}x{T}x{B}")
+            if traffic is not None:
+                traffic_source = tj.get("source", "ncu --set full capture of one steady-state pass of this workload (profiles/), not of the timed passes")
         except Exception:
             traffic = None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{B} synthetic {A}A/{T}T envs per GPU (BASELINE configs[2]), {args.policy} policy (in-kernel Philox), auto-reset, "
-                               f"fp64 event clock, fp32 obs; one step = one leader decision per env",
-                   "envs_per_gpu": B, "agents": A, "tasks": T, "max_coalition": 5,
+        "config": {"workload": (f"{args.total_envs} synthetic {A}A/{T}T envs sharded evenly over {world} GPU(s) (BASELINE configs[3])" if strong else
+                                f"{B} synthetic {A}A/{T}T envs per GPU (BASELINE configs[2])") +
+                               f", {args.policy} policy (in-kernel Philox), auto-reset, fp64 event clock, fp32 obs; one step = one leader decision per env",
+                   "envs_per_gpu": B, "total_envs": args.total_envs if strong else B * world, "agents": A, "tasks": T, "max_coalition": 5,
+                   "phase": {"preroll_passes": args.preroll, "episodes_completed_before_timing": ep_before_all,
+                             "ended_envs_per_pass": ep_timed_all / max(args.steps, 1),
+                             "what": "steady state: envs desynchronised by the pre-roll, episode accounting + restart inside every timed pass"},
                    "l2": f"state {B * (env.record_bytes() + env.layout['sta_bytes']) / 1e6:.0f} MB + obs {B * 1551 / 1e6:.0f} MB per GPU > 126 MB L2, streamed every step (no flush needed)",
                    "parallelism": f"env shards x{world}, no data-path collective"},
         "e2e": {"value": e_val, "unit": UNIT, "h2d_bytes_per_step": e_h2d, "d2h_bytes_per_step": e_d2h,
@@ -311,7 +336,7 @@ def run_ours(args):
         "e2e_full_obs": {"value": f_val, "unit": UNIT, "h2d_bytes_per_step": f_h2d, "d2h_bytes_per_step": f_d2h,
                          "what": "as e2e plus agent_obs/task_obs/mask copied to pinned host memory every step"},
         "gpu_launches": launched, "env_steps_timed": total_steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                      "kernel": "one pass = k_step, then k_episode_list (priority side stream) beside k_obs_tile", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
                      "launch_us": per_launch_s * 1e6},
         "clocks": clocks,

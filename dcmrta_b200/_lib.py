@@ -60,6 +60,7 @@ SIGNATURES = {
     "dcm_layout": (i32, [vp, vp, i32]),
     "dcm_env_flags": (i32, [vp, vp, vp]),
     "dcm_total_steps": (i32, [vp, C.POINTER(u64)]),
+    "dcm_total_episodes": (i32, [vp, C.POINTER(u64)]),
     "dcm_algorithmic_bytes_per_step": (sz, [vp]),
     "dcm_launch_count": (u64, [vp]),
     "dcm_debug_pass_trace": (i32, [vp, vp, sz]),

@@ -146,6 +146,12 @@ class BatchedTaskEnv:
         check(lib().dcm_reset(self._h, _ptr(w), _ptr(l), _ptr(self.agent_obs), _ptr(self.task_obs), _ptr(self.mask_u8),
                               _ptr(self.leader), self._stream()))
         self._keep = [w, l]
+        # dcm_reset does not write the per-step outputs: a restarted env is not done and has earned nothing yet
+        if w is None:
+            self.done_u8.zero_(); self.reward.zero_()
+        else:
+            sel = w.view(torch.bool)
+            self.done_u8.masked_fill_(sel, 0); self.reward.masked_fill_(sel, 0.0)
         return self.agent_obs, self.task_obs, self.mask, self.leader
 
     def step(self, actions=None, followers=None, next_leaders=None, policy="external"):
@@ -261,6 +267,11 @@ class BatchedTaskEnv:
     def total_steps(self):
         out = C.c_uint64()
         check(lib().dcm_total_steps(self._h, C.byref(out)))
+        return out.value
+
+    def total_episodes(self):
+        out = C.c_uint64()
+        check(lib().dcm_total_episodes(self._h, C.byref(out)))
         return out.value
 
     def launch_count(self):

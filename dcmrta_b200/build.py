@@ -35,19 +35,33 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    if force or stale():
-        cmd = [nvcc(), *NVCC_FLAGS, "-o", str(SO), *map(str, SOURCES)]
-        # DCM_BUILD_FAST=1 (development only): optimise the kernels of the one translation unit in parallel, 3 min -> under 1.
-        # Not the default: register allocation then differs from build to build (k_step 0..64 B of spills, k_obs_tile 76..94 registers).
-        if os.environ.get("DCM_BUILD_FAST") == "1":
-            cmd[1:1] = ["--split-compile", "0"]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-        if verbose:
-            print(r.stderr)
+    """Compile to a temporary file and os.replace() it into place under an exclusive file lock: N ranks of one torchrun job
+    that all find the library stale build it once, and nobody ever dlopens a half-written file."""
+    if not (force or stale()):
+        return SO
+    import fcntl
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():            # another process built it while we waited
+                return SO
+            tmp = SO.with_name(f".{SO.name}.{os.getpid()}.tmp")
+            cmd = [nvcc(), *NVCC_FLAGS, "-o", str(tmp), *map(str, SOURCES)]
+            # DCM_BUILD_FAST=1 (development only): optimise the kernels of the one translation unit in parallel, 3 min -> under 1.
+            # Not the default: register allocation then differs from build to build (k_step 0..64 B of spills, k_obs_tile 76..94 registers).
+            if os.environ.get("DCM_BUILD_FAST") == "1":
+                cmd[1:1] = ["--split-compile", "0"]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, SO)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 

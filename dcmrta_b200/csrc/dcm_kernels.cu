@@ -1338,6 +1338,13 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
     EL(c, total, 1, 0) = h.total_steps;
 }
 
+__global__ void k_sum_episodes(const __grid_constant__ EnvArgs E, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < E.S.B; b += gridDim.x * blockDim.x) { const TC c = make_tc(E, b); acc += EL(c, episode, 1, 0); }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 __global__ void k_sum_steps(const __grid_constant__ EnvArgs E, unsigned long long* out) {
     unsigned long long acc = 0;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < E.S.B; b += gridDim.x * blockDim.x) { const TC c = make_tc(E, b); acc += EL(c, total, 1, 0); }
@@ -1379,8 +1386,15 @@ struct dcm_env {
     bool obs_persistent; int sm_count;
     bool obs_ready, obs_tile, obs_resets;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs); it also writes restarted envs' observations
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
+    // DCM_* experiment switches, read ONCE in dcm_create (never on the step path)
+    bool sw_obs_reset_by_episode, sw_obs_chunked, sw_episode_carveout_default; int epi_warps, epi_per_sm;
+    // dcm_step_host runs on its own stream: it must start after the asynchronous work earlier calls queued on the CALLER's stream
+    cudaStream_t last_stream; bool last_pending; cudaEvent_t ev_order;
     uint64_t launches;
 };
+
+// remember the stream an asynchronous entry point queued work on (dcm_step_host orders itself after it)
+static inline void note_stream(dcm_env* v, cudaStream_t s) { if (s != v->hstream || !v->hstream) { v->last_stream = s; v->last_pending = true; } }
 
 struct DeviceGuard {
     int prev, target; bool ok;
@@ -1447,6 +1461,15 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_ecount, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(v->d_ecount, 0, 2 * sizeof(unsigned));
     { const char* gs = getenv("DCM_EPISODE_DENSE"); v->dense_episode = gs && gs[0] == '1'; }
+    {   // every other experiment switch, once per handle
+        auto on = [](const char* name) { const char* g = getenv(name); return g && g[0] == '1'; };
+        v->sw_obs_reset_by_episode = on("DCM_OBS_RESET_BY_EPISODE"); v->obs_persistent = on("DCM_OBS_PERSISTENT");   // persistent: measured slower than one block per tile, DESIGN.md section 4
+        v->sw_obs_chunked = on("DCM_OBS_CHUNKED"); v->sw_episode_carveout_default = on("DCM_EPISODE_CARVEOUT_DEFAULT");
+        v->epi_warps = 2; { const char* gw = getenv("DCM_EPISODE_WARPS"); if (gw && atoi(gw) >= 1 && atoi(gw) <= EPI_LIST_MAX_WARPS) v->epi_warps = atoi(gw); }   // envs (warps) per block
+        v->epi_per_sm = 8; { const char* gg = getenv("DCM_EPISODE_GRID"); if (gg && atoi(gg) > 0) v->epi_per_sm = atoi(gg); }                                  // warps per SM
+    }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_order, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_ctl, sizeof(PassCtl));
     if (e == cudaSuccess) e = cudaMemset(v->d_ctl, 0, sizeof(PassCtl));
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_queue, (size_t)NT * sizeof(unsigned long long));
@@ -1484,6 +1507,7 @@ int dcm_destroy(dcm_env* v) {
     if (v->side) cudaStreamDestroy(v->side);
     if (v->ev_fork) cudaEventDestroy(v->ev_fork);
     if (v->ev_join) cudaEventDestroy(v->ev_join);
+    if (v->ev_order) cudaEventDestroy(v->ev_order);
     delete v;
     return DCM_OK;
 }
@@ -1506,6 +1530,7 @@ int dcm_load_instances(dcm_env* v, const double* task_xy, const double* depot_xy
     DeviceGuard g(v->device);
     k_pack_static<<<grid_env(v, 128), 128, 0, (cudaStream_t)stream>>>(v->E, task_xy, depot_xy, req, dur);
     CK(cudaGetLastError());
+    note_stream(v, (cudaStream_t)stream);
     v->launches++; v->have_instances = true;
     return DCM_OK;
 }
@@ -1537,6 +1562,7 @@ int dcm_generate(dcm_env* v, double max_duration, int random_duration, void* str
     v->E.gen_max_duration = max_duration; v->E.gen_random_duration = random_duration;
     k_generate<<<grid_env(v, 128), 128, 0, (cudaStream_t)stream>>>(v->E, v->have_instances ? 1 : 0);
     CK(cudaGetLastError());
+    note_stream(v, (cudaStream_t)stream);
     v->launches++; v->have_instances = true;
     return DCM_OK;
 }
@@ -1572,11 +1598,8 @@ static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 static int prepare_obs(dcm_env* v) {
     if (v->obs_ready) return DCM_OK;
     v->obs_ready = true; v->obs_tile = false;
-    { const char* gr = getenv("DCM_OBS_RESET_BY_EPISODE"); v->obs_resets = !(gr && gr[0] == '1'); }
-    { const char* gp = getenv("DCM_OBS_PERSISTENT"); v->obs_persistent = gp && gp[0] == '1'; }   // measured slower than one block per tile, DESIGN.md section 4
-    CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device));
-    const char* gs = getenv("DCM_OBS_CHUNKED");
-    if (gs && gs[0] == '1') return DCM_OK;
+    v->obs_resets = !v->sw_obs_reset_by_episode;
+    if (v->sw_obs_chunked) return DCM_OK;
     int optin = 0, per_sm = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, v->device));
     CK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, v->device));
@@ -1590,11 +1613,10 @@ static int prepare_obs(dcm_env* v) {
     // after the other, profiles/r03_timeline.txt), so it asks for the same split.
     const void* fe = v->E.S.TW == 1 ? (const void*)k_episode_list<1> : v->E.S.TW == 2 ? (const void*)k_episode_list<2> : (const void*)k_episode_list<4>;
     const void* fd = v->E.S.TW == 1 ? (const void*)k_episode<1> : v->E.S.TW == 2 ? (const void*)k_episode<2> : (const void*)k_episode<4>;
-    { const char* gc = getenv("DCM_EPISODE_CARVEOUT_DEFAULT");
-      if (!(gc && gc[0] == '1')) {
-          CK(cudaFuncSetAttribute(fe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          CK(cudaFuncSetAttribute(fd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      } }
+    if (!v->sw_episode_carveout_default) {
+        CK(cudaFuncSetAttribute(fe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(fd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     v->obs_tile = true;
     return DCM_OK;
 }
@@ -1612,10 +1634,9 @@ static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
 }
 
 static int launch_episode_list(dcm_env* v, const EpiArgs& P, const unsigned* ecount, cudaStream_t s) {
-    int nw = 2; { const char* gw = getenv("DCM_EPISODE_WARPS"); if (gw && atoi(gw) >= 1 && atoi(gw) <= EPI_LIST_MAX_WARPS) nw = atoi(gw); }   // envs (warps) per block
+    const int nw = v->epi_warps;                                              // envs (warps) per block
     const size_t smem = nw * ((epi_scratch_bytes(v->E.S.A, v->E.S.T, v->E.S.MC) + 15) / 16 * 16);
-    int per_sm = 8; { const char* gg = getenv("DCM_EPISODE_GRID"); if (gg && atoi(gg) > 0) per_sm = atoi(gg); }              // experiment switch: warps per SM
-    int grid = (148 * per_sm + nw - 1) / nw; if (grid > v->E.S.B) grid = v->E.S.B;
+    int grid = (v->sm_count * v->epi_per_sm + nw - 1) / nw; if (grid > v->E.S.B) grid = v->E.S.B;
     if (v->d_trace) CK(cudaMemsetAsync(v->d_trace + (size_t)v->E.S.NT * 8, 0, (size_t)grid * nw * 4 * sizeof(unsigned long long), s));
     if (v->E.S.TW == 1) k_episode_list<1><<<grid, 32 * nw, smem, s>>>(v->E, P, v->d_elist, ecount, v->d_trace);
     else if (v->E.S.TW == 2) k_episode_list<2><<<grid, 32 * nw, smem, s>>>(v->E, P, v->d_elist, ecount, v->d_trace);
@@ -1642,6 +1663,7 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_reset: load or generate instances first");
     DeviceGuard g(v->device);
     cudaStream_t s = (cudaStream_t)stream;
+    note_stream(v, s);
     CK(cudaMemsetAsync(v->d_ctl, 0, sizeof(PassCtl), s));                     // k_pass work-queue counters (they reset themselves; this heals an aborted launch)
     EpiArgs P{1, which, leader_in, next_leader, v->metrics, ObsArgs{nullptr, nullptr, nullptr, nullptr, 0}, 0};
     int rc = launch_episode(v, P, s);
@@ -1660,6 +1682,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     if (followers && fstride < 0) return fail(DCM_ERR_ARG, "dcm_step: negative follower stride");
     DeviceGuard g(v->device);
     cudaStream_t s = (cudaStream_t)stream;
+    note_stream(v, s);
     StepArgs F; memset(&F, 0, sizeof F);
     F.action = action; F.followers = followers; F.fstride = fstride; F.leader_in = next_leader_in; F.policy = policy;
     F.next_leader = next_leader; F.reward = reward; F.done = done; F.used_action = used_action;
@@ -1747,6 +1770,13 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
     if (rc) return rc;
     const size_t B = v->E.S.B, A = v->E.S.A, T = v->E.S.T;
     cudaStream_t s = v->hstream;
+    // hstream is a non-blocking stream: order it after whatever earlier calls (dcm_reset, dcm_generate, dcm_load_instances, dcm_step,
+    // granular ops, dcm_import_state) queued asynchronously on the caller's stream -- including the legacy NULL stream
+    if (v->last_pending) {
+        CK(cudaEventRecord(v->ev_order, v->last_stream));
+        CK(cudaStreamWaitEvent(s, v->ev_order, 0));
+        v->last_pending = false;
+    }
     if (action) CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
     v->forked = false;
     rc = dcm_step(v, v->d_action, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
@@ -1783,6 +1813,7 @@ static int launch_gran(dcm_env* v, const GranArgs& G, void* stream) {
     DeviceGuard g(v->device);
     LAUNCH_TW(v, k_granular, grid_env(v, STEP_THREADS), STEP_THREADS, (cudaStream_t)stream, v->E, G);
     CK(cudaGetLastError());
+    note_stream(v, (cudaStream_t)stream);
     v->launches++;
     return DCM_OK;
 }
@@ -1818,6 +1849,7 @@ int dcm_build_obs(dcm_env* v, const int32_t* leader, float* agent_obs, float* ta
     if (!v->have_instances) return fail(DCM_ERR_STATE, "dcm_build_obs: load or generate instances first");
     DeviceGuard g(v->device);
     ObsArgs O{leader, agent_obs, task_obs, mask, 0};
+    note_stream(v, (cudaStream_t)stream);
     return launch_obs(v, O, (cudaStream_t)stream);
 }
 int dcm_check_finished(dcm_env* v, uint8_t* finished, void* stream) {
@@ -1839,6 +1871,7 @@ int dcm_execute_by_route(dcm_env* v, const int32_t* routes, int rstride, const i
     if (!v->d_cursor) CK(cudaMalloc(&v->d_cursor, (size_t)v->E.S.B * v->E.S.A));
     LAUNCH_TW(v, k_routes, grid_env(v, STEP_THREADS), STEP_THREADS, (cudaStream_t)stream, v->E, routes, rstride, route_len, v->d_cursor, makespan);
     CK(cudaGetLastError());
+    note_stream(v, (cudaStream_t)stream);
     v->launches++;
     return DCM_OK;
 }
@@ -1869,6 +1902,7 @@ int dcm_import_state(dcm_env* v, const void* src, size_t bytes, void* stream) {
     CK(cudaMemcpyAsync(v->d_record, src, need, cudaMemcpyDefault, s));
     LAUNCH_TW(v, k_import, grid_env(v, 128), 128, s, v->E, v->L, v->d_record);
     CK(cudaGetLastError());
+    note_stream(v, s);
     v->launches++;
     return DCM_OK;
 }
@@ -1888,7 +1922,20 @@ int dcm_total_steps(dcm_env* v, uint64_t* out) {
     if (!v || !out) return fail(DCM_ERR_ARG, "dcm_total_steps: NULL argument");
     DeviceGuard g(v->device);
     CK(cudaMemset(v->d_counter, 0, sizeof(unsigned long long)));
-    k_sum_steps<<<148, 256>>>(v->E, v->d_counter);
+    k_sum_steps<<<v->sm_count, 256>>>(v->E, v->d_counter);
+    CK(cudaGetLastError());
+    v->launches++;
+    unsigned long long h = 0;
+    CK(cudaMemcpy(&h, v->d_counter, sizeof h, cudaMemcpyDeviceToHost));
+    *out = h;
+    return DCM_OK;
+}
+
+int dcm_total_episodes(dcm_env* v, uint64_t* out) {
+    if (!v || !out) return fail(DCM_ERR_ARG, "dcm_total_episodes: NULL argument");
+    DeviceGuard g(v->device);
+    CK(cudaMemset(v->d_counter, 0, sizeof(unsigned long long)));
+    k_sum_episodes<<<v->sm_count, 256>>>(v->E, v->d_counter);
     CK(cudaGetLastError());
     v->launches++;
     unsigned long long h = 0;

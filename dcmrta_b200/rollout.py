@@ -24,9 +24,9 @@ from .policy import greedy_actions, sample_actions
 @dataclass
 class Episodes:
     """Result of one batched rollout.  L = decisions actually played (max over envs)."""
-    reward: torch.Tensor        # [B] f64   -makespan (get_episode_reward, task_env.py:420-425); NaN where the env did not end within the horizon
+    reward: torch.Tensor        # [B] f64   -makespan (get_episode_reward, task_env.py:420-425); -current_time where the horizon cut the episode
     metrics: torch.Tensor       # [B,8] f64 reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions
-    ended: torch.Tensor         # [B] bool
+    ended: torch.Tensor         # [B] bool  False = cut by the buffer horizon before the env was done
     length: int
     # experience (None when record=False); index [t, b]
     agent_obs: torch.Tensor | None = None   # [L,B,A,6]  f32
@@ -82,7 +82,12 @@ class BatchedRollout:
                 break
         ended = env.done.clone()
         metrics = env.episode_metrics()
-        reward = torch.where(ended, metrics[:, 0], torch.full_like(metrics[:, 0], float("nan")))
+        if not bool(ended.all()):
+            # Episodes cut by the buffer horizon: scored like the reference scores an episode cut at MAX_TIME (worker.py:45, :87 ->
+            # get_episode_reward = -current_time, task_env.py:420-425), from the state they stopped in -- never dropped from training.
+            live = env.compute_metrics()
+            metrics = torch.where(ended.unsqueeze(1), metrics, live)
+        reward = metrics[:, 0].clone()
         if was_training:
             net.train()
         ep = Episodes(reward=reward, metrics=metrics, ended=ended, length=t)

@@ -64,6 +64,20 @@ def allreduce_gradients(module: torch.nn.Module) -> None:
         g.copy_(q)
 
 
+def agreed_update_count(n_local: int, batch_size: int, updates_per_iteration: int = 0) -> int:
+    """Optimiser steps of this iteration, IDENTICAL on every rank: each step is one gradient all-reduce, and the number of decisions a
+    rank collected (n_local) differs from rank to rank, so the ranks agree on min(n_local) first (one scalar all_reduce MIN).  0 when
+    some rank has nothing to train on (then nobody updates).  `updates_per_iteration` > 0 overrides the count, not the agreement."""
+    n_min = int(n_local)
+    if world()[1] > 1:
+        t = torch.tensor([n_min], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        n_min = int(t.item())
+    if n_min == 0:
+        return 0
+    return int(updates_per_iteration) or max(1, n_min // int(batch_size))
+
+
 def reinforce_update(net, optimizer, lr_decay, tasks, agents, mask, action, advantage, max_norm: float = 10.0):
     """One optimiser step on one mini-batch (driver.py:162-176).  action [N] int64, advantage [N] fp32.  Returns diagnostics."""
     logp_list = net(tasks, agents, mask)
@@ -146,19 +160,20 @@ class ReinforceTrainer:
         clone_instances(self.env, self.base_env)
         ep = self.rollout.run(self.net, "sample", self.gen, amp=cfg.amp)
         base = self.base_rollout.run(self.baseline, "greedy", amp=cfg.amp)
-        valid = ep.ended & base.ended
-        adv_env = torch.where(valid, ep.reward - base.reward, torch.zeros_like(ep.reward)).float()        # worker.py:93
+        # every episode trains, as in the reference (worker.py:87-101): one the horizon cut is scored -current_time like a MAX_TIME cut
+        valid = torch.ones_like(ep.ended)
+        adv_env = (ep.reward - base.reward).float()                                                       # worker.py:93
         use = ep.active & valid.unsqueeze(0)
         idx = use.nonzero(as_tuple=False)                            # [N,2] (t, b)
         N = idx.shape[0]
         perm = torch.randperm(N, device=self.device, generator=self.gen)
-        n_up = cfg.updates_per_iteration or max(1, N // cfg.batch_size)
+        # The number of updates must be the SAME on every rank: each update is one gradient all-reduce, and N (the rank's own decision
+        # count) differs from rank to rank.  Agree on min N over the ranks; no rank updates if any rank has nothing to train on.
+        n_up = self.agreed_updates(N)
         stats = []
         self.net.train()
         for u in range(n_up):
-            sel = idx[perm[(u * cfg.batch_size) % max(N, 1):][:cfg.batch_size]]
-            if sel.shape[0] == 0:
-                break
+            sel = idx[perm[(u * cfg.batch_size) % N:][:cfg.batch_size]]
             t, b = sel[:, 0], sel[:, 1]
             stats.append(reinforce_update(self.net, self.optimizer, self.lr_decay, ep.task_obs[t, b], ep.agent_obs[t, b],
                                           ep.mask[t, b].view(torch.bool), ep.action[t, b].long(), adv_env[b]))
@@ -174,10 +189,12 @@ class ReinforceTrainer:
             out[k] = float(torch.stack([s[k] for s in stats]).mean()) if stats else float("nan")
         return out
 
+    def agreed_updates(self, n_local: int) -> int:
+        return agreed_update_count(n_local, self.cfg.batch_size, self.cfg.updates_per_iteration)
+
     # ---- baseline test (driver.py:208-279) ------------------------------------------------------------------------------------
     def _eval(self, net):
         r = self.eval_rollout.run(net, "greedy", amp=self.cfg.amp).reward
-        r = torch.nan_to_num(r, nan=-2.0 * self.cfg.max_time)
         if self.world > 1:
             allr = [torch.empty_like(r) for _ in range(self.world)]
             dist.all_gather(allr, r)

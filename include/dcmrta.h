@@ -120,7 +120,10 @@ int dcm_step(dcm_env* env, const int32_t* action_d, const int32_t* followers_d, 
 
 /* Same call with HOST buffers (pageable or pinned): actions are copied in, outputs copied out, the call returns when the
  * outputs are valid.  Any output pointer may be NULL (then it is not copied).  next_leader, reward and done are final when the
- * step kernel ends and are copied on a second stream while the episode and observation kernels still run. */
+ * step kernel ends and are copied on a second stream while the episode and observation kernels still run.  The call runs on a
+ * stream of the handle; it first waits (on the device, through an event) for the asynchronous work earlier calls on this handle
+ * queued on the caller's stream -- dcm_reset / dcm_generate / dcm_load_instances / dcm_step / granular calls -- so no host
+ * synchronisation is needed between those and dcm_step_host. */
 int dcm_step_host(dcm_env* env, const int32_t* action_h, int policy,
                   float* agent_obs_h, float* task_obs_h, uint8_t* mask_h,
                   int32_t* next_leader_h, float* reward_h, uint8_t* done_h);
@@ -170,6 +173,9 @@ int dcm_layout(const dcm_env* env, int32_t* out, int n);
 int dcm_env_flags(dcm_env* env, uint32_t* flags_d, void* stream);
 /* total leader decisions applied by this handle since creation (device counter read back; synchronises) */
 int dcm_total_steps(dcm_env* env, uint64_t* out_h);
+/* episodes accounted by this handle since creation, summed over its envs (worker.py:87 runs once per episode; device counters
+ * read back; synchronises).  bench.py reports the episode-end rate of the timed passes from it. */
+int dcm_total_episodes(dcm_env* env, uint64_t* out_h);
 /* algorithmic HBM bytes per env-step for this handle's shape (SURVEY.md 8(d) formula, w = 8) */
 size_t dcm_algorithmic_bytes_per_step(const dcm_env* env);
 /* number of kernels this handle has launched since creation */

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from dcmrta_b200.policy import AttentionNet
-from dcmrta_b200.trainer import allreduce_gradients, broadcast_parameters, paired_ttest_improved, reinforce_update
+from dcmrta_b200.trainer import agreed_update_count, allreduce_gradients, broadcast_parameters, paired_ttest_improved, reinforce_update
 
 
 def _batch(seed, n, A=6, T1=9):
@@ -69,6 +69,47 @@ def test_two_rank_update_equals_single_process_on_the_joint_batch():
         reinforce_update(net, opt, sch, *[torch.cat([x, y]) for x, y in zip(b0, b1)])
     ref = torch.cat([p.data.flatten() for p in net.parameters()]).numpy()
     np.testing.assert_allclose(g0, ref, rtol=2e-4, atol=2e-6)
+
+
+def _worker_unequal(rank, world, port, out):
+    """The shape of ReinforceTrainer.iteration()'s update loop with UNEQUAL decision counts per rank: the ranks
+    must issue the same number of gradient all-reduces, then a trailing collective (the all_gather of _eval) must still pair up."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net, opt, sch = _make(seed=3)
+    broadcast_parameters(net)
+    n_local = [100, 37][rank]                               # rank-local decision counts: 100 // 16 = 6 updates vs 37 // 16 = 2
+    n_up = agreed_update_count(n_local, 16)
+    data = _batch(7 + rank, n_local)
+    perm = torch.randperm(n_local, generator=torch.Generator().manual_seed(rank))
+    for u in range(n_up):
+        sel = perm[(u * 16) % n_local:][:16]
+        reinforce_update(net, opt, sch, *[x[sel] for x in data])
+    none = agreed_update_count([0, 50][rank], 16)           # one rank without decisions: nobody updates
+    flat = torch.cat([p.data.flatten() for p in net.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)                         # would hang or mis-pair if the update counts had differed
+    if rank == 0:
+        out.put((n_up, none, [g.numpy() for g in gathered]))
+    dist.destroy_process_group()
+
+
+def test_update_count_is_agreed_across_ranks_with_unequal_decision_counts():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_unequal, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n_up, none, (g0, g1) = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n_up == 2 and none == 0                          # min(100, 37) // 16
+    assert np.array_equal(g0, g1)
+    assert agreed_update_count(100, 16) == 6 and agreed_update_count(100, 16, 3) == 3 and agreed_update_count(0, 16, 3) == 0
 
 
 def test_update_moves_only_live_parameters_and_steps_the_schedule():
