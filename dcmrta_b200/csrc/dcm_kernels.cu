@@ -24,7 +24,8 @@
 
 using namespace dcm;
 
-#define STEP_THREADS 64
+#define STEP_THREADS 64         // == SCR_STRIDE (dcm_thread.cuh): the stride of the per-thread shared-memory scratch
+static_assert(STEP_THREADS == SCR_STRIDE, "scratch stride");
 #define OBS_THREADS 64          // 110 registers: capping them at 80 for 12 blocks / SM spills the load batches (92 vs 63 us, profiles/r02b)
 #define OBS_PITCH 65            // words per env in the staging tile: 60 floats + 12 mask bytes + pad (odd => conflict-free)
 #define OBS_AGENTS_PER_CHUNK 10 // 60 floats
@@ -89,21 +90,6 @@ __device__ __noinline__ void t_generate(const TC& c, u64 seed, u64 gid, unsigned
 // ---------------------------------------------------------------------------------------------------------------
 // k_step: one leader decision per env
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int choose_leader(const TC& c, const Rng& rng, unsigned episode, unsigned n_steps, u64 pending, u64& group,
-                                             unsigned& flags, const int* leader_in, int b) {
-    group = t_current_group(c, pending);                                      // task_env.py:291-298
-    const int inj = leader_in ? leader_in[b] : -1;
-    if (inj >= 0) {
-        if (inj < c.A && ((group >> inj) & 1ull)) return inj;
-        flags |= ENV_ERR_LEADER;
-        return __ffsll((long long)group) - 1;
-    }
-    const int n = __popcll(group);
-    if (n == 1) return __ffsll((long long)group) - 1;                         // same value as pick(word, 1) == 0
-    const uint4 blk = draw_block(rng, episode, n_steps, 0);
-    return kth_bit(group, pick(blk.y, n));                                    // worker.py:54
-}
-
 // every mask and bound of the env (full-warp 8-byte stores; cheaper than keeping a copy of the loaded state to diff against)
 template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, const St<TW>& st) {
 #pragma unroll
@@ -116,11 +102,30 @@ template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, cons
     EL(c, x_fin, 1, 0) = st.xfin; EL(c, x_amin, 1, 0) = st.xamin; EL(c, x_asg, 1, 0) = st.xasg; EL(c, x_ret, 1, 0) = st.xret; EL(c, x_last, 1, 0) = st.xlast;
 }
 
-// one leader decision of env b; returns the env's status bits after it
-template <int TW, int NW>
-__device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b) {
-    const TC c = make_tc(E, b);
+// One leader decision of env b; returns the env's status bits after it.  The duration of k_step is the length of one warp's chain
+// of DEPENDENT memory round trips (the grid is less than one wave), so the decision is organised as two rounds of loads:
+//   round 1  nothing depends on anything: masks, bounds, scalars; next_decision of every agent and the node ids, copied
+//            asynchronously (cp.async, no registers) into the thread's shared-memory scratch (TC::nds / nws);
+//   round 2  everything that depends on (action, leader) only: target coordinate, leader position, and the HEAD of the chosen
+//            task's record -- count, ids, status, requirement, duration, {amin, amax} or {time_start, time_finish}.
+// The members join, the joined task is evaluated (t_eval_task with the head in registers) and the movers' next_decision is set
+// (t_agent_update with `known`) from registers; the slot advance scans next_decision in shared memory.  What still goes to memory
+// are the rare paths: a re-visit, a removal, the waiting-coalition scan when the earliest waiting member may give up.
+template <int TW>
+__device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b, double* nds, unsigned* nws) {
+    TC c = make_tc(E, b); c.nds = nds; c.nws = nws;
+    const int A = c.A, T = c.T;
+    // ---- round 1
+    for (int i = 0; i < A; ++i) cp_async8(&nds[(unsigned)i * SCR_STRIDE], &EL(c, a_nd, A, i));
+    for (int k = 0; k < (A + 3) >> 2; ++k) cp_async4(&nws[(unsigned)k * SCR_STRIDE], (const unsigned*)&ANODE(c, 0) + k);
     unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
+    St<TW> st; ld_state(c, st);
+    double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
+    unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0), total = EL(c, total, 1, 0);
+    int leader = EL(c, leader, 1, 0);
+    const int ext_action = F.policy == 0 ? F.action[b] : 0;
+    const int inj = F.leader_in ? F.leader_in[b] : -1;                        // injected leader of the NEXT decision (trace replay)
+    cp_async_wait_all();
     if (flags & ENV_DONE) {                                                   // finished earlier and not restarted: untouched
         if (F.next_leader) F.next_leader[b] = -1;
         if (F.reward) F.reward[b] = 0.f;
@@ -128,11 +133,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         if (F.used_action) F.used_action[b] = -1;
         return flags;
     }
-    St<TW> st; ld_state(c, st);
-    Nodes<NW> nodes; ld_nodes<NW>(c, nodes);          // route[-1] of every agent: who stands where decides the groups without reading coordinates
-    double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
-    unsigned n_steps = EL(c, n_steps, 1, 0); const unsigned episode = EL(c, episode, 1, 0);
-    int leader = EL(c, leader, 1, 0);
+    const NodeFromScratch node_of{nws};              // route[-1] of every agent: who stands where decides the groups without reading coordinates
     const Rng rng{E.seed, E.first_gid + (u64)b};
     float reward_out = 0.f; int action_out = -1;
 
@@ -142,18 +143,31 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     int action;
     if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
     else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
-    else action = F.action[b];
-    if (action < 0 || action > c.T) { flags |= ENV_ERR_ACTION; ok = false; }
+    else action = ext_action;
+    if (action < 0 || action > T) { flags |= ENV_ERR_ACTION; ok = false; }
+    const bool to_task = ok && action != 0; const int j = to_task ? action - 1 : 0;
+    const bool feas_j = to_task && tbit<TW>(st.feas, j), ne_j = to_task && tbit<TW>(st.ne, j);
+    // ---- round 2
+    double tx = 0.0, ty = 0.0; double2 Lp = make_double2(0.0, 0.0), ti = make_double2(0.0, 0.0);
+    TaskR tr;
+    if (ok) {
+        Lp = AREC2(c, leader, 0);
+        if (to_task) {
+            tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j);
+            tr.dur = EL(c, s_dur, T, j); tr.req = (int)EL(c, s_req, T, j); tr.status = (int)EL(c, t_status, T, j);
+            tr.n = EL(c, t_nmem, T, j); tr.ids = *(const u64*)&SMEM(c, j, 0); ti = TINFO2(c, j);    // (stale when the task has no members: not used then)
+        } else { tx = EL(c, s_dep, 2, 0); ty = EL(c, s_dep, 2, 1); }
+    }
     int want = 0; u64 g = group & ~(1ull << leader);                          // task_env.py:328
     const int* fp = F.followers ? F.followers + (size_t)b * F.fstride : nullptr;
     if (ok) {
-        const int vacancy = action == 0 ? __popcll(group) : (int)EL(c, t_status, c.T, action - 1);   // :327
+        const int vacancy = action == 0 ? __popcll(group) : tr.status;        // :327
         if (vacancy > 1) { const int avail = __popcll(g); want = vacancy - 1 < avail ? vacancy - 1 : avail; }   // :330-331
         if (fp && action != 0) {                                              // validate injected followers before touching state
             u64 gg = g;
             for (int k = 0; k < want && ok; ++k) {
                 const int fo = k < F.fstride ? fp[k] : -1;
-                if (fo < 0 || fo >= c.A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
+                if (fo < 0 || fo >= A || !((gg >> fo) & 1ull)) ok = false; else gg &= ~(1ull << fo);
             }
             if (ok && want < F.fstride && fp[want] >= 0) ok = false;
             if (!ok) flags |= ENV_ERR_FOLLOW;
@@ -162,47 +176,39 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     if (ok) {
         action_out = action;
         // every member stands where the leader stands and goes to the same node: one distance and one arrival for all (:315-318)
-        const bool to_task = action != 0; const int j = action - 1;
         const unsigned target = to_task ? (unsigned)j : DCM_NODE_DEPOT;
-        double tx, ty; node_xy(c, target, tx, ty);
-        const double2 Lp = AREC2(c, leader, 0);
         // observation cache of the movers (AOBS2, dcm_thread.cuh): what their agent row shows of the task they now stand at
         double2 aobs = make_double2(0.0, 0.0);
-        if (to_task) { if (tbit<TW>(st.feas, j)) aobs = TINFO2(c, j); else aobs.y = 0.0 + EL(c, s_dur, c.T, j); }
-        // the task's membership is read ONCE and then kept in registers while the members join (the reference re-reads its
-        // lists per agent_step; every load here would be another dependent round trip)
-        const bool feas_j = to_task && tbit<TW>(st.feas, j), ne_j = to_task && tbit<TW>(st.ne, j);
-        int n = 0; u64 ids0 = 0, ids1 = 0; double amin = CUDART_INF;
-        if (ne_j) {
-            n = EL(c, t_nmem, c.T, j);
-            const u64* idw = (const u64*)&SMEM(c, j, 0);
-            ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1];
-            amin = TINFO(c, j, 0);
-        }
-        const int n0 = n; bool amin_new = false, revisit = false;
+        if (to_task) { if (feas_j) aobs = ti; else aobs.y = 0.0 + tr.dur; }
+        // the task's membership was read ONCE (round 2) and stays in registers while the members join (the reference re-reads its
+        // lists per agent_step); {amin, amax} = earliest / latest member arrival of a waiting coalition
+        int n = ne_j ? tr.n : 0; u64 ids = tr.ids;
+        const bool waiting = ne_j && !feas_j;
+        double amin = waiting ? ti.x : CUDART_INF, amax = waiting ? ti.y : -CUDART_INF;
+        const int n0 = n; bool mm_new = false, revisit = false;
         double d, tt; travel(c, Lp.x, Lp.y, tx, ty, d, tt);
         const double arrival = now + tt;                                      // :318
-        double reward = 0.0; int nm = 0;
+        double reward = 0.0; int nm = 0; u64 movers = 0;
         auto move = [&](int i) {                                              // agent_step (:300-324)
             const u64 bit = 1ull << i;
             AREC2(c, i, 0) = make_double2(tx, ty);                            // :320
             AREC(c, i, AR_LAST) = arrival;                                    // :318
             atomicAdd(&AREC(c, i, AR_DIST), d);                               // :317 travel_dist += d: a reduction, no load
-            ANODE(c, i) = (unsigned char)target; nset<NW>(nodes, i, target);  // :314
-            st.route |= bit; st.touched |= bit; pending &= ~bit;
+            ANODE(c, i) = (unsigned char)target; scratch_set_node(nws, i, target);   // :314
+            st.route |= bit; st.touched |= bit; pending &= ~bit; movers |= bit;
             if (!to_task) { st.depot |= bit; st.member &= ~bit; }
             else {
                 st.depot &= ~bit; AOBS2(c, i) = aobs;
                 int pos = -1;                                                 // :321-322
-                for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) if (sl < n && ((unsigned)(ids >> (8 * sl)) & 0xffu) == (unsigned)i) pos = sl;
                 if (pos >= 0) {                                               // re-visit by a current member (Q8): last arrival wins
                     SARR(c, j, pos) = arrival; st.member |= bit; revisit = true;
                 } else if (n < c.MC) {
                     SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
-                    if (n < 8) ids0 = (ids0 & ~(0xffull << (8 * n))) | ((u64)(unsigned)i << (8 * n));          // (slots past n hold stale ids)
-                    else ids1 = (ids1 & ~(0xffull << (8 * (n - 8)))) | ((u64)(unsigned)i << (8 * (n - 8)));
-                    if (n == 0 || arrival < amin) { amin = arrival; amin_new = true; }
-                    ++n; st.member |= bit;
+                    ids = (ids & ~(0xffull << (8 * n))) | ((u64)(unsigned)i << (8 * n));                      // (slots past n hold stale ids)
+                    if (n == 0) { amin = arrival; amax = arrival; } else { amin = arrival < amin ? arrival : amin; amax = arrival > amax ? arrival : amax; }
+                    mm_new = true; ++n; st.member |= bit;
                 } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }
             }
             reward += -tt; ++nm;
@@ -227,37 +233,36 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         st.xlast = arrival > st.xlast ? arrival : st.xlast;
         if (!to_task) st.xret = arrival < st.xret ? arrival : st.xret;
         else {
-            if (n != n0) { EL(c, t_nmem, c.T, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
-            if (!feas_j) {                                                    // earliest member arrival of a waiting coalition
-                if (revisit) {                                                // the slots again, in one batch (a loop of dependent loads otherwise)
+            if (n != n0) { EL(c, t_nmem, T, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
+            if (!feas_j) {
+                if (revisit) {                                                // rare: the slots, in one batch (a loop of dependent loads otherwise)
                     double v8[8];
 #pragma unroll
                     for (int sl = 0; sl < 8; ++sl) v8[sl] = sl < c.MC ? SARR(c, j, sl) : 0.0;
-                    amin = CUDART_INF;
+                    amin = CUDART_INF; amax = -CUDART_INF;
 #pragma unroll
-                    for (int sl = 0; sl < 8; ++sl) if (sl < n) amin = v8[sl] < amin ? v8[sl] : amin;
-                    for (int sl = 8; sl < n; ++sl) { const double a = SARR(c, j, sl); amin = a < amin ? a : amin; }
-                    amin_new = true;
+                    for (int sl = 0; sl < 8; ++sl) if (sl < n) { amin = v8[sl] < amin ? v8[sl] : amin; amax = v8[sl] > amax ? v8[sl] : amax; }
+                    mm_new = true;
                 }
-                if (amin_new) { TINFO(c, j, 0) = amin; st.xamin = amin < st.xamin ? amin : st.xamin; }
+                if (mm_new) { TINFO2(c, j) = make_double2(amin, amax); st.xamin = amin < st.xamin ? amin : st.xamin; }
             }
+            tr.j = j; tr.n = n; tr.ids = ids; tr.amin = amin; tr.amax = amax;  // the head the evaluation below starts from
+            tr.feas = feas_j; tr.ts = ti.x; tr.tf = ti.y;
         }
         reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
-        auto node_of = [&](int m) -> unsigned { return nget<NW>(nodes, m); };
-        t_task_update<TW>(c, st, now, nullptr, node_of);                      // worker.py:74
-        t_agent_update<TW>(c, st, now, st.touched, node_of);                  // worker.py:76
-        ++n_steps; EL(c, total, 1, 0) = EL(c, total, 1, 0) + 1;
+        t_task_update<TW>(c, st, now, nullptr, node_of, false, 0, &tr);       // worker.py:74
+        t_agent_update<TW>(c, st, now, st.touched, node_of, &tr, movers, arrival);   // worker.py:76
+        ++n_steps; EL(c, total, 1, 0) = total + 1;
         if (!pending) t_advance<TW>(c, st, now, pending, flags, node_of);     // worker.py:85, :45-51
         if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
         else {
-            group = f_current_group<NW>(c, nodes, pending);                   // task_env.py:291-298
-            const int inj = F.leader_in ? F.leader_in[b] : -1;
+            group = f_current_group(c, node_of, pending);                     // task_env.py:291-298
             if (inj >= 0) {
-                if (inj < c.A && ((group >> inj) & 1ull)) leader = inj;
+                if (inj < A && ((group >> inj) & 1ull)) leader = inj;
                 else { flags |= ENV_ERR_LEADER; leader = ctz64(group); }
             } else {
-                const int n = __popcll(group);
-                leader = n == 1 ? ctz64(group) : kth_bit(group, pick(draw_block(rng, episode, n_steps, 0).y, n));   // worker.py:54
+                const int ng = __popcll(group);
+                leader = ng == 1 ? ctz64(group) : kth_bit(group, pick(draw_block(rng, episode, n_steps, 0).y, ng));   // worker.py:54
             }
         }
     }
@@ -266,10 +271,9 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         // The episode kernel restarts this env; the first leader of the new episode (episode_env, worker.py:54) is a function of the
         // RNG contract alone, so the OUTPUT carries it already: next_leader, reward and done are then final when k_step ends and
         // dcm_step_host sends them to the host while the episode and observation kernels run.  (The stored leader stays -1.)
-        const int inj = F.leader_in ? F.leader_in[b] : -1;
-        if (inj >= 0) leader_out = inj < c.A ? inj : 0;
-        else if (c.A == 1) leader_out = 0;
-        else leader_out = kth_bit(c.A >= 64 ? ~0ull : ((1ull << c.A) - 1), pick(draw_block(rng, episode + 1, 0, 0).y, c.A));
+        if (inj >= 0) leader_out = inj < A ? inj : 0;
+        else if (A == 1) leader_out = 0;
+        else leader_out = kth_bit(A >= 64 ? ~0ull : ((1ull << A) - 1), pick(draw_block(rng, episode + 1, 0, 0).y, A));
     }
     if (F.next_leader) F.next_leader[b] = leader_out;
     if (F.reward) F.reward[b] = reward_out;
@@ -281,11 +285,14 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     return flags;
 }
 
-template <int TW, int NW>
+__host__ __device__ inline size_t step_smem_bytes(int A, int ANB) { return (size_t)STEP_THREADS * (8 * (size_t)A + (size_t)ANB); }
+
+template <int TW>
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
+    extern __shared__ __align__(16) unsigned char step_smem[];               // per-thread scratch: [A][64] next_decision, [ANB/4][64] node-id words
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     unsigned flags = 0;
-    if (b < E.S.B) flags = step_env<TW, NW>(E, F, b);
+    if (b < E.S.B) flags = step_env<TW>(E, F, b, (double*)step_smem + threadIdx.x, (unsigned*)(step_smem + (size_t)STEP_THREADS * 8 * E.S.A) + threadIdx.x);
     if (F.elist) {                                                            // envs whose episode just ended: one warp-aggregated append per warp that has any
         const bool need = (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
         const unsigned m = __ballot_sync(0xffffffffu, need), lane = threadIdx.x & 31u;
@@ -314,100 +321,14 @@ struct EpiArgs { int mode; const unsigned char* which; const int* leader_in; int
 __device__ __forceinline__ double wmax(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; } return v; }
 __device__ __forceinline__ double wmin(double v) { for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; } return v; }
 
-// per-warp scratch of k_episode, carved from dynamic shared memory and sized for the handle's (A, T, MC)
-struct EpiScratch {
-    double* sa;            // [32][MC]  arrivals of the slots of the 32 tasks of a batch
-    double* smx;           // [32]      latest arrival per task
-    double *s_task, *s_ts; // [T]
-    double *s_agent, *s_dist;   // [A]
-    unsigned char* sm;     // [32][MC]  member ids
-    unsigned char* sn;     // [32]      member count | feasible << 7
-    int MC;
-};
-// handles with at most 8 member slots (w_episode_metrics8) keep the member data in registers and only stage the four vectors that are summed
-__host__ __device__ inline size_t epi_scratch_bytes(int A, int T, int MC) {
-    if (MC <= 8) return (size_t)8 * (2 * T + 2 * A);
-    return (size_t)8 * (32 * MC + 32 + 2 * T + 2 * A) + (((size_t)32 * MC + 32 + 7) / 8) * 8;
-}
-__device__ __forceinline__ EpiScratch epi_scratch(unsigned char* base, int A, int T, int MC) {
+// per-warp scratch of k_episode, carved from dynamic shared memory: the four vectors that are summed (the member data of a task
+// stays in the registers of the lane that owns it, w_episode_metrics8)
+struct EpiScratch { double *s_task, *s_ts; /* [T] */ double *s_agent, *s_dist; /* [A] */ };
+__host__ __device__ inline size_t epi_scratch_bytes(int A, int T, int) { return (size_t)8 * (2 * T + 2 * A); }
+__device__ __forceinline__ EpiScratch epi_scratch(unsigned char* base, int A, int T, int) {
     EpiScratch S; double* d = (double*)base;
-    S.s_task = d; d += T; S.s_ts = d; d += T; S.s_agent = d; d += A; S.s_dist = d; d += A;
-    S.sa = d; S.smx = d; S.sm = (unsigned char*)d; S.sn = S.sm; S.MC = MC;
-    if (MC > 8) { d += 32 * MC; S.smx = d; d += 32; S.sm = (unsigned char*)d; S.sn = S.sm + 32 * MC; }
+    S.s_task = d; d += T; S.s_ts = d; d += T; S.s_agent = d; d += A; S.s_dist = d;
     return S;
-}
-
-// out[8]: reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions.  Returns the final clock.
-// Warp-cooperative: tasks are staged 32 at a time (lane <-> task, all slot loads in flight at once), then the agent sums are
-// accumulated in the reference order (tasks ascending, members in list order, :358-362) from shared memory.
-template <int TW>
-__device__ __forceinline__ double w_episode_metrics(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, const EpiScratch& S) {
-    const int T = c.T, A = c.A;
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int j0 = 0; j0 < T; j0 += 32) {
-        const int j = j0 + (int)lane;
-        int n = 0; bool feas = false; double mx = 0.0;
-        if (j < T) { feas = tbit<TW>(st.feas, j); if (tbit<TW>(st.ne, j)) n = EL(c, t_nmem, T, j); }
-        u64 ids0 = 0, ids1 = 0;
-        if (n) { const u64* idw = (const u64*)&SMEM(c, j, 0); ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1]; }
-        for (int s0 = 0; s0 < n; s0 += 4) {                                   // four arrivals in flight
-            const double a0 = SARR(c, j, s0), a1 = SARR(c, j, s0 + 1 < n ? s0 + 1 : s0), a2 = SARR(c, j, s0 + 2 < n ? s0 + 2 : s0), a3 = SARR(c, j, s0 + 3 < n ? s0 + 3 : s0);
-            S.sa[lane * S.MC + s0] = a0; mx = (s0 == 0 || a0 > mx) ? a0 : mx;
-            if (s0 + 1 < n) { S.sa[lane * S.MC + s0 + 1] = a1; mx = a1 > mx ? a1 : mx; }
-            if (s0 + 2 < n) { S.sa[lane * S.MC + s0 + 2] = a2; mx = a2 > mx ? a2 : mx; }
-            if (s0 + 3 < n) { S.sa[lane * S.MC + s0 + 3] = a3; mx = a3 > mx ? a3 : mx; }
-        }
-        for (int sl = 0; sl < n; ++sl) S.sm[lane * S.MC + sl] = (unsigned char)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu);
-        S.sn[lane] = (unsigned char)(n | (feas ? 0x80 : 0)); S.smx[lane] = mx;
-        if (j < T) {                                                          // task['sum_waiting_time'] :349-357
-            const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
-            double v = w_ab;
-            if (n) { double acc = 0.0; for (int s = 0; s < n; ++s) { const double a = S.sa[lane * S.MC + s]; acc += feas ? (mx - a) : (now - a); } v = acc + w_ab; }
-            S.s_task[j] = v;
-            S.s_ts[j] = feas ? TINFO(c, j, 0) : 0.0;
-        }
-        __syncwarp();
-        const int nt = T - j0 < 32 ? T - j0 : 32;
-        for (int t = 0; t < nt; ++t) {
-            const int cnt = S.sn[t] & 0x7f; const bool ft = S.sn[t] & 0x80; const double mxt = S.smx[t];
-            for (int s = 0; s < cnt; ++s) {
-                const unsigned m = S.sm[t * S.MC + s]; const double a = S.sa[t * S.MC + s];
-                double add;
-                if (ft) add = mxt - a; else { const double wv = now - a; add = wv > 0.0 ? wv : 0.0; }     // :360 / :362
-                if (lane == (m & 31u)) { if (m < 32u) acc0 += add; else acc1 += add; }
-            }
-        }
-        __syncwarp();
-    }
-    for (int r = 0; r < 2; ++r) {                                             // + W per abandoned_agent entry (:363-364; added last, ~1e-16 rel.)
-        const int i = lane + 32 * r;
-        if (i < A) {
-            double acc = r ? acc1 : acc0;
-            for (int k = 0; k < (int)EL(c, a_nab, A, i); ++k) acc += c.W;
-            S.s_agent[i] = acc; S.s_dist[i] = AREC(c, i, AR_DIST);
-        }
-    }
-    // :422 check_finished side effect on the clock
-    double mn = CUDART_INF, la = 0.0;
-    for (int i = lane; i < A; i += 32) { const double nd = EL(c, a_nd, A, i); if (nd < mn) mn = nd; const double l2 = AREC(c, i, AR_LAST); la = l2 > la ? l2 : la; }
-    mn = wmin(mn); la = wmax(la);
-    if (mn == CUDART_INF) now = la;
-    int nfin = 0;
-#pragma unroll
-    for (int w = 0; w < TW; ++w) nfin += __popcll(st.fin[w]);
-    __syncwarp();
-    if (lane == 0) {
-        out[0] = -now;                                                        // :424
-        out[1] = (double)nfin / (double)T;                                    // worker.py:103
-        out[2] = now;                                                         // :104
-        out[3] = np_sum([&](int j) { return S.s_ts[j]; }, T) / (double)T;     // :105 nanmean(time_start)
-        out[4] = np_sum([&](int i) { return S.s_agent[i]; }, A) / (double)A;  // :106
-        out[5] = np_sum([&](int i) { return S.s_dist[i]; }, A);               // :107
-        out[6] = np_sum([&](int j) { return S.s_task[j]; }, T) / (double)T;   // :108
-        out[7] = (double)n_steps;
-    }
-    __syncwarp();
-    return now;
 }
 
 // numpy pairwise add.reduce of n <= 128 values in shared memory by 8 lanes (lane8 = 0..7 of the group); same order of
@@ -429,8 +350,9 @@ __device__ __forceinline__ double g_np_sum(const double* v, int n, unsigned lane
     return g_np_sum_le128(v, 0, n2, lane8, gmask) + g_np_sum_le128(v, n2, n - n2, lane8, gmask);
 }
 
-// w_episode_metrics with every load of a 32-task batch issued in one round (and the next batch's before this one is
-// consumed), for handles with at most 8 member slots; the four final sums run on four groups of 8 lanes.  Same arithmetic.
+// out[8]: reward, success_rate, makespan, time_cost, waiting_time, travel_dist, efficiency, decisions.  Returns the final clock.
+// Warp-cooperative, lane <-> task: every load of a 32-task batch is issued in one round (and the next batch's before this one is
+// consumed); the four final sums run on four groups of 8 lanes in numpy's pairwise order.
 template <int TW>
 __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& st, unsigned lane, double now, unsigned n_steps, double* out, const EpiScratch& S) {
     const int T = c.T, A = c.A, MC = c.MC;
@@ -544,8 +466,7 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
     const bool regen = P.mode == 0 && (E.cflags & DCM_FLAG_REGENERATE);
     if (P.mode == 0) {
         const double now0 = EL(c, now, 1, 0); const unsigned ns = EL(c, n_steps, 1, 0);
-        const double now = E.S.MC <= 8 ? w_episode_metrics8(c, st, lane, now0, ns, P.metrics + (size_t)be * 8, scratch)
-                                       : w_episode_metrics(c, st, lane, now0, ns, P.metrics + (size_t)be * 8, scratch);
+        const double now = w_episode_metrics8(c, st, lane, now0, ns, P.metrics + (size_t)be * 8, scratch);
         ++episode; flags |= ENV_ACCOUNTED;
         if (!(E.cflags & DCM_FLAG_AUTO_RESET)) {
             if (lane == 0) { EL(c, now, 1, 0) = now; EL(c, flags, 1, 0) = flags; EL(c, episode, 1, 0) = episode; }
@@ -614,12 +535,6 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
         if (P.next_leader) P.next_leader[be] = leader;
     }
     __syncwarp();
-}
-
-// out-of-line copy for k_pass: the rare episode path must not raise the register pressure of the step / observe loop
-template <int TW>
-__device__ __noinline__ void episode_env_cold(const EnvArgs& E, const EpiArgs& P, int be, unsigned lane, unsigned char* smem, const ObsArgs* O) {
-    episode_env<TW>(E, P, be, lane, epi_scratch(smem, E.S.A, E.S.T, E.S.MC), O);
 }
 
 // EPI_WARPS single-warp blocks per tile: block (tile, r) takes the tile's r-th, (r + EPI_WARPS)-th, ... env that needs work.
@@ -1012,94 +927,6 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_pass: the whole pass (one leader decision of every env + the observation of the next leader) in ONE launch.
-// Persistent warps take work units from a ticket counter:
-//   units [0, NT)            step   : one tile of 32 envs, thread per env (step_env); the tile id and the mask of the envs
-//                                     whose episode just ended are published in the TILE QUEUE.
-//   units [NT, NT + NT*CH)   observe: unit u serves chunk k = (u - NT) % CH of the (u - NT) / CH-th tile IN COMPLETION ORDER,
-//                                     as soon as that entry is published, for the envs that are not in the entry's mask (obs_unit).
-//   episode accounting + restart of an env whose episode ended, and its observation, by a whole warp (episode_env): the
-//   first such env of a tile by the step warp itself right after it published the tile, the (k+1)-th by the tile's k-th
-//   observe unit -- the long, rare episode path runs beside everything else instead of after it.
-// The bandwidth-bound observation work of the tiles that are done overlaps the latency-bound tail of the step work (the
-// step is less than one wave: 14 warps per SM at 65,536 envs), and nothing waits on a kernel boundary.
-// Forward progress: every step ticket is taken before any observe ticket (one monotonic counter) and a warp that holds a
-// step unit never waits, so every entry an observe unit spins on is being produced by a running warp.
-// Entries carry the launch epoch (the queue is never cleared); the last warp to leave resets the counters.
-// ---------------------------------------------------------------------------------------------------------------
-struct PassCtl { unsigned ticket, tail, warps_done, pad; };
-#define PASS_WARPS 2
-
-__host__ __device__ inline size_t pass_warp_smem(int A, int T, int MC) {
-    const size_t o = (size_t)32 * OBS_PITCH * sizeof(float), e = epi_scratch_bytes(A, T, MC);
-    return ((o > e ? o : e) + 15) / 16 * 16;
-}
-__device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *(const volatile unsigned*)p; }
-__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
-
-template <int TW>
-__global__ void __launch_bounds__(32 * PASS_WARPS, 7) k_pass(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F, const __grid_constant__ EpiArgs P,
-                                                             const __grid_constant__ ObsArgs O, PassCtl* ctl, unsigned long long* queue, unsigned* qmask,
-                                                             unsigned epoch, int CH, unsigned long long* trace) {
-    extern __shared__ __align__(16) unsigned char pass_smem[];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int B = E.S.B, A = E.S.A, T = E.S.T;
-    const unsigned NT = (unsigned)E.S.NT, total = NT + NT * (unsigned)CH;
-    unsigned char* mysmem = pass_smem + warp * pass_warp_smem(A, T, E.S.MC);
-    for (;;) {
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(&ctl->ticket, 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= total) break;
-        unsigned long long t_take = 0;
-        if (trace && lane == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_take)); trace[4 * (size_t)u] = t_take; }
-        if (u < NT) {                                                         // ---- step unit
-            const int b = (int)(u * 32 + lane);
-            unsigned flags = 0;
-            if (b < B) flags = step_env<TW, 8>(E, F, b);
-            const bool need = b < B && (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
-            unsigned todo = __ballot_sync(0xffffffffu, need);
-            if (CH == 0) {                                                    // nobody observes: the step warp does the episode work itself
-                for (; todo; todo &= todo - 1) episode_env_cold<TW>(E, P, (int)(u * 32 + (__ffs(todo) - 1)), lane, mysmem, nullptr);
-                continue;
-            }
-            __threadfence();                                                  // the tile's state is visible device-wide ...
-            __syncwarp();
-            if (lane == 0) {                                                  // ... before the entry that points at it is
-                const unsigned slot = atomicAdd(&ctl->tail, 1u);
-                *(volatile unsigned*)&qmask[slot] = todo;
-                __threadfence();
-                *(volatile unsigned long long*)&queue[slot] = ((unsigned long long)epoch << 32) | u;
-                if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4 * (size_t)u + 1] = t_take; trace[4 * (size_t)u + 2] = t; trace[4 * (size_t)u + 3] = ((unsigned long long)__popc(todo) << 32) | slot; }
-            }
-            if (todo) episode_env_cold<TW>(E, P, (int)(u * 32 + (__ffs(todo) - 1)), lane, mysmem, &O);   // nobody is earlier than this warp
-        } else {                                                              // ---- observe unit
-            const unsigned q = (u - NT) / (unsigned)CH; const int chunk = (int)((u - NT) % (unsigned)CH);
-            unsigned tile_id = 0, ended = 0;
-            if (lane == 0) {
-                unsigned long long e;
-                while ((unsigned)((e = ld_vol(&queue[q])) >> 32) != epoch) __nanosleep(100);
-                __threadfence();
-                tile_id = (unsigned)e; ended = ld_vol(&qmask[q]);
-                if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4 * (size_t)u + 1] = t; }
-            }
-            tile_id = __shfl_sync(0xffffffffu, tile_id, 0); ended = __shfl_sync(0xffffffffu, ended, 0);
-            unsigned mine = ended & (ended - 1);                              // the first ended env is restarted by the step warp itself;
-            for (int k = 0; k < chunk && mine; ++k) mine &= mine - 1;         // this unit takes the (chunk+1)-th, the last chunk all that is left
-            if (chunk != CH - 1) mine &= 0u - mine;
-            for (; mine; mine &= mine - 1) episode_env_cold<TW>(E, P, (int)(tile_id * 32 + (__ffs(mine) - 1)), lane, mysmem, &O);
-            obs_unit<TW>(E, O, tile_id, chunk, lane, (float*)mysmem, ended);
-            __syncwarp();                                                     // the staging tile is reused by the next unit
-            if (trace && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4 * (size_t)u + 2] = t; trace[4 * (size_t)u + 3] = ((unsigned long long)__popc(ended) << 32) | tile_id; }
-        }
-    }
-    if (lane == 0) {
-        __threadfence();
-        if (atomicAdd(&ctl->warps_done, 1u) == gridDim.x * PASS_WARPS - 1) { ctl->ticket = 0; ctl->tail = 0; ctl->warps_done = 0; __threadfence(); }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // k_granular: one TaskEnv method per launch
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW>
@@ -1297,16 +1124,16 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
     const int T = c.T, A = c.A, Tp = L.Tp;
     for (int j = 0; j < T; ++j) {
         const int n = (r + L.o_nmem)[j]; const int stt = ((const signed char*)(r + L.o_status))[j]; const unsigned tf = (r + L.o_tflags)[j];
-        double amin = CUDART_INF;
+        double amin = CUDART_INF, amax = -CUDART_INF;
         for (int s = 0; s < n && s < c.MC; ++s) {
             const double a = ((const double*)(r + L.o_arr))[s * Tp + j];
-            SARR(c, j, s) = a; SMEM(c, j, s) = (r + L.o_mem)[s * Tp + j]; amin = a < amin ? a : amin;
+            SARR(c, j, s) = a; SMEM(c, j, s) = (r + L.o_mem)[s * Tp + j]; amin = a < amin ? a : amin; amax = a > amax ? a : amax;
         }
         const double ts = ((const double*)(r + L.o_tstart))[j];
         if (tf & DCM_TF_FEAS) {
             const double tfin = ts + EL(c, s_dur, T, j); TINFO(c, j, 0) = ts; TINFO(c, j, 1) = tfin;
             if (!(tf & DCM_TF_FIN) && tfin < st.xfin) st.xfin = tfin;
-        } else { TINFO(c, j, 0) = amin; if (n > 0 && amin < st.xamin) st.xamin = amin; }
+        } else { TINFO2(c, j) = make_double2(amin, amax); if (n > 0 && amin < st.xamin) st.xamin = amin; }
         EL(c, t_nab, T, j) = ((const unsigned short*)(r + L.o_tnab))[j];
         EL(c, t_nmem, T, j) = (unsigned char)n; EL(c, t_status, T, j) = (signed char)stt;
         tset<TW>(st.feas, j, tf & DCM_TF_FEAS); tset<TW>(st.fin, j, tf & DCM_TF_FIN); tset<TW>(st.dirty, j, tf & DCM_TF_STALE);
@@ -1370,10 +1197,8 @@ static int fail_cuda(cudaError_t e, const char* where) {
 
 struct dcm_env {
     int device; EnvArgs E; DcmLayout L; bool have_instances;
-    bool fused_pass;                 // DCM_PASS_FUSED=1 at dcm_create: the whole pass in the single persistent kernel k_pass (measured slower)
     bool serial_pass;                // DCM_PASS_SERIAL=1 at dcm_create: k_step, k_episode, k_obs one after the other on the caller's stream (cross-check)
-    PassCtl* d_ctl; unsigned long long* d_queue; unsigned* d_qmask; unsigned epoch; int pass_grid;
-    unsigned long long* d_trace; size_t trace_units;   // DCM_PASS_TRACE=1: per-unit globaltimer stamps of the last k_pass (tools/pass_trace.py)
+    unsigned long long* d_trace; size_t trace_units;   // DCM_PASS_TRACE=1: globaltimer stamps of k_obs_tile blocks / k_episode_list warps (tools/obs_trace.py)
     unsigned char* arena; size_t arena_bytes;
     double* metrics;                 // [B,8]
     unsigned long long* d_counter;   // scratch for reductions
@@ -1413,7 +1238,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!out) return fail(DCM_ERR_ARG, "dcm_create: out is NULL");
     *out = nullptr;
     if (B < 1 || A < 1 || A > DCM_MAX_AGENTS || T < 1 || T > DCM_MAX_TASKS || M < 1 || M > DCM_MAX_M)
-        return fail(DCM_ERR_SHAPE, "dcm_create: need B>=1, 1<=A<=64, 1<=T<=254, 1<=M<=16");
+        return fail(DCM_ERR_SHAPE, "dcm_create: need B>=1, 1<=A<=64, 1<=T<=254, 1<=M<=8");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(DCM_ERR_DEVICE, "dcm_create: no CUDA device (there is no CPU fallback)"); }
     if (device < 0 || device >= n) return fail(DCM_ERR_DEVICE, "dcm_create: bad device index");
@@ -1423,7 +1248,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (!v) return fail(DCM_ERR_NOMEM, "dcm_create: host allocation failed");
     memset(v, 0, sizeof *v);
     v->device = device;
-    { const char* gs = getenv("DCM_PASS_FUSED"); v->fused_pass = gs && gs[0] == '1'; gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; }
+    { const char* gs = getenv("DCM_PASS_SERIAL"); v->serial_pass = gs && gs[0] == '1'; }
     v->L = dcm_make_layout(A, T, M);
     DcmSoa& S = v->E.S;
     S.B = B; S.NT = (B + 31) / 32; S.A = A; S.T = T; S.M = M; S.MC = M; S.TW = T <= 64 ? 1 : (T <= 128 ? 2 : 4);
@@ -1433,7 +1258,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     const int NT = S.NT, TW = S.TW;
     size_t off = 0;
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(K, elem) + 255) / 256 * 256; return o; };
-    const int MCB = M <= 8 ? 8 : 16; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
+    const int MCB = 8; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
     const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32), o_a_obs = carve(A, 16),
                  o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_asg = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
                  o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dur32 = carve(T, 4), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
@@ -1470,11 +1295,6 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_order, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_ctl, sizeof(PassCtl));
-    if (e == cudaSuccess) e = cudaMemset(v->d_ctl, 0, sizeof(PassCtl));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_queue, (size_t)NT * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(v->d_queue, 0, (size_t)NT * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&v->d_qmask, (size_t)NT * sizeof(unsigned));
     { const char* tr = getenv("DCM_PASS_TRACE"); if (e == cudaSuccess && tr && tr[0] == '1') { v->trace_units = (size_t)NT * 64; e = cudaMalloc((void**)&v->d_trace, v->trace_units * 4 * sizeof(unsigned long long)); if (e == cudaSuccess) e = cudaMemset(v->d_trace, 0, v->trace_units * 4 * sizeof(unsigned long long)); } }
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
@@ -1500,7 +1320,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
 int dcm_destroy(dcm_env* v) {
     if (!v) return DCM_OK;
     DeviceGuard g(v->device);
-    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_ctl); cudaFree(v->d_queue); cudaFree(v->d_qmask); cudaFree(v->d_trace); cudaFree(v->d_cursor); cudaFree(v->d_record); cudaFree(v->d_elist); cudaFree(v->d_ecount);
+    cudaFree(v->arena); cudaFree(v->metrics); cudaFree(v->d_counter); cudaFree(v->d_trace); cudaFree(v->d_cursor); cudaFree(v->d_record); cudaFree(v->d_elist); cudaFree(v->d_ecount);
     cudaFree(v->d_action); cudaFree(v->d_agent); cudaFree(v->d_task); cudaFree(v->d_mask); cudaFree(v->d_leader); cudaFree(v->d_reward); cudaFree(v->d_done);
     if (v->hstream) cudaStreamDestroy(v->hstream);
     if (v->hcopy) cudaStreamDestroy(v->hcopy);
@@ -1664,7 +1484,6 @@ int dcm_reset(dcm_env* v, const uint8_t* which, const int32_t* leader_in, float*
     DeviceGuard g(v->device);
     cudaStream_t s = (cudaStream_t)stream;
     note_stream(v, s);
-    CK(cudaMemsetAsync(v->d_ctl, 0, sizeof(PassCtl), s));                     // k_pass work-queue counters (they reset themselves; this heals an aborted launch)
     EpiArgs P{1, which, leader_in, next_leader, v->metrics, ObsArgs{nullptr, nullptr, nullptr, nullptr, 0}, 0};
     int rc = launch_episode(v, P, s);
     if (rc) return rc;
@@ -1689,36 +1508,14 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     ObsArgs O{nullptr, agent_obs, task_obs, mask, 0};
     EpiArgs P{0, nullptr, next_leader_in, next_leader, v->metrics, O, 0};
     const bool want_obs = agent_obs || task_obs || mask;
-    if (v->fused_pass) {                                                      // the whole pass in one launch (k_pass)
-        const int NA = (v->E.S.A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (v->E.S.T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
-        const int CH = want_obs ? NA + NR : 0;
-        const size_t smem = PASS_WARPS * pass_warp_smem(v->E.S.A, v->E.S.T, v->E.S.MC);
-        if (!v->pass_grid) {
-            int per_sm = 0, sms = 0;
-            const void* fn = v->E.S.TW == 1 ? (const void*)k_pass<1> : v->E.S.TW == 2 ? (const void*)k_pass<2> : (const void*)k_pass<4>;
-            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * PASS_WARPS, smem));
-            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
-            v->pass_grid = per_sm * sms > 0 ? per_sm * sms : sms;
-        }
-        const unsigned units = (unsigned)v->E.S.NT * (unsigned)(1 + CH);
-        int grid = v->pass_grid; if ((unsigned)grid * PASS_WARPS > units) grid = (int)((units + PASS_WARPS - 1) / PASS_WARPS);
-        const unsigned epoch = ++v->epoch;
-        if (v->E.S.TW == 1) k_pass<1><<<grid, 32 * PASS_WARPS, smem, s>>>(v->E, F, P, O, v->d_ctl, v->d_queue, v->d_qmask, epoch, CH, v->d_trace);
-        else if (v->E.S.TW == 2) k_pass<2><<<grid, 32 * PASS_WARPS, smem, s>>>(v->E, F, P, O, v->d_ctl, v->d_queue, v->d_qmask, epoch, CH, v->d_trace);
-        else k_pass<4><<<grid, 32 * PASS_WARPS, smem, s>>>(v->E, F, P, O, v->d_ctl, v->d_queue, v->d_qmask, epoch, CH, v->d_trace);
-        CK(cudaGetLastError());
-        v->launches++;
-        return DCM_OK;
-    }
     const bool use_list = !v->dense_episode;
     unsigned* ecount = nullptr;
     if (use_list) { const unsigned p = v->pass_no++ & 1u; ecount = v->d_ecount + p; F.elist = v->d_elist; F.ecount = ecount; F.ecount_next = v->d_ecount + (p ^ 1u); }
     {
-        const int grid = grid_env(v, STEP_THREADS); const int TW = v->E.S.TW; const bool small = v->E.S.ANB == 32;
-#define LAUNCH_STEP(tw) do { if (small) k_step<tw, 4><<<grid, STEP_THREADS, 0, s>>>(v->E, F); else k_step<tw, 8><<<grid, STEP_THREADS, 0, s>>>(v->E, F); } while (0)
-        if (TW == 1) LAUNCH_STEP(1); else if (TW == 2) LAUNCH_STEP(2); else LAUNCH_STEP(4);
-#undef LAUNCH_STEP
+        const int grid = grid_env(v, STEP_THREADS); const size_t smem = step_smem_bytes(v->E.S.A, v->E.S.ANB);
+        if (v->E.S.TW == 1) k_step<1><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
+        else if (v->E.S.TW == 2) k_step<2><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
+        else k_step<4><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
     }
     CK(cudaGetLastError());
     v->launches++;

@@ -15,7 +15,7 @@
 
 #define DCM_MAX_AGENTS 64
 #define DCM_MAX_TASKS 254
-#define DCM_MAX_M 16
+#define DCM_MAX_M 8          // member slots per task: the ids of a task fit one 64-bit word, its arrivals one batch of loads
 #define DCM_NODE_DEPOT 0xFFu
 
 #define DCM_TF_FEAS 1u       // task flags

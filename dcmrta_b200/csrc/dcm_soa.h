@@ -24,13 +24,13 @@ struct DcmSoa {
     int B;        // envs
     int NT;       // tiles = ceil(B / 32)
     int A, T, M, MC, TW;
-    int MCB;      // bytes reserved per (task, lane) for member ids: 8 (MC <= 8) or 16
+    int MCB;      // bytes reserved per (task, lane) for member ids: 8 (MC <= DCM_MAX_M = 8: one 64-bit word)
     int ANB;      // bytes reserved per env for the agents' node ids: 32 (A <= 32) or 64
     size_t tile_stride;   // bytes of one tile's block; every pointer below addresses tile 0, tile t is at + t * tile_stride
     // ---- per task, lane-contiguous ----
     double* t_slot_arr;        // [T][32][MC]   arrival of member slot s (last visit, task_env.py:202-205)
     unsigned char* t_slot_mem; // [T][32][MCB]  member ids, ordered
-    double* t_info;            // [T][32][2]    feasible: {time_start, time_finish}; otherwise {amin = earliest member arrival, -}
+    double* t_info;            // [T][32][2]    feasible: {time_start, time_finish}; otherwise {amin, amax} = earliest / latest arrival over the member slots
     // ---- per task, row-major ----
     unsigned char* t_nmem;     // [T]    valid when the non-empty bit is set
     signed char* t_status;     // [T]    stored status (may be stale, Q3)

@@ -28,7 +28,14 @@ struct TC {
     size_t tb;                 // byte offset of the tile's block in the arena
     int A, T, MC;
     double W, vel, max_time;
+    // Per-thread scratch in SHARED memory (fused step only, NULL elsewhere).  Element k of this thread lives at [k * SCR_STRIDE]: the
+    // bank of an access then depends on the thread alone, so 32 lanes that index 32 DIFFERENT elements never conflict -- a dynamically
+    // indexed per-thread array at shared-memory latency instead of a chain of DRAM round trips (next_decision scan) or of register
+    // selects (node ids).
+    double* nds = nullptr;     // next_decision of the env's agents, write-through copy of a_nd
+    unsigned* nws = nullptr;   // route[-1] of the env's agents, four ids per word, write-through copy of a_node
 };
+#define SCR_STRIDE 64          // threads per block of the fused step (STEP_THREADS)
 
 // The arena is TILE-MAJOR: all arrays of one tile of 32 envs are contiguous (c.tb = tile * tile_stride bytes), so the
 // working set of a warp-step lies in one or two 2 MB pages instead of one page per array (TLB reach is 256 MB, the state
@@ -39,7 +46,7 @@ struct TC {
 // lane-contiguous arrays
 #define LANE_ROW(c, K, k) ((void)(K), (size_t)(((unsigned)(k) << 5) + (c).l))
 #define SARR(c, j, sl) (TB(c, t_slot_arr)[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
-#define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * (unsigned)(c).s.MCB + (unsigned)(sl)])   // member id of slot s
+#define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * 8u + (unsigned)(sl)])                        // member id of slot s (8 id bytes per task and lane)
 #define TINFO(c, j, k) (TB(c, t_info)[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
 #define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // {x, y, last arrival, travel_dist}
 enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
@@ -169,30 +176,44 @@ __device__ __forceinline__ void node_xy(const TC& c, unsigned node, double& x, d
 }
 __device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double by) { return ax < bx || (ax == bx && ay < by); }
 
-// ---- packed node ids of all agents of one env, in registers ------------------------------------------------------
-template <int NW> struct Nodes { u64 w[NW]; };
-template <int NW> __device__ __forceinline__ void ld_nodes(const TC& c, Nodes<NW>& nd) {
-    const ulonglong2* p = (const ulonglong2*)&ANODE(c, 0);
-#pragma unroll
-    for (int k = 0; k < NW / 2; ++k) {                                        // the line of an env holds ANB = 32 or 64 bytes
-        if (16 * k < c.s.ANB) { const ulonglong2 v = p[k]; nd.w[2 * k] = v.x; nd.w[2 * k + 1] = v.y; }
-        else { nd.w[2 * k] = 0; nd.w[2 * k + 1] = 0; }
-    }
+// ---- node ids of all agents of one env in the thread's shared-memory scratch (TC::nws) ------------------------------
+struct NodeFromScratch {
+    const unsigned* w;
+    __device__ __forceinline__ unsigned operator()(int i) const { return (w[(unsigned)(i >> 2) * SCR_STRIDE] >> (8 * (i & 3))) & 0xffu; }
+};
+__device__ __forceinline__ void scratch_set_node(unsigned* w, int i, unsigned v) {
+    unsigned& x = w[(unsigned)(i >> 2) * SCR_STRIDE]; const int sh = 8 * (i & 3);
+    x = (x & ~(0xffu << sh)) | (v << sh);
 }
-// the words are pinned to registers with empty asm statements: without them the compiler turns the select chains into a
-// dynamically indexed local-memory array (66 LDL per warp-step, profiles/r01o)
-template <int NW> __device__ __forceinline__ unsigned nget(const Nodes<NW>& nd, int i) {
-    u64 w = nd.w[0];
-#pragma unroll
-    for (int k = 1; k < NW; ++k) { u64 wk = nd.w[k]; asm("" : "+l"(wk)); w = (i >> 3) == k ? wk : w; }
-    return (unsigned)(w >> (8 * (i & 7))) & 0xffu;
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
-template <int NW> __device__ __forceinline__ void nset(Nodes<NW>& nd, int i, unsigned v) {
-    const int sh = 8 * (i & 7); const u64 m = 0xffull << sh, val = (u64)v << sh;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) { u64 wk = nd.w[k]; asm("" : "+l"(wk)); nd.w[k] = (i >> 3) == k ? ((wk & ~m) | val) : wk; }
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// next_decision of agent i: HBM, plus the scratch copy the slot advance scans
+__device__ __forceinline__ void set_nd(const TC& c, int i, double nd) {
+    EL(c, a_nd, c.A, i) = nd;
+    if (c.nds) c.nds[(unsigned)i * SCR_STRIDE] = nd;
 }
 
+// The head of one task's coalition record in registers.  For a task that is NOT feasible TINFO holds {amin, amax} = the earliest and
+// the latest arrival over its member slots (exact, maintained by every join / removal); with them the two common outcomes of an
+// evaluation -- "enough members and they arrive within max_waiting_time of each other" (:254-258) and "still short and nobody gives
+// up" (:266-269) -- need NO member slot at all: mx - mn is amax - amin, and fl(now - a) >= W holds for some member iff it holds for
+// the earliest one (fl is monotone).  The fused step fills the record from the loads its join needs anyway, so the task that was
+// just joined is evaluated without another round trip to memory.
+struct TaskR {
+    int j = -1;                // task id, -1 = none
+    int n = 0;                 // member count
+    int status = 0, req = 0;   // stored status (may be stale, Q3), requirement
+    u64 ids = 0;               // member ids of slots 0..7
+    double amin = 0, amax = 0; // earliest / latest member arrival (meaningful when n > 0 and the task is not feasible)
+    double dur = 0;            // task['time']
+    bool feas = false;         // the task is feasible and {ts, tf} = {time_start, time_finish} are known here
+    double ts = 0, tf = 0;
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // task_update (task_env.py:245-281).  newly: optional per-env [T] u8 (plain row-major global) of ids that became feasible.
@@ -220,82 +241,70 @@ template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c,
     if (node_of((int)m) == (unsigned)j) st.member &= ~(1ull << m);           // it no longer belongs to the task it stands at
 }
 
-// The member slots of the task are read in ONE batch together with the count (the first eight arrivals and the id word do not
-// depend on it; slots past the count hold stale values that are never used), so the common outcomes -- the coalition becomes
-// feasible, or it is still short and nobody gives up -- cost one round trip instead of one per member (profiles/r03_k_step_by_line).
-// Handles with more than eight slots per task keep the slot-by-slot loops for the tasks that hold more than eight members.
-template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of) {
+// Evaluation of one non-feasible task that has members (task_env.py:250-271).  `pre`: the head of the task's record when the caller
+// holds it in registers (the fused step, for the task that was just joined), else it is loaded here in one batch.  Only the two
+// rare outcomes read the member slots (one more batch, then registers only): members leave because the coalition is complete but
+// spread over more than max_waiting_time (:260-265, iterates a copy: Q4), or because they have waited long enough (:266-271,
+// mutates the list it iterates: Q2).  On return *pre, if given, says whether the task is feasible now and carries {time_start,
+// time_finish}; its count / ids / arrivals are stale after a removal (nobody uses them afterwards).
+template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of, TaskR* pre = nullptr) {
     const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
-    const int n = EL(c, t_nmem, T, j);                                        // :250
-    double a8[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) a8[s] = s < c.MC ? SARR(c, j, s) : 0.0;
-    const u64 ids = *(const u64*)&SMEM(c, j, 0);
+    TaskR r;
+    if (pre && pre->j == j) r = *pre;
+    else {
+        pre = nullptr;
+        r.n = EL(c, t_nmem, T, j); r.status = (int)EL(c, t_status, T, j); r.req = (int)EL(c, s_req, T, j);      // :250
+        r.ids = *(const u64*)&SMEM(c, j, 0); r.dur = EL(c, s_dur, T, j);
+        const double2 mm = TINFO2(c, j); r.amin = mm.x; r.amax = mm.y;
+    }
+    const int n = r.n; const u64 ids = r.ids;
     auto idb = [&](int s) -> unsigned { return (unsigned)(ids >> (8 * s)) & 0xffu; };
-    const bool small = n <= 8;
-    const int stt = (int)EL(c, s_req, T, j) - n;                              // :252 (not refreshed after removals: Q3)
-    if (stt != (int)EL(c, t_status, T, j)) EL(c, t_status, T, j) = (signed char)stt;
+    const int stt = r.req - n;                                                // :252 (not refreshed after removals: Q3)
+    if (stt != r.status) EL(c, t_status, T, j) = (signed char)stt;
     u64 open = stt > 0 ? bit : 0, feas = 0, ne = bit, dirty = 0;
+    bool removal = false;
     if (stt <= 0) {                                                           // :254
-        double mx = a8[0], mn = mx;
-#pragma unroll
-        for (int s = 1; s < 8; ++s) if (s < n) { mx = a8[s] > mx ? a8[s] : mx; mn = a8[s] < mn ? a8[s] : mn; }
-        for (int s = 8; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; mn = a < mn ? a : mn; }
-        if (mx - mn <= c.W) {                                                 // :255
-            const double tf = mx + EL(c, s_dur, T, j);
-            TINFO(c, j, 0) = mx; TINFO(c, j, 1) = tf;                         // :256-257 time_start, time_finish
+        if (r.amax - r.amin <= c.W) {                                         // :255 max(arrival) - min(arrival)
+            const double mx = r.amax, tf = mx + r.dur;
+            TINFO2(c, j) = make_double2(mx, tf);                              // :256-257 time_start, time_finish
             st.xfin = tf < st.xfin ? tf : st.xfin;
             feas = bit; open = 0;                                             // :258
             if (newly) newly[j] = 1;
             for (int i = 0; i < c.A; ++i)                                     // everybody who stands here (member or not, :166-171) now sees a feasible task
                 if (node_of(i) == (unsigned)j) AOBS2(c, i) = make_double2(mx, tf);
-            for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
-                const unsigned m = s < 8 ? idb(s) : (unsigned)SMEM(c, j, s);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) if (s < n) {                          // members standing here get next_decision = time_finish
+                const unsigned m = idb(s);
                 if (node_of((int)m) == (unsigned)j) st.touched |= 1ull << m;
             }
-        } else {                                                              // :260-265 (iterates a copy: no skipping, Q4)
-            const double thr = mx - c.W;
-            int wv = 0, nab = 0; double amin = CUDART_INF;
-            auto one = [&](int s, double a, unsigned m) {
-                if (a <= thr) { ++nab; abandon(c, st, m, j, node_of); }
-                else { if (wv != s) { SARR(c, j, wv) = a; SMEM(c, j, wv) = (unsigned char)m; } ++wv; amin = a < amin ? a : amin; }
-            };
+            if (pre) { pre->feas = true; pre->ts = mx; pre->tf = tf; }
+        } else removal = true;
+    } else removal = now - r.amin >= c.W;                                     // :269 for the earliest member (Q1: false when fl(arr+W) rounded down)
+    if (removal) {
+        double a8[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) if (s < n) one(s, a8[s], idb(s));
-            for (int s = 8; s < n; ++s) one(s, SARR(c, j, s), SMEM(c, j, s));
+        for (int s = 0; s < 8; ++s) a8[s] = s < c.MC ? SARR(c, j, s) : 0.0;   // slots past the count hold stale values that are never used
+        const bool q4 = stt <= 0; const double thr = r.amax - c.W;
+        int wv = 0, nab = 0; double amin = CUDART_INF, amax = -CUDART_INF; bool skip = false;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < n) {
+            const double a = a8[s]; const unsigned m = idb(s);
+            // Q4 (:260-265) tests every member of a COPY of the list; Q2 (:266-271) removes from the list it iterates, so the member
+            // that moves into the vacated slot is skipped by the next index and stays without being tested
+            const bool out = q4 ? (a <= thr) : (!skip && now - a >= c.W);
+            skip = out;
+            if (out) { ++nab; abandon(c, st, m, j, node_of); }
+            else {
+                if (wv != s) { SARR(c, j, wv) = a; SMEM(c, j, wv) = (unsigned char)m; }
+                ++wv; amin = a < amin ? a : amin; amax = a > amax ? a : amax;
+            }
+        }
+        if (nab) {
             EL(c, t_nmem, T, j) = (unsigned char)wv; bump_u16(&EL(c, t_nab, T, j), (unsigned)nab);
-            TINFO(c, j, 0) = amin;
+            TINFO2(c, j) = make_double2(amin, amax);
             if (wv == 0) ne = 0;
-            dirty = bit;
         }
-    } else {                                                                  // :266-271 (mutates while iterating: Q2)
-        bool any = !small;                                                    // does anybody give up?  (:269 on the batch; Q1: false when fl(arr+W) rounded down)
-#pragma unroll
-        for (int s = 0; s < 8; ++s) any = any || (s < n && now - a8[s] >= c.W);
-        if (any) {
-            int i = 0, nn = n, nab = 0;
-            while (i < nn) {
-                const double a = SARR(c, j, i);
-                if (now - a >= c.W) {                                         // :269
-                    abandon(c, st, SMEM(c, j, i), j, node_of);
-                    for (int k = i; k < nn - 1; ++k) { SARR(c, j, k) = SARR(c, j, k + 1); SMEM(c, j, k) = SMEM(c, j, k + 1); }
-                    --nn; ++nab;                                              // the element that moved into slot i is skipped
-                }
-                ++i;
-            }
-            if (nab) {
-                EL(c, t_nmem, T, j) = (unsigned char)nn; bump_u16(&EL(c, t_nab, T, j), (unsigned)nab);
-                double v8[8], amin = CUDART_INF;                              // the survivors, again in one batch
-#pragma unroll
-                for (int s = 0; s < 8; ++s) v8[s] = s < c.MC ? SARR(c, j, s) : 0.0;
-#pragma unroll
-                for (int s = 0; s < 8; ++s) if (s < nn) amin = v8[s] < amin ? v8[s] : amin;
-                for (int s = 8; s < nn; ++s) { const double a = SARR(c, j, s); amin = a < amin ? a : amin; }
-                TINFO(c, j, 0) = amin;
-                if (nn == 0) ne = 0;
-                dirty = bit;
-            }
-        }
+        if (nab || q4) dirty = bit;                                           // the stored status is not refreshed after a removal (Q3): the next call does it
     }
 #pragma unroll
     for (int k = 0; k < TW; ++k) if (TW == 1 || k == w) {
@@ -314,7 +323,7 @@ template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC
 // task_update call examines them, :272 is the else-branch) and states that did not come from the fused protocol
 // (dcm_import_state, granular calls) until their first slot start; a slot without deciders runs the full scan.
 template <int TW, class NF> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly, const NF& node_of,
-                                                                        bool slot_start = false, u64 dec = 0) {
+                                                                        bool slot_start = false, u64 dec = 0, TaskR* pre = nullptr) {
     const int T = c.T;
     // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished.  Both scans are skipped
     //      while the clock has not reached the per-env lower bounds (fl(now - x) >= W and now >= x are monotone in x).
@@ -357,7 +366,7 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
     // ---- full evaluation (rare: the task that was just joined, a coalition whose earliest member gives up)
 #pragma unroll
     for (int w = 0; w < TW; ++w)
-        for (u64 mm = hot[w]; mm; mm &= mm - 1) t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of);
+        for (u64 mm = hot[w]; mm; mm &= mm - 1) t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of, pre);
     bool allf = true;
 #pragma unroll
     for (int w = 0; w < TW; ++w) allf = allf && st.feas[w] == all_tasks<TW>(T, w);
@@ -379,7 +388,11 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 //   watch: members of a feasible task that are not assigned yet only need `now >= time_start` re-checked (:232-233).
 // For every other agent the reference recomputes exactly what is already stored (see DESIGN.md "restricted update").
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which, const NF& node_of) {
+// `known` (fused step): a task whose {time_start, time_finish} the caller holds in registers when it is feasible -- the task that was
+// just joined -- with `movers` = the agents that moved in this decision, all arriving at `arrival`.  Agents that stand at that task,
+// and agents at the depot, are then updated without touching memory; the others take the general path (loads batched by four).
+template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which, const NF& node_of,
+                                                                         const TaskR* known = nullptr, u64 movers = 0, double arrival = 0.0) {
     const int A = c.A;
     if (now >= st.xasg) {                                                     // watch: load-only pass, only when somebody can become assigned
         u64 asg = 0; double nx = CUDART_INF;
@@ -387,28 +400,35 @@ template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const
                           [&](u64 bit, int, double ts) { if (now >= ts) asg |= bit; else nx = ts < nx ? ts : nx; });
         st.assigned |= asg; st.watch &= ~asg; st.xasg = nx;
     }
-    // full recomputation, four agents per trip: level 1 = their nodes, level 2 = task info + last arrival, then the stores
-    for (u64 m = which & st.route; m;) {                                      // :209
+    auto member_of_feasible = [&](u64 bit, int i, double ts, double tf) {     // :229-233
+        set_nd(c, i, tf);                                                     // :231 time_finish
+        if (now >= ts) st.assigned |= bit;                                    // :232-233 (otherwise unchanged: Q5)
+        else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = ts; st.xasg = ts < st.xasg ? ts : st.xasg; }
+    };
+    u64 rest = 0;                                                             // :209
+    for (u64 q = which & st.route; q; q &= q - 1) {                           // first the agents that need nothing from memory
+        const u64 bit = q & (0 - q); const int i = ctz64(q);
+        if (st.depot & bit) { st.watch &= ~bit; set_nd(c, i, CUDART_NAN); continue; }          // :212, :226
+        if (!known || known->j < 0 || node_of(i) != (unsigned)known->j) { rest |= bit; continue; }
+        const bool fj = tbit<TW>(st.feas, known->j);
+        const bool fm = fj && (st.member & bit);
+        if ((fj && !known->feas) || (!fm && !(movers & bit))) { rest |= bit; continue; }   // {time_start, time_finish} / its last arrival are in memory
+        st.watch &= ~bit;
+        if (fm) member_of_feasible(bit, i, known->ts, known->tf);
+        else { set_nd(c, i, arrival + c.W); st.assigned &= ~bit; }            // :235 / :238
+    }
+    // general path, four agents per trip: level 1 = their nodes, level 2 = task info + last arrival, then the stores
+    for (u64 m = rest; m;) {
         const u64 b0 = m & (0 - m); m ^= b0; const u64 b1 = m & (0 - m); m ^= b1;
         const u64 b2 = m & (0 - m); m ^= b2; const u64 b3 = m & (0 - m); m ^= b3;
         const int i0 = ctz64(b0), i1 = b1 ? ctz64(b1) : i0, i2 = b2 ? ctz64(b2) : i0, i3 = b3 ? ctz64(b3) : i0;
-        const unsigned n0 = node_of(i0), n1 = node_of(i1), n2 = node_of(i2), n3 = node_of(i3);
-        const unsigned k0 = n0 == DCM_NODE_DEPOT ? 0u : n0, k1 = n1 == DCM_NODE_DEPOT ? 0u : n1, k2 = n2 == DCM_NODE_DEPOT ? 0u : n2, k3 = n3 == DCM_NODE_DEPOT ? 0u : n3;
+        const unsigned k0 = node_of(i0), k1 = node_of(i1), k2 = node_of(i2), k3 = node_of(i3);    // not the depot: those are done
         const double2 t0 = TINFO2(c, k0), t1 = TINFO2(c, k1), t2 = TINFO2(c, k2), t3 = TINFO2(c, k3);
         const double l0 = AREC(c, i0, AR_LAST), l1 = AREC(c, i1, AR_LAST), l2 = AREC(c, i2, AR_LAST), l3 = AREC(c, i3, AR_LAST);
         auto one = [&](u64 bit, int i, unsigned k, double2 tinfo, double last) {
-            double nd;
             st.watch &= ~bit;
-            if (st.depot & bit) nd = CUDART_NAN;                              // :212, :226
-            else if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) {        // :229-230
-                nd = tinfo.y;                                                 // :231 time_finish
-                if (now >= tinfo.x) st.assigned |= bit;                       // :232-233 (otherwise unchanged: Q5)
-                else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = tinfo.x; st.xasg = tinfo.x < st.xasg ? tinfo.x : st.xasg; }
-            } else {
-                nd = last + c.W;                                              // :235 / :238
-                st.assigned &= ~bit;
-            }
-            EL(c, a_nd, A, i) = nd;
+            if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) member_of_feasible(bit, i, tinfo.x, tinfo.y);
+            else { set_nd(c, i, last + c.W); st.assigned &= ~bit; }           // :235 / :238
         };
         one(b0, i0, k0, t0, l0); if (b1) one(b1, i1, k1, t1, l1); if (b2) one(b2, i2, k2, t2, l2); if (b3) one(b3, i3, k3, t3, l3);
     }
@@ -425,6 +445,14 @@ template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St
 __device__ __forceinline__ u64 t_next_decision(const TC& c, double& t_out, const double* xlast = nullptr) {
     const int A = c.A;
     double mn = CUDART_INF; u64 mask = 0;
+    if (c.nds) {                                                              // fused step: the scratch copy in shared memory, no round trip
+#pragma unroll 4
+        for (int i = 0; i < A; ++i) {
+            const double v = c.nds[(unsigned)i * SCR_STRIDE];
+            if (v < mn) { mn = v; mask = 1ull << i; }                         // NaN compares false
+            else if (v == mn) mask |= 1ull << i;                              // :288
+        }
+    } else
     for (int i0 = 0; i0 < A; i0 += 10) {                                      // ten loads in flight per round trip
         double v[10];
 #pragma unroll
@@ -470,11 +498,11 @@ __device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending) {
 // get_unique_group (task_env.py:291-298) for the group that acts next.  Agents that stand at the same node have the same
 // location, so when every pending agent stands at one node (always, in every recorded trajectory: SURVEY App. A Q10) the
 // group is the pending set and no coordinate is read; otherwise the coordinates decide (t_current_group).
-template <int NW> __device__ __forceinline__ u64 f_current_group(const TC& c, const Nodes<NW>& nodes, u64 pending) {
+template <class NF> __device__ __forceinline__ u64 f_current_group(const TC& c, const NF& node_of, u64 pending) {
     if ((pending & (pending - 1)) == 0) return pending;
-    const unsigned first = nget<NW>(nodes, ctz64(pending));
+    const unsigned first = node_of(ctz64(pending));
     bool same = true;
-    for (u64 m = pending & (pending - 1); m; m &= m - 1) same = same && nget<NW>(nodes, ctz64(m)) == first;
+    for (u64 m = pending & (pending - 1); m; m &= m - 1) same = same && node_of(ctz64(m)) == first;
     return same ? pending : t_current_group(c, pending);
 }
 
@@ -498,12 +526,11 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     const double2 ld = AREC2(c, i, 1);                                        // {last arrival, travel_dist}
     double2 aobs = make_double2(0.0, 0.0);                                    // observation cache (AOBS2)
     if (to_task) { if (feas) aobs = TINFO2(c, j); else aobs.y = 0.0 + EL(c, s_dur, T, j); }
-    int n = 0; u64 ids0 = 0, ids1 = 0; double amin = CUDART_INF;
+    int n = 0; u64 ids = 0; double amin = CUDART_INF, amax = -CUDART_INF;
     if (nonempty) {
         n = EL(c, t_nmem, T, j);
-        const u64* idw = (const u64*)&SMEM(c, j, 0);
-        ids0 = idw[0]; if (c.s.MCB > 8) ids1 = idw[1];
-        amin = TINFO(c, j, 0);
+        ids = *(const u64*)&SMEM(c, j, 0);
+        if (!feas) { const double2 mm = TINFO2(c, j); amin = mm.x; amax = mm.y; }   // {earliest, latest} member arrival of a waiting coalition
     }
     const double arrival = now + tt;                                          // :318
     AREC2(c, i, 1) = make_double2(arrival, ld.y + d);                         // :317-318
@@ -514,14 +541,21 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     if (!to_task) { st.depot |= bit; st.member &= ~bit; st.xret = arrival < st.xret ? arrival : st.xret; return; }
     st.depot &= ~bit; AOBS2(c, i) = aobs;
     int pos = -1;                                                             // :321-322
-    for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)(((sl < 8 ? ids0 : ids1) >> (8 * (sl & 7))) & 0xffu); if (id == (unsigned)i) pos = sl; }
+    for (int sl = 0; sl < n; ++sl) { const unsigned id = (unsigned)((ids >> (8 * sl)) & 0xffu); if (id == (unsigned)i) pos = sl; }
     if (pos >= 0) {                                                           // re-visit by a current member (Q8): last arrival wins
         SARR(c, j, pos) = arrival; st.member |= bit;
-        if (!feas) { double am = CUDART_INF; for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); am = a < am ? a : am; } TINFO(c, j, 0) = am; st.xamin = am < st.xamin ? am : st.xamin; }
+        if (!feas) {
+            double am = CUDART_INF, ax = -CUDART_INF;
+            for (int sl = 0; sl < n; ++sl) { const double a = SARR(c, j, sl); am = a < am ? a : am; ax = a > ax ? a : ax; }
+            TINFO2(c, j) = make_double2(am, ax); st.xamin = am < st.xamin ? am : st.xamin;
+        }
     } else if (n < c.MC) {
         SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
         EL(c, t_nmem, T, j) = (unsigned char)(n + 1);
-        if (!feas) { if (n == 0 || arrival < amin) TINFO(c, j, 0) = arrival; st.xamin = arrival < st.xamin ? arrival : st.xamin; }
+        if (!feas) {
+            if (n == 0) { amin = arrival; amax = arrival; } else { amin = arrival < amin ? arrival : amin; amax = arrival > amax ? arrival : amax; }
+            TINFO2(c, j) = make_double2(amin, amax); st.xamin = arrival < st.xamin ? arrival : st.xamin;
+        }
         tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true);
         st.member |= bit;
     } else { flags |= ENV_ERR_OVERFLOW; st.member &= ~bit; }

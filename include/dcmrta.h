@@ -181,8 +181,8 @@ size_t dcm_algorithmic_bytes_per_step(const dcm_env* env);
 /* number of kernels this handle has launched since creation */
 uint64_t dcm_launch_count(const dcm_env* env);
 
-/* developer aid: with DCM_PASS_TRACE=1 in the environment at dcm_create, the fused pass kernel stamps every work unit with
- * %globaltimer: out_h[4*u .. 4*u+3] = {taken, ready, finished, info} in ns for unit u of the last dcm_step (synchronises) */
+/* developer aid: with DCM_PASS_TRACE=1 in the environment at dcm_create, every k_obs_tile block and every k_episode_list warp of the
+ * last dcm_step stamps %globaltimer / %smid: 8 words per observation tile, then 4 per episode warp (tools/obs_trace.py; synchronises) */
 int dcm_debug_pass_trace(dcm_env* env, uint64_t* out_h, size_t n_words);
 
 const char* dcm_last_error(void);
