@@ -112,8 +112,8 @@ template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, cons
 // (t_agent_update with `known`) from registers; the slot advance scans next_decision in shared memory.  What still goes to memory
 // are the rare paths: a re-visit, a removal, the waiting-coalition scan when the earliest waiting member may give up.
 template <int TW>
-__device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b, double* nds, unsigned* nws) {
-    TC c = make_tc(E, b); c.nds = nds; c.nws = nws;
+__device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b, double* nds, unsigned* nws, double* tmp) {
+    TC c = make_tc(E, b); c.nds = nds; c.nws = nws; c.tmp = tmp;
     const int A = c.A, T = c.T;
     // ---- round 1
     for (int i = 0; i < A; ++i) cp_async8(&nds[(unsigned)i * SCR_STRIDE], &EL(c, a_nd, A, i));
@@ -236,12 +236,10 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
             if (n != n0) { EL(c, t_nmem, T, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
             if (!feas_j) {
                 if (revisit) {                                                // rare: the slots, in one batch (a loop of dependent loads otherwise)
-                    double v8[8];
-#pragma unroll
-                    for (int sl = 0; sl < 8; ++sl) v8[sl] = sl < c.MC ? SARR(c, j, sl) : 0.0;
+                    for (int sl = 0; sl < n; ++sl) cp_async8(&TMPV(c, sl), &SARR(c, j, sl));
+                    cp_async_wait_all();
                     amin = CUDART_INF; amax = -CUDART_INF;
-#pragma unroll
-                    for (int sl = 0; sl < 8; ++sl) if (sl < n) { amin = v8[sl] < amin ? v8[sl] : amin; amax = v8[sl] > amax ? v8[sl] : amax; }
+                    for (int sl = 0; sl < n; ++sl) { const double a = TMPV(c, sl); amin = a < amin ? a : amin; amax = a > amax ? a : amax; }
                     mm_new = true;
                 }
                 if (mm_new) { TINFO2(c, j) = make_double2(amin, amax); st.xamin = amin < st.xamin ? amin : st.xamin; }
@@ -250,10 +248,8 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
             tr.feas = feas_j; tr.ts = ti.x; tr.tf = ti.y;
         }
         reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
-        t_task_update<TW>(c, st, now, nullptr, node_of, false, 0, &tr);       // worker.py:74
-        t_agent_update<TW>(c, st, now, st.touched, node_of, &tr, movers, arrival);   // worker.py:76
         ++n_steps; EL(c, total, 1, 0) = total + 1;
-        if (!pending) t_advance<TW>(c, st, now, pending, flags, node_of);     // worker.py:85, :45-51
+        t_update_and_advance<TW>(c, st, now, pending, flags, node_of, &tr, movers, arrival);    // worker.py:74-76, then :85 / :45-51 while nobody is pending
         if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
         else {
             group = f_current_group(c, node_of, pending);                     // task_env.py:291-298
@@ -285,14 +281,16 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     return flags;
 }
 
-__host__ __device__ inline size_t step_smem_bytes(int A, int ANB) { return (size_t)STEP_THREADS * (8 * (size_t)A + (size_t)ANB); }
+// per-thread scratch of the fused step: [SCR_TMP][64] staging doubles, [A][64] next_decision, [ANB/4][64] node-id words
+__host__ __device__ inline size_t step_smem_bytes(int A, int ANB) { return (size_t)STEP_THREADS * (8 * (size_t)(SCR_TMP + A) + (size_t)ANB); }
 
 template <int TW>
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
-    extern __shared__ __align__(16) unsigned char step_smem[];               // per-thread scratch: [A][64] next_decision, [ANB/4][64] node-id words
+    extern __shared__ __align__(16) unsigned char step_smem[];
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     unsigned flags = 0;
-    if (b < E.S.B) flags = step_env<TW>(E, F, b, (double*)step_smem + threadIdx.x, (unsigned*)(step_smem + (size_t)STEP_THREADS * 8 * E.S.A) + threadIdx.x);
+    double* const tmp = (double*)step_smem + threadIdx.x; double* const nds = tmp + SCR_TMP * STEP_THREADS;
+    if (b < E.S.B) flags = step_env<TW>(E, F, b, nds, (unsigned*)(nds - threadIdx.x + (size_t)STEP_THREADS * E.S.A) + threadIdx.x, tmp);
     if (F.elist) {                                                            // envs whose episode just ended: one warp-aggregated append per warp that has any
         const bool need = (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
         const unsigned m = __ballot_sync(0xffffffffu, need), lane = threadIdx.x & 31u;
@@ -931,9 +929,10 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
 // ---------------------------------------------------------------------------------------------------------------
 template <int TW>
 __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant__ EnvArgs E, const __grid_constant__ GranArgs G) {
+    __shared__ double tmp_smem[SCR_TMP * STEP_THREADS];
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
-    const TC c = make_tc(E, b);
+    TC c = make_tc(E, b); c.tmp = tmp_smem + threadIdx.x;
     const double now = EL(c, now, 1, 0);
     St<TW> st, st0; ld_state(c, st); st0 = st;
     switch (G.op) {
@@ -998,9 +997,11 @@ __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant
 template <int TW>
 __global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__ EnvArgs E, const int* routes, int rstride, const int* route_len,
                                                          unsigned char* cursor /*[B,A] scratch*/, double* makespan) {
+    __shared__ double tmp_smem[SCR_TMP * STEP_THREADS];
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (b >= E.S.B) return;
-    const TC c{E.S, (unsigned)b >> 5, (unsigned)b & 31u, (size_t)((unsigned)b >> 5) * E.S.tile_stride, E.S.A, E.S.T, E.S.MC, 100.0 /* :564 */, E.vel, E.max_time};
+    TC c{E.S, (unsigned)b >> 5, (unsigned)b & 31u, (size_t)((unsigned)b >> 5) * E.S.tile_stride, E.S.A, E.S.T, E.S.MC, 100.0 /* :564 */, E.vel, E.max_time};
+    c.tmp = tmp_smem + threadIdx.x;
     double now = EL(c, now, 1, 0); unsigned flags = EL(c, flags, 1, 0); unsigned n_steps = EL(c, n_steps, 1, 0);
     unsigned char* pos = cursor + (size_t)b * c.A;
     for (int i = 0; i < c.A; ++i) pos[i] = 0;

@@ -34,8 +34,15 @@ struct TC {
     // selects (node ids).
     double* nds = nullptr;     // next_decision of the env's agents, write-through copy of a_nd
     unsigned* nws = nullptr;   // route[-1] of the env's agents, four ids per word, write-through copy of a_node
+    // Staging area of SCR_TMP doubles (every kernel that runs the update functions provides it): the values a data-dependent SET of
+    // tasks / agents needs -- earliest arrivals of the waiting coalitions, the member slots of one task, time_start of the watched
+    // agents -- are gathered with cp.async (LDGSTS: no destination registers, any number in flight) and consumed by ROLLED loops.  One
+    // round trip per SCR_TMP items, no register arrays, no unrolled copies of the loop bodies.
+    double* tmp = nullptr;
 };
-#define SCR_STRIDE 64          // threads per block of the fused step (STEP_THREADS)
+#define SCR_STRIDE 64          // threads per block of the kernels that carry the scratch (STEP_THREADS)
+#define SCR_TMP 16
+#define TMPV(c, k) ((c).tmp[(unsigned)(k) * SCR_STRIDE])
 
 // The arena is TILE-MAJOR: all arrays of one tile of 32 envs are contiguous (c.tb = tile * tile_stride bytes), so the
 // working set of a warp-step lies in one or two 2 MB pages instead of one page per array (TLB reach is 256 MB, the state
@@ -247,16 +254,24 @@ template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c,
 // spread over more than max_waiting_time (:260-265, iterates a copy: Q4), or because they have waited long enough (:266-271,
 // mutates the list it iterates: Q2).  On return *pre, if given, says whether the task is feasible now and carries {time_start,
 // time_finish}; its count / ids / arrivals are stale after a removal (nobody uses them afterwards).
-template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of, TaskR* pre = nullptr) {
+// `expect_removal`: the caller already knows that the earliest member gives up (the waiting-coalition scan), so the member slots are
+// loaded together with the head instead of one round trip later.  Returns the earliest member arrival of the task afterwards, +inf when
+// it no longer waits (feasible, or empty) -- the caller keeps the per-env bound St::xamin exact with it.
+template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of, TaskR* pre = nullptr,
+                                                                        bool expect_removal = false) {
     const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
     TaskR r;
+    bool have_slots = false;
+    auto stage_slots = [&]() { for (int s = 0; s < c.MC; ++s) cp_async8(&TMPV(c, s), &SARR(c, j, s)); have_slots = true; };   // slots past the count hold stale values that are never used
     if (pre && pre->j == j) r = *pre;
     else {
         pre = nullptr;
+        if (expect_removal) stage_slots();
         r.n = EL(c, t_nmem, T, j); r.status = (int)EL(c, t_status, T, j); r.req = (int)EL(c, s_req, T, j);      // :250
         r.ids = *(const u64*)&SMEM(c, j, 0); r.dur = EL(c, s_dur, T, j);
         const double2 mm = TINFO2(c, j); r.amin = mm.x; r.amax = mm.y;
     }
+    double amin_after = r.amin;
     const int n = r.n; const u64 ids = r.ids;
     auto idb = [&](int s) -> unsigned { return (unsigned)(ids >> (8 * s)) & 0xffu; };
     const int stt = r.req - n;                                                // :252 (not refreshed after removals: Q3)
@@ -272,23 +287,21 @@ template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC
             if (newly) newly[j] = 1;
             for (int i = 0; i < c.A; ++i)                                     // everybody who stands here (member or not, :166-171) now sees a feasible task
                 if (node_of(i) == (unsigned)j) AOBS2(c, i) = make_double2(mx, tf);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) if (s < n) {                          // members standing here get next_decision = time_finish
+            for (int s = 0; s < n; ++s) {                                     // members standing here get next_decision = time_finish
                 const unsigned m = idb(s);
                 if (node_of((int)m) == (unsigned)j) st.touched |= 1ull << m;
             }
             if (pre) { pre->feas = true; pre->ts = mx; pre->tf = tf; }
+            amin_after = CUDART_INF;
         } else removal = true;
     } else removal = now - r.amin >= c.W;                                     // :269 for the earliest member (Q1: false when fl(arr+W) rounded down)
     if (removal) {
-        double a8[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) a8[s] = s < c.MC ? SARR(c, j, s) : 0.0;   // slots past the count hold stale values that are never used
+        if (!have_slots) stage_slots();
+        cp_async_wait_all();
         const bool q4 = stt <= 0; const double thr = r.amax - c.W;
         int wv = 0, nab = 0; double amin = CUDART_INF, amax = -CUDART_INF; bool skip = false;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < n) {
-            const double a = a8[s]; const unsigned m = idb(s);
+        for (int s = 0; s < n; ++s) {
+            const double a = TMPV(c, s); const unsigned m = idb(s);
             // Q4 (:260-265) tests every member of a COPY of the list; Q2 (:266-271) removes from the list it iterates, so the member
             // that moves into the vacated slot is skipped by the next index and stays without being tested
             const bool out = q4 ? (a <= thr) : (!skip && now - a >= c.W);
@@ -303,13 +316,15 @@ template <int TW, class NF> __device__ __forceinline__ void t_eval_task(const TC
             EL(c, t_nmem, T, j) = (unsigned char)wv; bump_u16(&EL(c, t_nab, T, j), (unsigned)nab);
             TINFO2(c, j) = make_double2(amin, amax);
             if (wv == 0) ne = 0;
+            amin_after = amin;                                                // +inf when nobody is left
         }
         if (nab || q4) dirty = bit;                                           // the stored status is not refreshed after a removal (Q3): the next call does it
-    }
+    } else if (have_slots) cp_async_wait_all();                               // never leave with copies in flight into the staging area
 #pragma unroll
     for (int k = 0; k < TW; ++k) if (TW == 1 || k == w) {
         st.open[k] = (st.open[k] & ~bit) | open; st.feas[k] |= feas; st.ne[k] = (st.ne[k] & ~bit) | ne; st.dirty[k] = (st.dirty[k] & ~bit) | dirty;
     }
+    return amin_after;
 }
 
 // slot_start (worker.py:50, the call right after the clock moved to `now` = min next_decision, deciders `dec`): which feasible
@@ -328,19 +343,33 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
     // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished.  Both scans are skipped
     //      while the clock has not reached the per-env lower bounds (fl(now - x) >= W and now >= x are monotone in x).
     const bool scan_wait = now - st.xamin >= c.W, scan_fin = now >= st.xfin || (slot_start && dec == 0);
-    double new_amin = CUDART_INF, new_fin = CUDART_INF;
-    u64 hot[TW], done[TW];
+    double new_amin = CUDART_INF, new_fin = CUDART_INF;                       // new_amin: over the waiting coalitions that are NOT evaluated below
+    u64 hot[TW], done[TW], expired[TW];
 #pragma unroll
     for (int w = 0; w < TW; ++w) {
         hot[w] = st.dirty[w] & ~st.feas[w] & st.ne[w]; done[w] = 0;
         u64 h = 0, dn = 0;
-        if (scan_wait) for_bitsN<8, double>(~st.feas[w] & st.ne[w], 64 * w,            // waiting coalitions: earliest arrival only
-                          [&](int j) { return TINFO(c, j, 0); },
-                          [&](u64 bit, int, double amin) { if (now - amin >= c.W) h |= bit & ~st.dirty[w]; new_amin = amin < new_amin ? amin : new_amin; });
-        if (scan_fin) for_bits4<double>(st.feas[w] & ~st.fin[w], 64 * w,                // :272-274
-                          [&](int j) { return TINFO(c, j, 1); },
-                          [&](u64 bit, int, double tf) { if (now >= tf) dn |= bit; else new_fin = tf < new_fin ? tf : new_fin; });
-        hot[w] |= h; done[w] = dn;
+        if (scan_wait) for (u64 m = ~st.feas[w] & st.ne[w]; m;) {               // waiting coalitions: earliest arrival only, SCR_TMP per round trip
+            u64 chunk = 0; int q = 0;
+            for (u64 mm = m; mm && q < SCR_TMP; mm &= mm - 1, ++q) { chunk |= mm & (0 - mm); cp_async8(&TMPV(c, q), &TINFO(c, 64 * w + ctz64(mm), 0)); }
+            m &= ~chunk; cp_async_wait_all();
+            q = 0;
+            for (u64 mm = chunk; mm; mm &= mm - 1, ++q) {
+                const u64 bit = mm & (0 - mm); const double amin = TMPV(c, q);
+                if (now - amin >= c.W) h |= bit; else if (!(hot[w] & bit)) new_amin = amin < new_amin ? amin : new_amin;
+            }
+        }
+        if (scan_fin) for (u64 m = st.feas[w] & ~st.fin[w]; m;) {                 // :272-274
+            u64 chunk = 0; int q = 0;
+            for (u64 mm = m; mm && q < SCR_TMP; mm &= mm - 1, ++q) { chunk |= mm & (0 - mm); cp_async8(&TMPV(c, q), &TINFO(c, 64 * w + ctz64(mm), 1)); }
+            m &= ~chunk; cp_async_wait_all();
+            q = 0;
+            for (u64 mm = chunk; mm; mm &= mm - 1, ++q) {
+                const u64 bit = mm & (0 - mm); const double tf = TMPV(c, q);
+                if (now >= tf) dn |= bit; else new_fin = tf < new_fin ? tf : new_fin;
+            }
+        }
+        expired[w] = h; hot[w] |= h; done[w] = dn;
     }
     // ---- tasks that lost their last member in an EARLIER call: status = requirements (:252 with no members); tasks whose
     //      count changed but that are feasible are not recomputed by the reference (:249)
@@ -354,7 +383,6 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
         st.dirty[w] &= ~st.feas[w] & st.ne[w];
         st.fin[w] |= done[w];
     }
-    if (scan_wait) st.xamin = new_amin;                                       // exact again (tasks evaluated below only raise theirs)
     if (scan_fin) st.xfin = new_fin;
     if (slot_start) {
         st.xfin = CUDART_INF;                                                 // everything feasible so far is covered by the rule from now on
@@ -366,14 +394,25 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
     // ---- full evaluation (rare: the task that was just joined, a coalition whose earliest member gives up)
 #pragma unroll
     for (int w = 0; w < TW; ++w)
-        for (u64 mm = hot[w]; mm; mm &= mm - 1) t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of, pre);
+        for (u64 mm = hot[w]; mm; mm &= mm - 1) {
+            const double am = t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of, pre, (expired[w] & mm & (0 - mm)) != 0);
+            new_amin = am < new_amin ? am : new_amin;
+        }
+    // After a scan the bound is EXACT again, evaluated tasks included: the next call at the same clock does not scan unless a member
+    // that should have left is still there (Q2).  Without a scan it stays a lower bound (evaluations only raise a task's earliest arrival).
+    if (scan_wait) st.xamin = new_amin;
     bool allf = true;
 #pragma unroll
     for (int w = 0; w < TW; ++w) allf = allf && st.feas[w] == all_tasks<TW>(T, w);
     if (allf && now >= st.xret) {                                             // :277-280 depot members
         u64 ret = 0; double nx = CUDART_INF;
-        for_bits4<double>(st.depot & st.route & ~st.returned, 0, [&](int i) { return AREC(c, i, AR_LAST); },
-                          [&](u64 bit, int, double last) { if (now >= last) ret |= bit; else nx = last < nx ? last : nx; });
+        for (u64 m = st.depot & st.route & ~st.returned; m;) {
+            u64 chunk = 0; int q = 0;
+            for (u64 mm = m; mm && q < SCR_TMP; mm &= mm - 1, ++q) { chunk |= mm & (0 - mm); cp_async8(&TMPV(c, q), &AREC(c, ctz64(mm), AR_LAST)); }
+            m &= ~chunk; cp_async_wait_all();
+            q = 0;
+            for (u64 mm = chunk; mm; mm &= mm - 1, ++q) { const double last = TMPV(c, q); if (now >= last) ret |= mm & (0 - mm); else nx = last < nx ? last : nx; }
+        }
         st.returned |= ret; st.xret = nx;
     }
 }
@@ -396,8 +435,13 @@ template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const
     const int A = c.A;
     if (now >= st.xasg) {                                                     // watch: load-only pass, only when somebody can become assigned
         u64 asg = 0; double nx = CUDART_INF;
-        for_bits4<double>(st.watch & ~which, 0, [&](int i) { return EL(c, a_ts, A, i); },
-                          [&](u64 bit, int, double ts) { if (now >= ts) asg |= bit; else nx = ts < nx ? ts : nx; });
+        for (u64 m = st.watch & ~which; m;) {
+            u64 chunk = 0; int q = 0;
+            for (u64 mm = m; mm && q < SCR_TMP; mm &= mm - 1, ++q) { chunk |= mm & (0 - mm); cp_async8(&TMPV(c, q), &EL(c, a_ts, A, ctz64(mm))); }
+            m &= ~chunk; cp_async_wait_all();
+            q = 0;
+            for (u64 mm = chunk; mm; mm &= mm - 1, ++q) { const double ts = TMPV(c, q); if (now >= ts) asg |= mm & (0 - mm); else nx = ts < nx ? ts : nx; }
+        }
         st.assigned |= asg; st.watch &= ~asg; st.xasg = nx;
     }
     auto member_of_feasible = [&](u64 bit, int i, double ts, double tf) {     // :229-233
@@ -417,20 +461,22 @@ template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const
         if (fm) member_of_feasible(bit, i, known->ts, known->tf);
         else { set_nd(c, i, arrival + c.W); st.assigned &= ~bit; }            // :235 / :238
     }
-    // general path, four agents per trip: level 1 = their nodes, level 2 = task info + last arrival, then the stores
+    // general path, five agents per trip: {time_start, time_finish} of the task each stands at and its last arrival, then the stores
     for (u64 m = rest; m;) {
-        const u64 b0 = m & (0 - m); m ^= b0; const u64 b1 = m & (0 - m); m ^= b1;
-        const u64 b2 = m & (0 - m); m ^= b2; const u64 b3 = m & (0 - m); m ^= b3;
-        const int i0 = ctz64(b0), i1 = b1 ? ctz64(b1) : i0, i2 = b2 ? ctz64(b2) : i0, i3 = b3 ? ctz64(b3) : i0;
-        const unsigned k0 = node_of(i0), k1 = node_of(i1), k2 = node_of(i2), k3 = node_of(i3);    // not the depot: those are done
-        const double2 t0 = TINFO2(c, k0), t1 = TINFO2(c, k1), t2 = TINFO2(c, k2), t3 = TINFO2(c, k3);
-        const double l0 = AREC(c, i0, AR_LAST), l1 = AREC(c, i1, AR_LAST), l2 = AREC(c, i2, AR_LAST), l3 = AREC(c, i3, AR_LAST);
-        auto one = [&](u64 bit, int i, unsigned k, double2 tinfo, double last) {
+        u64 chunk = 0; int q = 0;
+        for (u64 mm = m; mm && q + 3 <= SCR_TMP; mm &= mm - 1, q += 3) {
+            const int i = ctz64(mm); const unsigned k = node_of(i);           // not the depot: those are done
+            chunk |= mm & (0 - mm);
+            cp_async8(&TMPV(c, q), &TINFO(c, k, 0)); cp_async8(&TMPV(c, q + 1), &TINFO(c, k, 1)); cp_async8(&TMPV(c, q + 2), &AREC(c, i, AR_LAST));
+        }
+        m &= ~chunk; cp_async_wait_all();
+        q = 0;
+        for (u64 mm = chunk; mm; mm &= mm - 1, q += 3) {
+            const u64 bit = mm & (0 - mm); const int i = ctz64(mm);
             st.watch &= ~bit;
-            if (tbit<TW>(st.feas, (int)k) && (st.member & bit)) member_of_feasible(bit, i, tinfo.x, tinfo.y);
-            else { set_nd(c, i, last + c.W); st.assigned &= ~bit; }           // :235 / :238
-        };
-        one(b0, i0, k0, t0, l0); if (b1) one(b1, i1, k1, t1, l1); if (b2) one(b2, i2, k2, t2, l2); if (b3) one(b3, i3, k3, t3, l3);
+            if (tbit<TW>(st.feas, (int)node_of(i)) && (st.member & bit)) member_of_feasible(bit, i, TMPV(c, q), TMPV(c, q + 1));
+            else { set_nd(c, i, TMPV(c, q + 2) + c.W); st.assigned &= ~bit; }   // :235 / :238
+        }
     }
     st.touched = 0;
 }
@@ -673,22 +719,27 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
 // ---------------------------------------------------------------------------------------------------------------
 // slot boundary (worker.py:45-51, :85): check_finished, loop condition, next_decision, clock, task_update, agent_update
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW, class NF> __device__ __forceinline__ void t_advance(const TC& c, St<TW>& st, double& now, u64& pending, unsigned& flags, const NF& node_of) {
-    int empty_slots = 0;
+// The two updates that follow a decision (worker.py:74-76) and the slot boundary are ONE loop with ONE copy of task_update / agent_update
+// in the kernel's code: trip 0 is the pair of updates after the members' moves (`pre` = the head of the joined task, `movers` arriving at
+// `arrival`), every later trip a slot start.  (Two inlined copies made the step kernel 146 kB of SASS; its warps were stalled on
+// instruction fetch 12 % of the time, profiles/r08c.)
+template <int TW, class NF> __device__ __forceinline__ void t_update_and_advance(const TC& c, St<TW>& st, double& now, u64& pending, unsigned& flags, const NF& node_of,
+                                                                                TaskR* pre, u64 movers, double arrival) {
+    int empty_slots = 0; bool slot = false; u64 dec = 0;
     for (;;) {
-        double t; const u64 dec = t_next_decision(c, t, &st.xlast);
+        t_task_update<TW>(c, st, now, nullptr, node_of, slot, dec, slot ? nullptr : pre);                      // worker.py:74 / :50
+        t_agent_update<TW>(c, st, now, st.touched, node_of, slot ? nullptr : pre, slot ? 0ull : movers, arrival);   // worker.py:76 / :51
+        if (pending) return;
+        // Nobody could decide in this slot.  One such slot is normal (it marks agents as returned); a second in a row means the
+        // state can no longer change and the reference `while` (worker.py:45) would spin forever: stop and flag it.
+        if (slot && ++empty_slots >= 2) { flags |= ENV_DONE | ENV_STUCK; return; }
+        double t; dec = t_next_decision(c, t, &st.xlast);                     // worker.py:85, :45-49
         if (dec == 0) {                                                       // check_finished :368-370
             now = t;
             if (t_all_returned_and_finished(c, st)) flags |= ENV_FINISHED;
         }
         if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; return; }     // worker.py:45
-        pending = dec; now = t;                                               // worker.py:47-49
-        t_task_update<TW>(c, st, now, nullptr, node_of, true, dec);           // :50
-        t_agent_update<TW>(c, st, now, st.touched, node_of);                  // :51
-        if (pending) return;
-        // Nobody could decide.  One such slot is normal (it marks agents as returned); a second in a row means the
-        // state can no longer change and the reference `while` (worker.py:45) would spin forever: stop and flag it.
-        if (++empty_slots >= 2) { flags |= ENV_DONE | ENV_STUCK; return; }
+        pending = dec; now = t; slot = true;                                  // worker.py:47-49
     }
 }
 

@@ -35,6 +35,7 @@ class Episodes:
     action: torch.Tensor | None = None      # [L,B]      i32
     leader: torch.Tensor | None = None      # [L,B]      i32  (agent id, buffer slot 5 of the reference)
     active: torch.Tensor | None = None      # [L,B]      bool: env b took its t-th decision
+    logp: torch.Tensor | None = None        # [L,B,T+1]  f32 log-probabilities of every decision (run(keep_logp=True) only)
 
 
 class BatchedRollout:
@@ -53,21 +54,33 @@ class BatchedRollout:
         return t if self.record else t & 1
 
     @torch.no_grad()
-    def run(self, net, mode: str = "sample", generator: torch.Generator | None = None, amp: bool = False) -> Episodes:
-        """Play one episode per env with `net` (sampling: worker.py:70; greedy: worker.py:222).  The env must not auto-reset."""
+    def run(self, net, mode: str = "sample", generator: torch.Generator | None = None, amp: bool = False, replay: dict | None = None,
+            keep_logp: bool = False) -> Episodes:
+        """Play one episode per env with `net` (sampling: worker.py:70; greedy: worker.py:222).  The env must not auto-reset.
+
+        replay (tests: pins this loop to a recorded reference episode): the draws the reference made OUTSIDE the env, injected instead of
+        drawn here -- "leader" [L+1,B] int32 (np.random.choice(group), worker.py:54; -1 where the env is done), "followers" [L,B,F] int32
+        (-1 padded, task_env.py:331) and, optionally, "action" [L,B] int32 (Categorical.sample, worker.py:70; without it `mode` picks)."""
         env = self.env
         assert not env.auto_reset, "rollouts use one episode per env: create the env with auto_reset=False"
         was_training = net.training
         net.eval()
         s = self._slot(0)
         env.set_output_buffers(self.agent_obs[s], self.task_obs[s], self.mask[s])
-        env.reset()
+        env.reset(leaders=replay["leader"][0] if replay else None)
+        horizon = min(self.horizon, replay["followers"].shape[0]) if replay else self.horizon
+        logps = [] if keep_logp else None
         t = 0
-        while t < self.horizon:
+        while t < horizon:
             s = self._slot(t)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
                 logp = net(self.task_obs[s], self.agent_obs[s], self.mask[s].view(torch.bool))
-            act = sample_actions(logp.float(), generator) if mode == "sample" else greedy_actions(logp)
+            if keep_logp:
+                logps.append(logp.float().clone())
+            if replay is not None and "action" in replay:
+                act = torch.where(env.done, torch.zeros_like(replay["action"][t]), replay["action"][t]).to(torch.int32)
+            else:
+                act = sample_actions(logp.float(), generator) if mode == "sample" else greedy_actions(logp)
             if self.record:
                 self.action[t].copy_(act)
                 self.leader[t].copy_(env.leader)
@@ -76,7 +89,10 @@ class BatchedRollout:
             env.set_output_buffers(self.agent_obs[n], self.task_obs[n], self.mask[n])
             if not self.record:                                      # an env that is done keeps a valid (stale) row in both slots
                 self.mask[n].copy_(self.mask[s])
-            env.step(act)
+            if replay is not None:
+                env.step(act, followers=replay["followers"][t], next_leaders=replay["leader"][t + 1])
+            else:
+                env.step(act)
             t += 1
             if t % self.check_every == 0 and bool(env.done.all()):
                 break
@@ -94,6 +110,8 @@ class BatchedRollout:
         if self.record:
             ep.agent_obs, ep.task_obs, ep.mask = self.agent_obs[:t], self.task_obs[:t], self.mask[:t]
             ep.action, ep.leader, ep.active = self.action[:t], self.leader[:t], self.active[:t]
+        if keep_logp:
+            ep.logp = torch.stack(logps) if logps else None
         return ep
 
 

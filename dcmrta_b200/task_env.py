@@ -122,8 +122,9 @@ class TaskEnv:
     # ---- instance / device handle --------------------------------------------------------------------------------
     def _install(self, A, task_xy, depot_xy, req, dur, cost=None):
         T = int(np.asarray(task_xy).shape[0])
-        M = max(int(self.max_coalition_size), int(np.max(req)), 8)     # member slots: routes / masked actions may exceed requirements
-        M = min(M, 16)
+        M = 8                                              # member slots (DCM_MAX_M): routes / masked actions may exceed the requirements
+        if int(np.max(req)) > M:
+            raise ValueError(f"requirements above {M} are not supported (the reference uses max_coalition_size = 5)")
         if self._be is None or (self._be.A, self._be.T, self._be.M) != (A, T, M):
             if self._be is not None:
                 self._be.close()

@@ -3,8 +3,8 @@ runner.py, worker.py:87-101), one process per GPU.
 
 What stays exactly as in the reference: loss = -(log pi(a|s) * advantage).mean() (driver.py:163-168), entropy diagnostic (:165),
 gradient clipping at L2 norm 10 (:174), Adam(lr=LR) + StepLR(DECAY_STEP, 0.98) stepped per update (:64-65, :175-176), mini-batches
-of BATCH_SIZE decisions (:133-138), advantage = episode reward - greedy reward of the baseline network on the same instance
-(worker.py:89-94), baseline replaced after a one-sided paired t-test at p < 0.05 on 256 held-out instances (:219-279), and the
+of BATCH_SIZE decisions (:133-138), advantage = episode reward - reward of a greedy episode on the same instance (worker.py:89-94;
+played by the CURRENT network as the reference does, TrainerConfig.baseline_net), baseline replaced after a one-sided paired t-test at p < 0.05 on 256 held-out instances (:219-279), and the
 checkpoint keys {model, optimizer, episode, lr_decay, level, best_perf} (:192-199) so checkpoints interchange with RL_test.py.
 
 What changes (B200-first): the 8 Ray CPU actors become env shards on the GPUs (sharding.shard_range, no data-path collective);
@@ -116,6 +116,11 @@ class TrainerConfig:
     max_time: float = MAX_TIME
     updates_per_iteration: int = 0   # 0 = one pass over the collected decisions
     amp: bool = False                # bf16 autocast for the rollout forward passes (the update stays fp32)
+    # Which network plays the greedy episode the advantage is measured against.  "local" is what the reference DOES: baseline_test
+    # (worker.py:222) calls self.local_net -- the network that just sampled -- and never the `local_baseline` it was handed, so the
+    # advantage is reward - greedy reward of the CURRENT policy and the t-test baseline swap (driver.py:219-279) never reaches the loss.
+    # "frozen" is what the reference's variable names suggest: the separately kept baseline network.
+    baseline_net: str = "local"
     seed: int = 0
     eval_instances: int = EVAL_INSTANCES
 
@@ -159,7 +164,7 @@ class ReinforceTrainer:
         self.env.generate(max_duration=5.0)                          # fresh instances (the reference builds a new TaskEnv per episode, worker.py:32)
         clone_instances(self.env, self.base_env)
         ep = self.rollout.run(self.net, "sample", self.gen, amp=cfg.amp)
-        base = self.base_rollout.run(self.baseline, "greedy", amp=cfg.amp)
+        base = self.base_rollout.run(self.net if cfg.baseline_net == "local" else self.baseline, "greedy", amp=cfg.amp)     # worker.py:89, :200-235
         # every episode trains, as in the reference (worker.py:87-101): one the horizon cut is scored -current_time like a MAX_TIME cut
         valid = torch.ones_like(ep.ended)
         adv_env = (ep.reward - base.reward).float()                                                       # worker.py:93

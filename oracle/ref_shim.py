@@ -156,9 +156,11 @@ def greedy_nearest(mask, task_rows64):
     return int(open_tasks[int(np.argmin(d2))]) + 1
 
 
-def run_reference_episode(env, policy: str, seed: int, on_decision=None, max_time=MAX_TIME):
+def run_reference_episode(env, policy, seed: int, on_decision=None, max_time=MAX_TIME, leader_fn=None, on_slot=None):
     """The loop of worker.py:45-87 around the REAL reference env, with the attention policy replaced by
-    `policy` in {"random", "greedy"} and every random draw recorded.
+    `policy` in {"random", "greedy"} -- or a callable (env, leader, mask_u8, k) -> action for scripted fixtures -- and every
+    random draw recorded.  leader_fn(group, k) -> leader replaces the random leader choice; on_slot(env, groups) is called
+    after get_unique_group (quirk fixtures record how many location groups a slot had).
 
     on_decision(env, leader, mask_u8[T+1], agent_obs_f64[A,6], task_obs_f64[T+1,5]) is called when the obs are built
     (before the action is applied).  Returns (trace, reward, finished_tasks)."""
@@ -173,15 +175,24 @@ def run_reference_episode(env, policy: str, seed: int, on_decision=None, max_tim
 
     env.random_choice = recording_choice                      # looked up through self (task_env.py:331)
     idx = 0
+    empty_slots = 0
     while not env.finished and env.current_time < max_time:    # worker.py:45
         ids, t = env.next_decision()
+        # Nobody can decide and the episode is not finished: one such slot is normal (it marks agents as returned), after a second
+        # in a row the state can no longer change and the reference loop would spin forever.  The oracle and the CUDA path stop
+        # there and flag the env STUCK; so does this driver.
+        empty_slots = empty_slots + 1 if len(ids) == 0 else 0
+        if empty_slots >= 3:
+            break
         groups = env.get_unique_group(ids)
+        if on_slot is not None:
+            on_slot(env, groups)
         env.current_time = t
         env.task_update()
         env.agent_update()
         for group in groups:
             while len(group) > 0:
-                leader = int(rng.choice(group))               # worker.py:54 (np.random.choice there)
+                leader = int(leader_fn(group, idx)) if leader_fn is not None else int(rng.choice(group))   # worker.py:54 (np.random.choice there)
                 agent = env.agent_dic[leader]
                 assert not agent["returned"], "reference would spin forever (worker.py:56)"
                 m = env.get_unfinished_task_mask()            # worker.py:57-61
@@ -191,7 +202,9 @@ def run_reference_episode(env, policy: str, seed: int, on_decision=None, max_tim
                 mask = m.astype(np.uint8)
                 if on_decision is not None:
                     on_decision(env, leader, mask, ag, tk)
-                if policy == "random":
+                if callable(policy):
+                    action = int(policy(env, leader, mask, idx))
+                elif policy == "random":
                     action = int(rng.choice(np.flatnonzero(mask == 0)))
                 else:
                     action = greedy_nearest(mask, tk)

@@ -62,3 +62,19 @@ def ctasd():
 
 def full_dump():
     return np.load(GOLD / "full_dump.npz")
+
+
+def quirk_traces():
+    """tests/golden/quirks.npz (oracle/make_quirk_golden.py): hand-built and searched small fixtures, one quirk of SURVEY App. A each."""
+    t = Traces(GOLD / "quirks.npz")
+    t.census_keys = [str(k) for k in t.z["census_keys"]]
+    return t
+
+
+def quirk_instance(tr: Traces, name: str):
+    g = lambda k: tr.z[f"inst/{name}/{k}"]
+    return dict(A=int(g("A")), task_xy=g("task_xy"), depot_xy=g("depot_xy"), req=g("req").astype(np.int32), dur=g("dur"))
+
+
+def quirk_census(tr: Traces, name: str):
+    return dict(zip(tr.census_keys, (int(x) for x in tr.z[f"census/{name}"])))

@@ -64,7 +64,7 @@ def perf_metrics(env, finished_tasks):
                 efficiency=np.mean(env.get_matrix(env.task_dic, "sum_waiting_time")))
 
 
-@pytest.mark.parametrize("episode", [0, 1, 37])
+@pytest.mark.parametrize("episode", [0, 1, 4, 9, 12, 17, 20, 23, 28, 33, 37, 40, 45, 48, 53, 56, 61, 66, 69, 74, 79, 82, 87, 90, 95, 99])
 def test_worker_loop_through_facade(episode):
     from dcmrta_b200.task_env import TaskEnv
     tr = pickle_traces()
@@ -129,3 +129,92 @@ def test_deepcopy_and_pickle_are_independent_snapshots():
     worker_loop(env3, ep, tr)
     r3, _ = env3.get_episode_reward(100)
     assert r1 == r2 == r3 == ep["metrics"][0]
+
+
+def test_individual_agent_loop_through_facade():
+    """worker.py:159-198 `run_test_IS` (RL_test.py METHOD = 'IA'): every decider acts on its own through agent_step, in id order, no groups,
+    no followers -- recorded from the real reference with the greedy-nearest policy (oracle/make_facade_golden.py)."""
+    from pathlib import Path
+    from dcmrta_b200.task_env import TaskEnv
+    z = np.load(Path(__file__).resolve().parent / "golden" / "facade_is.npz")
+    inst = pickle_instances()
+    for i in (int(x) for x in z["instances"]):
+        env = TaskEnv((20, 20), (50, 50), 1, 5, seed=0)
+        env.max_waiting_time = 10
+        env.reactive_planning = False
+        env.reset(as_dicts(inst[i]))
+        env.clear_decisions()
+        k = 0
+        while not env.finished and env.current_time < 100:                            # worker.py:163
+            decision_agents, current_time = env.next_decision()
+            env.current_time = current_time
+            env.task_update()
+            env.agent_update()
+            for agent_id in decision_agents:                                          # worker.py:170
+                agent = env.agent_dic[agent_id]
+                if not agent["returned"]:
+                    mask = env.get_unfinished_task_mask()
+                    mask = np.insert(mask, 0, False) if np.sum(mask) == env.tasks_num else np.insert(mask, 0, True)
+                    ag = np.float32(env.get_current_agent_status(agent))
+                    tk64 = np.asarray(env.get_current_task_status(agent), np.float64)
+                    assert int(agent_id) == int(z[f"{i}/agent"][k]) and env.current_time == z[f"{i}/now"][k], (i, k)
+                    assert canon.obs_digest(mask.astype(np.uint8), ag, np.float32(tk64)) == int(z[f"{i}/dig_obs"][k]), (i, k)
+                    action = int(z[f"{i}/action"][k])
+                    env.agent_step(int(agent_id), action)                             # worker.py:186
+                    env.task_update()
+                    env.agent_update()
+                    k += 1
+            env.finished = env.check_finished()
+        assert k == len(z[f"{i}/agent"])
+        reward, fin = env.get_episode_reward(100)
+        m = perf_metrics(env, fin)
+        gold = z[f"{i}/metrics"]
+        assert reward == gold[0] and np.array_equal(np.array(fin, np.uint8), z[f"{i}/finished"])
+        for c, key in enumerate(("success_rate", "makespan", "time_cost", "waiting_time", "travel_dist", "efficiency")):
+            assert m[key] == pytest.approx(gold[1 + c], rel=1e-12, abs=0), (i, key)
+
+
+class _OldSchemaEnv:
+    """Stand-in for the OLDER TaskEnv class the 50 bundled pickles were written by (SURVEY 8(c) "Pickle schema caveat")."""
+
+
+def test_reference_schema_pickle_loads_through_setstate():
+    """RL_test.py:35-44 with the class swapped: a pickle in the schema of the bundled env_i.pkl -- attributes coalition_size / tasks /
+    agents / cost, max_waiting_time = 3, task keys start_time / finish_time / members_tmp ... and none of feasible_assignment /
+    time_start / abandoned_agent, agent keys occupied / doing_task and no arrival_time / assigned, a depot without 'ID', per-task `time`
+    as ndarray(1,) -- is unpickled into dcmrta_b200.task_env.TaskEnv, normalised as RL_test.py does, and replays a recorded episode."""
+    import io
+    from dcmrta_b200.task_env import TaskEnv
+    tr = pickle_traces()
+    ep = tr.episode(12)
+    i = int(ep["name"].split("/")[0])
+    inst = pickle_instances()[i]
+    T, A = inst["task_xy"].shape[0], inst["A"]
+    old = _OldSchemaEnv()
+    old.coalition_size, old.tasks, old.agents, old.tasks_temp, old.agents_temp, old.cost = 5, (50, 50), (20, 20), T, A, None
+    old.tasks_num, old.agents_num, old.traits_dim, old.max_waiting_time, old.current_time, old.dt, old.finished = T, A, 1, 3, 0, 0.1, False
+    old.task_dic = {j: dict(ID=j, requirements=np.array([inst["req"][j]]), members=[], members_tmp=[], cost=[], location=inst["task_xy"][j],
+                            finished=False, start_time=0, finish_time=0, status=np.array([inst["req"][j]]), time=np.array([inst["dur"][j]]),
+                            label=0, consumed_time=0, start_tick=0, finish_tick=0) for j in range(T)}
+    old.agent_dic = {a: dict(ID=a, abilities=np.ones(1), location=inst["depot_xy"], route=[], current_task=-1, contributed=False,
+                             travel_time=0, velocity=0.2, next_decision=0, depot=inst["depot_xy"], travel_dist=0, occupied=False,
+                             doing_task=False, current_waiting_time=0, cost=np.zeros(1)) for a in range(A)}
+    old.depot = dict(location=inst["depot_xy"], members=list(range(A)))
+    blob = pickle.dumps(old)
+
+    class Unpickler(pickle.Unpickler):                       # the drop-in: wherever the pickle says TaskEnv, hand out ours
+        def find_class(self, module, name):
+            return TaskEnv if name == "_OldSchemaEnv" else super().find_class(module, name)
+    env = Unpickler(io.BytesIO(blob)).load()
+    assert isinstance(env, TaskEnv) and env.tasks_num == T and env.agents_num == A
+    agents, tasks, depot = env.agent_dic, env.task_dic, env.depot                      # RL_test.py:36-43
+    env.max_waiting_time = 10
+    env.reactive_planning = False
+    env.reset((tasks, agents, depot))
+    env.clear_decisions()
+    env.force_waiting = True
+    assert env.max_waiting_time == 10 and float(tasks[3]["time"]) == inst["dur"][3]
+    n = worker_loop(env, ep, tr)
+    assert n == len(ep["leader"])
+    reward, fin = env.get_episode_reward(100)
+    assert reward == ep["metrics"][0]

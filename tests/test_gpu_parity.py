@@ -10,7 +10,7 @@ import pytest
 from oracle import canon
 from oracle.oracle import OracleEnv
 
-from helpers import METRIC_KEYS, ctasd, pickle_instances, pickle_traces, sweep_instance, sweep_traces
+from helpers import METRIC_KEYS, ctasd, pickle_instances, pickle_traces, quirk_instance, quirk_traces, sweep_instance, sweep_traces
 
 pytestmark = pytest.mark.gpu
 REL = 1e-5
@@ -124,6 +124,30 @@ def test_replay_shape_sweep(shape):
     eps = [tr.episode(i) for i in idx]
     insts = [sweep_instance(tr, e["name"]) for e in eps]
     replay_batch(insts, eps, tr)
+
+
+def test_replay_quirk_fixtures():
+    """the hand-built and searched quirk fixtures recorded from the real reference (oracle/make_quirk_golden.py),
+    every decision.  q10_groups has one slot with FOUR location groups: the leaders arrive in np.unique(axis=0) order (x, then y), which
+    is not agent-id order, and an injected leader outside the current group raises DCM_ENV_ERR_LEADER -- so a green replay proves the
+    lexicographic multi-location branch of get_unique_group (t_current_group), which no other trace reaches.  q11_depot_stuck ends
+    in the state where the reference loop would spin forever: DCM_ENV_STUCK."""
+    from dcmrta_b200 import BatchedTaskEnv
+    tr = quirk_traces()
+    for e in range(len(tr)):
+        ep = tr.episode(e)
+        replay_batch([quirk_instance(tr, ep["name"])], [ep], tr)
+    # the stuck fixture once more, for the status bit
+    ep = tr.episode(tr.names.index("q11_depot_stuck"))
+    inst = quirk_instance(tr, "q11_depot_stuck")
+    env = BatchedTaskEnv(1, inst["A"], inst["task_xy"].shape[0], M=5)
+    env.load_instances(*stack_instances([inst]))
+    env.reset(leaders=np.array([int(ep["leader"][0])], np.int32))
+    fol = np.full((1, 8), -1, np.int32); f = tr.followers(ep, 0); fol[0, :len(f)] = f
+    env.step(np.array([int(ep["action"][0])], np.int32), fol, np.array([-1], np.int32))
+    flags = int(env.env_flags()[0])
+    assert flags & 1 and flags & 4 and not flags & 2          # DONE | STUCK, not FINISHED
+    env.close()
 
 
 def test_ctasd_routes_known_answer():

@@ -72,3 +72,165 @@ def test_trainer_iteration_and_checkpoint_roundtrip(tmp_path):
     assert tr2.episode == tr.episode == 256
     out2 = tr2.iteration()
     assert np.isfinite(out2["policy_loss"])
+
+
+def test_rollout_matches_reference_worker():
+    """SURVEY 8(f) row 1 pinned to the reference: the UNMODIFIED Worker.run_episode (worker.py:41-112, baseline_test :200-235) was run in
+    the build container on three seeded 10A/20T instances with fixed AttentionNet weights (oracle/make_rollout_golden.py).  The same
+    weights go into dcmrta_b200.policy.AttentionNet, the reference's draws (leader, sampled action, followers) are injected into
+    BatchedRollout.run, and everything the worker produced must come back: the policy inputs of every decision (episode_buffer slots
+    0, 1, 3: bit-exact), action and agent id (slots 2, 5), the log-probabilities (<= 2e-5: two implementations of the same network),
+    the episode reward, the greedy baseline episode (our network's argmax must pick the recorded actions) and its reward, the
+    advantage (slot 6, fp32) and perf_metrics."""
+    from pathlib import Path
+    from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.policy import AttentionNet
+    from dcmrta_b200.rollout import BatchedRollout
+    z = np.load(Path(__file__).resolve().parent / "golden" / "rollout_golden.npz")
+    net = AttentionNet(6, 5, 16)
+    net.load_state_dict({k[2:]: torch.tensor(z[k]) for k in z.files if k.startswith("w/")}, strict=True)
+    net = net.cuda()
+    B, A, T = 3, 10, 20
+    dev = torch.device("cuda", 0)
+
+    def replay_of(prefix, with_action):
+        n = [len(z[f"{prefix}{i}/leader"]) for i in range(B)]
+        L = max(n)
+        leader = torch.full((L + 1, B), -1, dtype=torch.int32)
+        fol = torch.full((L, B, 8), -1, dtype=torch.int32)
+        act = torch.zeros((L, B), dtype=torch.int32)
+        for i in range(B):
+            leader[:n[i], i] = torch.tensor(z[f"{prefix}{i}/leader"].astype(np.int32))
+            fol[:n[i], i] = torch.tensor(z[f"{prefix}{i}/followers"].astype(np.int32))
+            act[:n[i], i] = torch.tensor(z[f"{prefix}{i}/action"].astype(np.int32))
+        r = {"leader": leader.to(dev), "followers": fol.to(dev)}
+        if with_action:
+            r["action"] = act.to(dev)
+        return r, n, L, act
+
+    def make_env():
+        e = BatchedTaskEnv(B, A, T, M=5, auto_reset=False)
+        e.load_instances(z["inst/task_xy"], z["inst/depot_xy"], z["inst/req"], z["inst/dur"])
+        return e
+
+    # ---- the sampled episode (worker.py:45-85)
+    rp, n, L, _ = replay_of("ep", True)
+    env = make_env()
+    ep = BatchedRollout(env, horizon=L, record=True, check_every=1000).run(net, "sample", replay=rp, keep_logp=True)
+    assert ep.length == L and bool(ep.ended.all())
+    for i in range(B):
+        k = n[i]
+        assert bool(ep.active[:k, i].all()) and not bool(ep.active[k:, i].any())
+        assert np.array_equal(ep.agent_obs[:k, i].cpu().numpy(), z[f"ep{i}/agents"]), i          # slot 0
+        assert np.array_equal(ep.task_obs[:k, i].cpu().numpy(), z[f"ep{i}/tasks"]), i            # slot 1
+        assert np.array_equal(ep.mask[:k, i].cpu().numpy(), z[f"ep{i}/mask"]), i                 # slot 3
+        assert np.array_equal(ep.action[:k, i].cpu().numpy(), z[f"ep{i}/action"]), i             # slot 2
+        assert np.array_equal(ep.leader[:k, i].cpu().numpy(), z[f"ep{i}/agent_id"]), i           # slot 5
+        ref_lp, lp = z[f"ep{i}/logp"], ep.logp[:k, i].cpu().numpy()
+        free = z[f"ep{i}/mask"] == 0
+        np.testing.assert_allclose(lp[free], ref_lp[free], rtol=0, atol=2e-5)
+        assert float(ep.reward[i]) == float(z[f"ep{i}/reward"])                                 # worker.py:87, f64 bit-exact
+        m = ep.metrics[i].cpu().numpy()
+        perf = z[f"ep{i}/perf"]                                                                  # worker.py:103-108
+        for c, name in enumerate(("success_rate", "makespan", "time_cost", "waiting_time", "travel_dist", "efficiency")):
+            if name == "waiting_time":
+                assert m[1 + c] == pytest.approx(perf[c], rel=1e-12), (i, name)
+            else:
+                assert m[1 + c] == perf[c], (i, name)
+    # ---- the greedy baseline episode of the same instances, played by the SAME network (worker.py:200-235)
+    rpb, nb, Lb, act_b = replay_of("base", False)
+    env_b = make_env()
+    base = BatchedRollout(env_b, horizon=Lb, record=True, check_every=1000).run(net, "greedy", replay=rpb)
+    for i in range(B):
+        assert np.array_equal(base.action[:nb[i], i].cpu().numpy(), act_b[:nb[i], i].numpy()), i  # argmax picks what the reference's argmax picked
+        assert float(base.reward[i]) == float(z[f"ep{i}/greedy_reward"])
+    # ---- advantage (worker.py:93-101, GAMMA = 1: every decision of the episode carries reward - greedy reward, in fp32) and slot 4
+    adv = (ep.reward - base.reward).float().cpu().numpy()
+    for i in range(B):
+        assert (z[f"ep{i}/adv"] == adv[i]).all(), i
+        assert z[f"ep{i}/buf_reward"][-1] == np.float32(float(ep.reward[i])) and not z[f"ep{i}/buf_reward"][:-1].any()
+    env.close(); env_b.close()
+
+
+def test_second_rollout_trains_on_its_first_decision():
+    """reset() must clear the done flags of the previous episode, otherwise active[0] of every later rollout is False
+    and the first decision of every episode drops out of training."""
+    from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.policy import AttentionNet
+    from dcmrta_b200.rollout import BatchedRollout
+    torch.manual_seed(0)
+    net = AttentionNet(6, 5, 16).cuda()
+    env = BatchedTaskEnv(64, 6, 10, auto_reset=False, seed=2)
+    env.generate()
+    ro = BatchedRollout(env, horizon=4 * 16, record=True, check_every=4)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    first = ro.run(net, "sample", g)
+    assert bool(first.active[0].all()) and bool(first.ended.all())
+    second = ro.run(net, "sample", g)
+    assert bool(second.active[0].all())
+    assert torch.equal(second.active.sum(0).double(), second.metrics[:, 7])
+    env.close()
+
+
+def test_horizon_cut_episodes_are_scored_not_dropped():
+    """an episode the buffer horizon cuts is scored -current_time (the reference's MAX_TIME cut, worker.py:45/:87), not NaN."""
+    from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.policy import AttentionNet
+    from dcmrta_b200.rollout import BatchedRollout
+    torch.manual_seed(0)
+    net = AttentionNet(6, 5, 16).cuda()
+    env = BatchedTaskEnv(32, 10, 20, auto_reset=False, seed=4)
+    env.generate()
+    ep = BatchedRollout(env, horizon=10, record=True).run(net, "sample", torch.Generator(device="cuda").manual_seed(1))
+    assert not bool(ep.ended.any()) and torch.isfinite(ep.reward).all()
+    assert torch.equal(ep.reward, -env.get_clock())
+    env.close()
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from dcmrta_b200 import trainer as T
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    calls = []
+    real = dist.all_reduce
+
+    def counting(t, *a, **k):
+        calls.append(int(t.numel()))
+        return real(t, *a, **k)
+    dist.all_reduce = counting
+    cfg = T.TrainerConfig(agents=6, tasks=10, envs_per_rank=128 + 64 * rank, batch_size=256, embedding_dim=16, lr=1e-3, eval_instances=16, seed=5)
+    tr = T.ReinforceTrainer(cfg, device=rank)
+    out = tr.iteration()                                   # unequal decision counts per rank: the update count is agreed first
+    ev = tr.maybe_update_baseline()                        # the all_gather after the updates must still pair up
+    flat = torch.cat([p.data.flatten() for p in tr.net.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        q.put(dict(identical=all(torch.equal(gathered[0], g) for g in gathered), updates=out["updates"], decisions=out["decisions"],
+                   grad_allreduces=sum(1 for c in calls if c > 1000), p=ev["p"]))
+    dist.destroy_process_group()
+
+
+def test_trainer_iteration_two_ranks_nccl():
+    """BASELINE configs[4] on hardware: one ReinforceTrainer.iteration() per rank on two GPUs over NCCL, with a different number of envs
+    (hence of decisions) per rank.  The ranks must issue the same number of gradient all-reduces and end with bit-identical parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res["identical"] and res["updates"] >= 1 and res["grad_allreduces"] == res["updates"]

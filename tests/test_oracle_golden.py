@@ -6,7 +6,7 @@ import pytest
 from oracle import canon
 from oracle.oracle import OracleEnv, philox
 
-from helpers import METRIC_KEYS, ctasd, full_dump, pickle_instances, pickle_traces, sweep_instance, sweep_traces
+from helpers import METRIC_KEYS, ctasd, full_dump, pickle_instances, pickle_traces, quirk_census, quirk_instance, quirk_traces, sweep_instance, sweep_traces
 
 
 def replay_on_oracle(inst, ep, tr, check_full=None):
@@ -138,3 +138,24 @@ def test_builtin_policies_terminate_and_are_deterministic():
         runs.append((acts, o.episode_metrics()[0]))
     assert runs[0] == runs[1]
     assert 60 < len(runs[0][0]) < 400
+
+
+def test_quirk_fixtures_digest_exact():
+    """small fixtures recorded from the real reference, one per quirk of App. A -- four location groups in one slot
+    ordered by np.unique(axis=0) (Q10), the group that follows its leader to the depot (Q11), the clock jump when nobody can decide
+    (Q13), members skipped while the list they are removed from is iterated (Q2), stale status (Q3), spread removals (Q4), sticky
+    `assigned` (Q5), ghost members (Q1), re-visits (Q8), and the state in which the reference loop would spin forever (STUCK)."""
+    tr = quirk_traces()
+    seen = dict.fromkeys(tr.census_keys, 0)
+    for e in range(len(tr)):
+        ep = tr.episode(e)
+        inst = quirk_instance(tr, ep["name"])
+        o, fin = replay_on_oracle(inst, ep, tr)
+        assert np.array_equal(fin, tr.z[f"finished/{ep['name']}"])
+        assert o.stuck == (ep["name"] == "q11_depot_stuck")
+        for k, v in quirk_census(tr, ep["name"]).items():
+            seen[k] = max(seen[k], v) if k == "q10_max_groups" else seen[k] + v
+    assert seen["q10_max_groups"] == 4 and seen["q10_multi_group_slot"] >= 3
+    for k in ("q1_ghost_member_decides", "q2_skipped_after_removal", "q3_stale_status", "q4_spread_removal", "q5_sticky_assigned",
+              "q8_revisit", "q11_group_follows_to_depot", "q13_clock_jump"):
+        assert seen[k] >= 1, k
