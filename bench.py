@@ -61,6 +61,7 @@ def parse():
                         "PyTorch attention policy in the loop (rollout) and with the REINFORCE update + gradient all-reduce (train)")
     p.add_argument("--iters", type=int, default=3, help="--mode rollout/train: timed iterations (one episode per env each)")
     p.add_argument("--amp", action="store_true", help="--mode rollout/train: bf16 autocast for the rollout forward passes")
+    p.add_argument("--eager", action="store_true", help="--mode rollout/train: eager decision loop instead of the CUDA-graph replay")
     return p.parse_args()
 
 
@@ -199,11 +200,6 @@ def run_ours(args):
     from dcmrta_b200.sharding import dist_env, reduce_job_totals, shard_range
 
     rank, local, world = dist_env()
-    if world != args.gpus and world == 1 and args.gpus > 1:
-        # not launched under torchrun: re-exec ourselves with one rank per GPU
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", "29533", __file__] + sys.argv[1:]
-        os.execv(sys.executable, cmd)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -365,14 +361,15 @@ def run_training(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.envs if args.envs != 65536 else 8192
-    cfg = TrainerConfig(agents=args.agents, tasks=args.tasks, envs_per_rank=B, amp=args.amp, seed=1234, eval_instances=max(world, 64))
+    cfg = TrainerConfig(agents=args.agents, tasks=args.tasks, envs_per_rank=B, amp=args.amp, seed=1234, eval_instances=max(world, 64),
+                        graph_rollout=not args.eager)
     tr = ReinforceTrainer(cfg, device=local)
 
     def one():
         if args.mode == "train":
             return tr.iteration()["decisions"]
         tr.env.generate(max_duration=5.0)
-        ep = tr.rollout.run(tr.net, "sample", tr.gen, amp=cfg.amp)
+        ep = tr.rollout.run(tr.net, "sample", None if cfg.graph_rollout else tr.gen, amp=cfg.amp)
         return int(ep.active.sum())
 
     one()                                                            # warm-up (allocator, cuBLAS handles, autotune)
@@ -397,7 +394,7 @@ def run_training(args):
             "ms_per_step": float(t.item()) / args.iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 env / " + ("bf16" if args.amp else "fp32") + " policy", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[4]: {B} synthetic {args.agents}A/{args.tasks}T envs per GPU, one episode per env per iteration, "
-                                   f"AttentionNet(128) in PyTorch, mode={args.mode}", "envs_per_gpu": B, "iterations": args.iters,
+                                   f"AttentionNet(128) in PyTorch, mode={args.mode}, decision loop " + ("eager" if args.eager else "replayed from a CUDA graph"), "envs_per_gpu": B, "iterations": args.iters,
                        "parallelism": f"env shards x{world}" + (", one flat NCCL gradient all-reduce per update" if args.mode == "train" else "")},
             "env_steps_timed": float(cnt.item())}), flush=True)
     if world > 1:
@@ -406,6 +403,11 @@ def run_training(args):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # not launched under torchrun: re-exec ourselves with one rank per GPU (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", __file__] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
     if args.impl == "reference":
         run_reference(args)
     elif args.mode != "env":

@@ -46,6 +46,7 @@ struct StepArgs {
     const int* action; const int* followers; int fstride; const int* leader_in; int policy;
     int* next_leader; float* reward; unsigned char* done; int* used_action;
     unsigned* elist; unsigned* ecount; unsigned* ecount_next;   // ended-env list of this pass (k_episode_list), its counter, and the next pass's counter to clear
+    unsigned long long* trace;                                  // DCM_PASS_TRACE=1: [0] earliest block entry, [1] latest block exit of k_step (globaltimer ns)
 };
 
 struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask;
@@ -99,7 +100,7 @@ template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, cons
     }
     EL(c, am_route, 1, 0) = st.route; EL(c, am_assigned, 1, 0) = st.assigned; EL(c, am_returned, 1, 0) = st.returned;
     EL(c, am_member, 1, 0) = st.member; EL(c, am_depot, 1, 0) = st.depot; EL(c, am_touched, 1, 0) = st.touched; EL(c, am_watch, 1, 0) = st.watch;
-    EL(c, x_fin, 1, 0) = st.xfin; EL(c, x_amin, 1, 0) = st.xamin; EL(c, x_asg, 1, 0) = st.xasg; EL(c, x_ret, 1, 0) = st.xret; EL(c, x_last, 1, 0) = st.xlast;
+    EL(c, x_fin, 1, 0) = st.xfin; EL(c, x_amin, 1, 0) = st.xamin; EL(c, x_ret, 1, 0) = st.xret; EL(c, x_last, 1, 0) = st.xlast;
 }
 
 // One leader decision of env b; returns the env's status bits after it.  The duration of k_step is the length of one warp's chain
@@ -117,7 +118,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     const int A = c.A, T = c.T;
     // ---- round 1
     for (int i = 0; i < A; ++i) cp_async8(&nds[(unsigned)i * SCR_STRIDE], &EL(c, a_nd, A, i));
-    for (int k = 0; k < (A + 3) >> 2; ++k) cp_async4(&nws[(unsigned)k * SCR_STRIDE], (const unsigned*)&ANODE(c, 0) + k);
+    for (int k = 0; k < (A + 3) >> 2; ++k) cp_async4(&nws[(unsigned)k * SCR_STRIDE], &ANODE_WORD(c, k));
     unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
     St<TW> st; ld_state(c, st);
     double now = EL(c, now, 1, 0); u64 pending = EL(c, pending, 1, 0), group = EL(c, group, 1, 0);
@@ -141,8 +142,9 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     uint4 b0 = make_uint4(0, 0, 0, 0);
     bool have_b0 = false;
     int action;
-    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
-    else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
+    const unsigned lnode = node_of(leader);                                   // where the leader -- and its whole group -- stands
+    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, lnode, 1, b0.x); }
+    else if (F.policy == 2) action = t_policy_action(c, st, lnode, 2, 0);
     else action = ext_action;
     if (action < 0 || action > T) { flags |= ENV_ERR_ACTION; ok = false; }
     const bool to_task = ok && action != 0; const int j = to_task ? action - 1 : 0;
@@ -151,7 +153,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     double tx = 0.0, ty = 0.0; double2 Lp = make_double2(0.0, 0.0), ti = make_double2(0.0, 0.0);
     TaskR tr;
     if (ok) {
-        Lp = AREC2(c, leader, 0);
+        node_xy(c, lnode, Lp.x, Lp.y);                                        // the group's location = the coordinate of the node it stands at
         if (to_task) {
             tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j);
             tr.dur = EL(c, s_dur, T, j); tr.req = (int)EL(c, s_req, T, j); tr.status = (int)EL(c, t_status, T, j);
@@ -191,11 +193,13 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         double reward = 0.0; int nm = 0; u64 movers = 0;
         auto move = [&](int i) {                                              // agent_step (:300-324)
             const u64 bit = 1ull << i;
-            AREC2(c, i, 0) = make_double2(tx, ty);                            // :320
             AREC(c, i, AR_LAST) = arrival;                                    // :318
             atomicAdd(&AREC(c, i, AR_DIST), d);                               // :317 travel_dist += d: a reduction, no load
-            ANODE(c, i) = (unsigned char)target; scratch_set_node(nws, i, target);   // :314
+            ANODE(c, i) = (unsigned char)target; scratch_set_node(nws, i, target);   // :314, :320 (the location is the node's coordinate)
             st.route |= bit; st.touched |= bit; pending &= ~bit; movers |= bit;
+            // a mover that was waiting for its feasible task to start (WATCH) decides at that task's time_finish >= time_start: `assigned`
+            // has turned true meanwhile (lazy, see t_agent_update)
+            if (st.watch & bit) { st.assigned |= bit; st.watch &= ~bit; }
             if (!to_task) { st.depot |= bit; st.member &= ~bit; }
             else {
                 st.depot &= ~bit; AOBS2(c, i) = aobs;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant_
     extern __shared__ __align__(16) unsigned char step_smem[];
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     unsigned flags = 0;
+    if (F.trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(F.trace, t); }
     double* const tmp = (double*)step_smem + threadIdx.x; double* const nds = tmp + SCR_TMP * STEP_THREADS;
     if (b < E.S.B) flags = step_env<TW>(E, F, b, nds, (unsigned*)(nds - threadIdx.x + (size_t)STEP_THREADS * E.S.A) + threadIdx.x, tmp);
     if (F.elist) {                                                            // envs whose episode just ended: one warp-aggregated append per warp that has any
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant_
         }
         if (b == 0) *F.ecount_next = 0;
     }
+    if (F.trace && (threadIdx.x & 31) == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(F.trace + 1, t); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -370,7 +376,7 @@ __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& 
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int i = lane + 32 * r; const bool in = i < A; const int ii = in ? i : 0;
-        a_nd_v[r] = in ? EL(c, a_nd, A, ii) : CUDART_NAN; const double2 ld = AREC2(c, ii, 1);
+        a_nd_v[r] = in ? EL(c, a_nd, A, ii) : CUDART_NAN; const double2 ld = AREC2(c, ii);
         a_last[r] = in ? ld.x : 0.0; a_dist[r] = ld.y; a_nab_v[r] = in ? (int)EL(c, a_nab, A, ii) : 0;
     }
     double acc0 = 0.0, acc1 = 0.0;
@@ -506,7 +512,7 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
         if (O->agent_obs) for (int k = lane; k < 6 * A; k += 32) O->agent_obs[(size_t)be * 6 * A + k] = 0.f;   // :165-180 nobody has a route
     }
     for (int i = lane; i < A; i += 32) {
-        AREC2(c, i, 0) = make_double2(dx, dy); AREC2(c, i, 1) = make_double2(0.0, 0.0);
+        AREC2(c, i) = make_double2(0.0, 0.0);
         EL(c, a_nd, A, i) = 0.0; ANODE(c, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
     }
     // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
@@ -527,7 +533,7 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
         }
         EL(c, am_route, 1, 0) = 0; EL(c, am_assigned, 1, 0) = 0; EL(c, am_returned, 1, 0) = 0; EL(c, am_member, 1, 0) = 0;
         EL(c, am_depot, 1, 0) = 0; EL(c, am_touched, 1, 0) = 0; EL(c, am_watch, 1, 0) = 0;
-        EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF; EL(c, x_last, 1, 0) = 0.0;
+        EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF; EL(c, x_last, 1, 0) = 0.0;
         EL(c, now, 1, 0) = 0.0; EL(c, pending, 1, 0) = pending; EL(c, group, 1, 0) = group; EL(c, n_steps, 1, 0) = 0;
         EL(c, episode, 1, 0) = episode; EL(c, leader, 1, 0) = leader; EL(c, flags, 1, 0) = nflags;
         if (P.next_leader) P.next_leader[be] = leader;
@@ -619,7 +625,7 @@ __device__ __forceinline__ void obs_unit(const EnvArgs& E, const ObsArgs& O, uns
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
     double Lx = 0, Ly = 0;
-    if (ok) { const double2 p = AREC2(c, leader, 0); Lx = p.x; Ly = p.y; }
+    if (ok) node_xy(c, ANODE(c, leader), Lx, Ly);                             // the leader's location = the coordinate of the node it stands at
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK;
     if (chunk < NA) {                                                         // ---- agent rows (:165-180)
         if (!O.agent_obs) return;
@@ -629,16 +635,17 @@ __device__ __forceinline__ void obs_unit(const EnvArgs& E, const ObsArgs& O, uns
             u64 feas[TW];
 #pragma unroll
             for (int w = 0; w < TW; ++w) feas[w] = EL(c, m_feas, TW, w);
-            const u64 route = EL(c, am_route, 1, 0), depot = EL(c, am_depot, 1, 0), assigned = EL(c, am_assigned, 1, 0);
-            const double now = EL(c, now, 1, 0);
+            const u64 route = EL(c, am_route, 1, 0), depot = EL(c, am_depot, 1, 0), assigned = EL(c, am_assigned, 1, 0), watch = EL(c, am_watch, 1, 0);
+            const double now = EL(c, now, 1, 0), dpx = EL(c, s_dep, 2, 0), dpy = EL(c, s_dep, 2, 1);
 #pragma unroll
-            for (int h = 0; h < OBS_AGENTS_PER_CHUNK; h += 5) {               // five agents per batch: 15 + 10 loads in flight
+            for (int h = 0; h < OBS_AGENTS_PER_CHUNK; h += 5) {               // five agents per batch: records and node ids, then one gather level
                 double2 xy[5], ld[5], ti[5]; double du[5]; unsigned kk[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); xy[q] = AREC2(c, i, 0); ld[q] = AREC2(c, i, 1); kk[q] = ANODE(c, i); }
+                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); ld[q] = AREC2(c, i); kk[q] = ANODE(c, i); }
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {                                   // one gather per agent that stands at a task, none otherwise
+                for (int q = 0; q < 5; ++q) {                                   // what the node says: its coordinate = the agent's location; the task's times
                     const bool at_task = kk[q] != DCM_NODE_DEPOT; const unsigned k = at_task ? kk[q] : 0u; const bool fe = at_task && tbit<TW>(feas, (int)k);
+                    xy[q] = at_task ? make_double2(EL(c, s_tx, T, k), EL(c, s_ty, T, k)) : make_double2(dpx, dpy);
                     ti[q] = fe ? TINFO2(c, k) : make_double2(0.0, 0.0); du[q] = (at_task && !fe) ? EL(c, s_dur, T, k) : 0.0;
                 }
 #pragma unroll
@@ -656,7 +663,8 @@ __device__ __forceinline__ void obs_unit(const EnvArgs& E, const ObsArgs& O, uns
                     }
                     float* r = mine + 6 * (h + q);                            // :176-177
                     r[0] = __double2float_rn(travel_t); r[1] = __double2float_rn(remain); r[2] = __double2float_rn(wait);
-                    r[3] = __double2float_rn(Lx - xy[q].x); r[4] = __double2float_rn(Ly - xy[q].y); r[5] = (assigned & bit) ? 1.0f : 0.0f;
+                    r[3] = __double2float_rn(Lx - xy[q].x); r[4] = __double2float_rn(Ly - xy[q].y);
+                    r[5] = ((assigned & bit) || ((watch & bit) && now >= ti[q].x)) ? 1.0f : 0.0f;       // lazy `assigned` (t_agent_update)
                 }
             }
         }
@@ -733,12 +741,14 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
 // fit twice in an SM's shared memory use k_obs.
 // ---------------------------------------------------------------------------------------------------------------
 #define OBS_TILE_MAX_WARPS 8
-struct ObsTileSmem { unsigned oA, oT, oM, iX, iY, iR, iO, iS, iQ, bar, total; };
+struct ObsTileSmem { unsigned oA, oT, oM, iX, iY, iR, iO, iS, iQ, iN, bar, total; };
 __host__ __device__ inline ObsTileSmem obs_tile_smem(int A, int T) {
+    const unsigned ANB = A <= 32 ? 32u : 64u;
     ObsTileSmem L; unsigned o = 0;
     auto take = [&](unsigned bytes) { const unsigned at = o; o += (bytes + 15u) & ~15u; return at; };
     L.oA = take(32u * 6 * A * 4); L.oT = take(32u * 5 * (T + 1) * 4); L.oM = take(32u * (T + 1));
-    L.iX = take(256u * T); L.iY = take(256u * T); L.iR = take(1024u * A); L.iO = take(512u * A); L.iS = take(32u * T); L.iQ = take(32u * T);
+    L.iX = take(256u * T); L.iY = take(256u * T); L.iR = take(512u * A); L.iO = take(512u * A); L.iS = take(32u * T); L.iQ = take(32u * T);
+    L.iN = take(32u * ANB);
     L.bar = take(8); L.total = o;
     return L;
 }
@@ -768,15 +778,17 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
     const double* iX = (const double*)(obs_smem + L.iX); const double* iY = (const double*)(obs_smem + L.iY);
     const double2* iR = (const double2*)(obs_smem + L.iR); const double2* iO = (const double2*)(obs_smem + L.iO);
     const signed char* iS = (const signed char*)(obs_smem + L.iS); const unsigned char* iQ = obs_smem + L.iQ;
+    const unsigned char* iN = obs_smem + L.iN; const unsigned ANB = (unsigned)E.S.ANB;      // node ids, [ANB/4 words][32 lanes][4]
     const unsigned bar = smem_u32(obs_smem + L.bar);
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
     const unsigned nA = 6u * A, nT = 5u * (T + 1), nM = (unsigned)(T + 1);
     auto clock_ns = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     auto issue_loads = [&](unsigned tile) {                                   // thread 0: the tile's rows, one contiguous span per array
         const TC c0 = make_tc(E, (int)(tile * 32));                           // lane 0 of the tile
-        const unsigned bytes = 256u * T * 2 + 1024u * A + 512u * A + 32u * T * 2;
+        const unsigned bytes = 256u * T * 2 + 512u * A + 512u * A + 32u * T * 2 + 32u * ANB;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        bulk_load(obs_smem + L.iR, &AREC2(c0, 0, 0), 1024u * A, bar);
+        bulk_load(obs_smem + L.iR, &AREC2(c0, 0), 512u * A, bar);
+        bulk_load(obs_smem + L.iN, &ANODE(c0, 0), 32u * ANB, bar);
         bulk_load(obs_smem + L.iO, &AOBS2(c0, 0), 512u * A, bar);
         bulk_load(obs_smem + L.iX, &EL(c0, s_tx, T, 0), 256u * T, bar);
         bulk_load(obs_smem + L.iY, &EL(c0, s_ty, T, 0), 256u * T, bar);
@@ -803,13 +815,21 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
         // per-env scalars of the warp's first chunk, all issued at once and before the leader is known
         int leader = -1; unsigned ended = 0;
         if (b < B) { leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0); if (O.skip_ended) ended = EL(c, ended, 1, 0); }
-        u64 open[TW]; u64 route = 0, depot = 0, assigned = 0; double now = 0.0, dpx = 0.0, dpy = 0.0; float dq[OBS_ROWS_PER_CHUNK];
-        auto agent_scalars = [&]() { route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); now = EL(c, now, 1, 0); };
+        u64 open[TW]; u64 route = 0, depot = 0, assigned = 0, watch = 0; double now = 0.0, dpx = 0.0, dpy = 0.0; float dq[OBS_ROWS_PER_CHUNK];
+        auto agent_scalars = [&]() {
+            route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); watch = EL(c, am_watch, 1, 0); now = EL(c, now, 1, 0);
+            dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1);
+        };
+        // an agent's location is the coordinate of the node it stands at (the staged task coordinates, or the depot)
+        auto node_pos = [&](unsigned i) -> double2 {
+            const unsigned k = iN[((((i >> 2) << 5) + lane) << 2) + (i & 3u)];
+            return k == DCM_NODE_DEPOT ? make_double2(dpx, dpy) : make_double2(iX[(k << 5) + lane], iY[(k << 5) + lane]);
+        };
         auto task_scalars = [&](int chunk) {
             const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
 #pragma unroll
             for (int w = 0; w < TW; ++w) open[w] = EL(c, m_open, TW, w);
-            if (r0 == 0 || O.skip_ended == 2) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
+            dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1);
 #pragma unroll
             for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) { const int jj = r0 + q; dq[q] = EL(c, s_dur32, T, (jj > 0 && jj <= T) ? jj - 1 : 0); }
         };
@@ -833,17 +853,17 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
                 if (!ok) continue;
                 const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
                 const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
-                const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+                const double2 Lp = node_pos((unsigned)leader);
                 float* mine = sA + lane * 6 * A + 6 * c0;
 #pragma unroll 5
                 for (int q = 0; q < na; ++q) {
                     const int i = c0 + q; const u64 bit = 1ull << i; const unsigned at = ((unsigned)i << 5) + lane;
-                    const double2 xy = iR[at << 1];
                     double travel_t = 0.0, wait = 0.0, remain = 0.0;
                     if (fresh) { float2* r = (float2*)(mine + 6 * q); r[0] = r[1] = r[2] = make_float2(0.f, 0.f); continue; }
+                    const double2 xy = node_pos((unsigned)i);
+                    const double2 tt = iO[at];                                // {time_start or 0 (Q6), fl(time_start + time)}
                     if ((route & bit) && !(depot & bit)) {                    // :168
-                        const double arr = iR[(at << 1) + 1].x;
-                        const double2 tt = iO[at];                            // {time_start or 0 (Q6), fl(time_start + time)}
+                        const double arr = iR[at].x;
                         const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;                         // :169
                         if (now <= tt.x) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }     // :170
                         if (now >= tt.x) { const double qv = tt.y - now; remain = qv < 0.0 ? 0.0 : qv; }  // :171
@@ -851,7 +871,7 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
                     float2* r = (float2*)(mine + 6 * q);                      // :176-177 (8-byte aligned: even offsets)
                     r[0] = make_float2(__double2float_rn(travel_t), __double2float_rn(remain));
                     r[1] = make_float2(__double2float_rn(wait), __double2float_rn(Lp.x - xy.x));
-                    r[2] = make_float2(__double2float_rn(Lp.y - xy.y), (assigned & bit) ? 1.0f : 0.0f);
+                    r[2] = make_float2(__double2float_rn(Lp.y - xy.y), ((assigned & bit) || ((watch & bit) && now >= tt.x)) ? 1.0f : 0.0f);   // lazy `assigned` (t_agent_update)
                 }
                 continue;
             }
@@ -863,8 +883,8 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
             bool any_open = false;
 #pragma unroll
             for (int w = 0; w < TW; ++w) any_open = any_open || open[w] != 0;
-            double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
-            if (fresh) { Lp = make_double2(dpx, dpy); any_open = true; }       // everybody stands at the depot, every task is open
+            double2 Lp = fresh ? make_double2(dpx, dpy) : node_pos((unsigned)leader);
+            if (fresh) any_open = true;                                       // everybody stands at the depot, every task is open
             float* mine = sT + lane * 5 * (T + 1) + 5 * r0;
             unsigned char* mm = sM + lane * (T + 1) + r0;
 #pragma unroll
@@ -942,7 +962,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant
         for (int i = 0; i < c.A; ++i) out[i] = -1;
         u64 rest = G.deciders_in[b]; int rank = 0;
         while (rest) {
-            const u64 g = t_current_group(c, rest);
+            const u64 g = t_current_group(c, rest, NodeFromMemory{c});
             for (u64 m = g; m; m &= m - 1) out[__ffsll((long long)m) - 1] = (signed char)rank;
             rest &= ~g; ++rank;
         }
@@ -966,7 +986,8 @@ __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant
             for (int k = 0; k < n; ++k) {
                 const int i = G.members[(size_t)b * G.mstride + k];
                 if (i < 0 || i >= c.A) { flags |= ENV_ERR_ACTION; continue; }
-                double d, tt; travel(c, AREC(c, i, AR_X), AREC(c, i, AR_Y), tx, ty, d, tt);
+                double ax, ay; node_xy(c, ANODE(c, i), ax, ay);
+                double d, tt; travel(c, ax, ay, tx, ty, d, tt);
                 t_agent_step(c, st, now, i, action, tx, ty, d, tt, flags);
                 reward += -tt;                                                // task_env.py:337-339
             }
@@ -1019,7 +1040,8 @@ __global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__
             if (p < len) { act = routes[((size_t)b * c.A + a) * rstride + p]; pos[a] = (unsigned char)(p + 1); }
             if (act < 0 || act > c.T) { flags |= ENV_ERR_ACTION; act = 0; }
             double tx, ty; node_xy(c, act == 0 ? DCM_NODE_DEPOT : (unsigned)(act - 1), tx, ty);
-            double dd, tt; travel(c, AREC(c, a, AR_X), AREC(c, a, AR_Y), tx, ty, dd, tt);
+            double ax, ay; node_xy(c, ANODE(c, a), ax, ay);
+            double dd, tt; travel(c, ax, ay, tx, ty, dd, tt);
             t_agent_step(c, st, now, a, act, tx, ty, dd, tt, flags);          // :585 agent_step
             t_task_update(c, st, now, nullptr); t_agent_update(c, st, now, st.route);   // :586-587
             ++n_steps;
@@ -1078,7 +1100,7 @@ __global__ void k_init(const __grid_constant__ EnvArgs E) {                   //
     if (b >= E.S.NT * 32) return;
     const TC c = make_tc(E, b);
     EL(c, flags, 1, 0) = ENV_DONE | ENV_ACCOUNTED; EL(c, leader, 1, 0) = -1;
-    EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_asg, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF;
+    EL(c, x_fin, 1, 0) = CUDART_INF; EL(c, x_amin, 1, 0) = CUDART_INF; EL(c, x_ret, 1, 0) = CUDART_INF;
 }
 
 // tiled SoA <-> per-env record of dcm_layout.h (export / import / checkpoint format)
@@ -1090,6 +1112,7 @@ __global__ void k_export(const __grid_constant__ EnvArgs E, const DcmLayout L, u
     St<TW> st; ld_state(c, st);
     unsigned char* r = dst + (size_t)b * L.dyn_bytes;
     const int T = c.T, A = c.A, Tp = L.Tp;
+    const double h_now = EL(c, now, 1, 0);
     for (int j = 0; j < T; ++j) {
         const bool fe = tbit<TW>(st.feas, j); const int n = tbit<TW>(st.ne, j) ? (int)EL(c, t_nmem, T, j) : 0;
         for (int s = 0; s < n; ++s) { ((double*)(r + L.o_arr))[s * Tp + j] = SARR(c, j, s); (r + L.o_mem)[s * Tp + j] = SMEM(c, j, s); }
@@ -1101,8 +1124,9 @@ __global__ void k_export(const __grid_constant__ EnvArgs E, const DcmLayout L, u
         ((double*)(r + L.o_alast))[i] = AREC(c, i, AR_LAST); ((double*)(r + L.o_and))[i] = EL(c, a_nd, A, i); ((double*)(r + L.o_adist))[i] = AREC(c, i, AR_DIST);
         ((unsigned short*)(r + L.o_anab))[i] = EL(c, a_nab, A, i); (r + L.o_anode)[i] = ANODE(c, i);
         const u64 bit = 1ull << i;
-        (r + L.o_aflags)[i] = (unsigned char)(((st.route & bit) ? DCM_AF_ROUTE : 0u) | ((st.assigned & bit) ? DCM_AF_ASSIGNED : 0u) | ((st.returned & bit) ? DCM_AF_RETURNED : 0u) |
-                                              ((st.member & bit) ? DCM_AF_MEMBER : 0u) | ((st.touched & bit) ? DCM_AF_TOUCHED : 0u) | ((st.watch & bit) ? DCM_AF_WATCH : 0u));
+        const bool started = (st.watch & bit) && h_now >= EL(c, a_ts, A, i);      // lazy `assigned` (t_agent_update): settled here, as every reader does
+        (r + L.o_aflags)[i] = (unsigned char)(((st.route & bit) ? DCM_AF_ROUTE : 0u) | (((st.assigned & bit) || started) ? DCM_AF_ASSIGNED : 0u) | ((st.returned & bit) ? DCM_AF_RETURNED : 0u) |
+                                              ((st.member & bit) ? DCM_AF_MEMBER : 0u) | ((st.touched & bit) ? DCM_AF_TOUCHED : 0u) | (((st.watch & bit) && !started) ? DCM_AF_WATCH : 0u));
     }
     DcmHdr h;
     h.now = EL(c, now, 1, 0); h.pending = EL(c, pending, 1, 0); h.group = EL(c, group, 1, 0); h.n_steps = EL(c, n_steps, 1, 0);
@@ -1120,7 +1144,7 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
 #pragma unroll
     for (int w = 0; w < TW; ++w) { st.feas[w] = st.fin[w] = st.ne[w] = st.open[w] = st.dirty[w] = 0; }
     st.route = st.assigned = st.returned = st.member = st.depot = st.touched = st.watch = 0;
-    st.xfin = st.xamin = st.xasg = st.xret = CUDART_INF; st.xlast = 0.0;
+    st.xfin = st.xamin = st.xret = CUDART_INF; st.xlast = 0.0;
     const unsigned char* r = src + (size_t)b * L.dyn_bytes;
     const int T = c.T, A = c.A, Tp = L.Tp;
     for (int j = 0; j < T; ++j) {
@@ -1142,8 +1166,7 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
     }
     for (int i = 0; i < A; ++i) {
         const unsigned node = (r + L.o_anode)[i]; const unsigned af = (r + L.o_aflags)[i]; const u64 bit = 1ull << i;
-        double x, y; node_xy(c, node, x, y);
-        AREC(c, i, AR_LAST) = ((const double*)(r + L.o_alast))[i]; AREC(c, i, AR_X) = x; AREC(c, i, AR_Y) = y; AREC(c, i, AR_DIST) = ((const double*)(r + L.o_adist))[i];
+        AREC2(c, i) = make_double2(((const double*)(r + L.o_alast))[i], ((const double*)(r + L.o_adist))[i]);
         EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i];
         EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; ANODE(c, i) = (unsigned char)node;
         if (node != DCM_NODE_DEPOT) {                                         // observation cache (AOBS2)
@@ -1155,7 +1178,7 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
         if (af & DCM_AF_RETURNED) st.returned |= bit;
         if (af & DCM_AF_MEMBER) st.member |= bit;
         if (af & DCM_AF_TOUCHED) st.touched |= bit;
-        if ((af & DCM_AF_WATCH) && node != DCM_NODE_DEPOT) { const double ts = ((const double*)(r + L.o_tstart))[node]; st.watch |= bit; EL(c, a_ts, A, i) = ts; if (ts < st.xasg) st.xasg = ts; }
+        if ((af & DCM_AF_WATCH) && node != DCM_NODE_DEPOT) { const double ts = ((const double*)(r + L.o_tstart))[node]; st.watch |= bit; EL(c, a_ts, A, i) = ts; }
         if ((af & DCM_AF_ROUTE) && node == DCM_NODE_DEPOT) { st.depot |= bit; if (!(af & DCM_AF_RETURNED)) { const double la = ((const double*)(r + L.o_alast))[i]; if (la < st.xret) st.xret = la; } }
         { const double la = ((const double*)(r + L.o_alast))[i]; if (la > st.xlast) st.xlast = la; }
     }
@@ -1260,8 +1283,8 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     size_t off = 0;
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(K, elem) + 255) / 256 * 256; return o; };
     const int MCB = 8; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
-    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32), o_a_obs = carve(A, 16),
-                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_asg = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
+    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 16), o_a_obs = carve(A, 16),
+                 o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
                  o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dur32 = carve(T, 4), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
                  o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
                  o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
@@ -1300,7 +1323,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
     S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec); S.a_obs = (double*)(a + o_a_obs);
-    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_asg = (double*)(a + o_x_asg); S.x_ret = (double*)(a + o_x_ret); S.x_last = (double*)(a + o_x_last); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
+    S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_ret = (double*)(a + o_x_ret); S.x_last = (double*)(a + o_x_last); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
     S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dur32 = (float*)(a + o_s_dur32); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
     S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_dirty = (u64*)(a + o_m_dirty);
     S.am_route = (u64*)(a + o_am_route); S.am_assigned = (u64*)(a + o_am_assigned); S.am_returned = (u64*)(a + o_am_returned); S.am_member = (u64*)(a + o_am_member);
@@ -1512,6 +1535,10 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     const bool use_list = !v->dense_episode;
     unsigned* ecount = nullptr;
     if (use_list) { const unsigned p = v->pass_no++ & 1u; ecount = v->d_ecount + p; F.elist = v->d_elist; F.ecount = ecount; F.ecount_next = v->d_ecount + (p ^ 1u); }
+    if (v->d_trace) {                                                         // the last two words of the trace buffer: k_step's first entry / last exit
+        F.trace = v->d_trace + v->trace_units * 4 - 2;
+        CK(cudaMemsetAsync(F.trace, 0xff, sizeof(unsigned long long), s)); CK(cudaMemsetAsync(F.trace + 1, 0, sizeof(unsigned long long), s));
+    }
     {
         const int grid = grid_env(v, STEP_THREADS); const size_t smem = step_smem_bytes(v->E.S.A, v->E.S.ANB);
         if (v->E.S.TW == 1) k_step<1><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
@@ -1530,19 +1557,19 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
         if (want_obs) return launch_obs(v, O, s);
         return DCM_OK;
     }
+    { const int rc0 = prepare_obs(v); if (rc0) return rc0; }
     CK(cudaEventRecord(v->ev_fork, s));
     v->forked = true;
-    CK(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
-    { const int rc0 = prepare_obs(v); if (rc0) return rc0; }
     // the restarted envs' observation: by k_obs_tile itself when it only depends on the static instance (auto-reset without
     // regeneration; DCM_OBS_RESET_BY_EPISODE=1 switches back), else by the episode kernel, from the registers that hold the new instance
     const bool auto_reset = (v->E.cflags & DCM_FLAG_AUTO_RESET) != 0;
     const bool obs_resets = auto_reset && v->obs_tile && v->obs_resets && !(v->E.cflags & DCM_FLAG_REGENERATE) && v->E.max_time > 0.0;
     P.obs = O; P.write_obs = (auto_reset && !obs_resets) ? 1 : 0;
+    O.skip_ended = obs_resets ? 2 : 1;
+    CK(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
     int rc = use_list ? launch_episode_list(v, P, ecount, v->side) : launch_episode(v, P, v->side);
     if (rc) return rc;
     CK(cudaEventRecord(v->ev_join, v->side));
-    O.skip_ended = obs_resets ? 2 : 1;
     rc = launch_obs(v, O, s);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(s, v->ev_join, 0));

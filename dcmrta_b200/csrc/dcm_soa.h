@@ -47,7 +47,7 @@ struct DcmSoa {
                                //              else {0, 0 + time} -- the operands of task_env.py:170-171, kept current by agent_step and task_update
     double* a_nd;              // [A]   next_decision
     double* a_ts;              // [A]   time_start of the feasible task the agent is a member of (valid with the watch bit)
-    unsigned char* a_node;     // [32 lanes][ANB]  route[-1] or DCM_NODE_DEPOT, per-env contiguous (ANB = 32 for A <= 32, else 64)
+    unsigned char* a_node;     // [ANB/4][32 lanes][4]  route[-1] or DCM_NODE_DEPOT: four agents per word, words row-major (ANB = 32 for A <= 32, else 64)
     unsigned short* a_nab;     // [A]   entries in abandoned_agent lists
     // ---- agent masks (rows: 1) ----
     unsigned long long* am_route;     // len(route) > 0

@@ -55,13 +55,18 @@ struct TC {
 #define SARR(c, j, sl) (TB(c, t_slot_arr)[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
 #define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * 8u + (unsigned)(sl)])                        // member id of slot s (8 id bytes per task and lane)
 #define TINFO(c, j, k) (TB(c, t_info)[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
-#define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 2) + (f)])                                 // {x, y, last arrival, travel_dist}
-enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
-#define AREC2(c, i, h) (((double2*)TB(c, a_rec))[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
+// agent record {arrival_time[-1], travel_dist}.  An agent's location is not stored: it is always the coordinate of the node it stands
+// at (task_env.py:93, :134, :320), so whoever needs it looks the node up (node_xy / the observation kernels' staged task coordinates)
+#define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 1) + (f)])
+enum { AR_LAST = 0, AR_DIST = 1 };
+#define AREC2(c, i) (((double2*)TB(c, a_rec))[LANE_ROW(c, (c).A, i)])                                     // {last, dist}
 #define AOBS2(c, i) (((double2*)TB(c, a_obs))[LANE_ROW(c, (c).A, i)])                                    // observation cache, see dcm_soa.h
 #define TINFO2(c, j) (((double2*)TB(c, t_info))[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
-// route[-1] of the agents of one env, packed: one 32- or 64-byte line per env so that a step can hold them all in registers
-#define ANODE(c, i) (TB(c, a_node)[(size_t)(c).l * (unsigned)(c).s.ANB + (unsigned)(i)])
+// route[-1] of the agents of one env, one byte each, four agents per 32-bit word, words row-major [ANB/4][32 lanes]: a warp reads word k of
+// its 32 envs with one coalesced access, and the tile's words land in shared memory (cp.async in the step, TMA in k_obs_tile) in a layout
+// whose bank depends on the lane alone
+#define ANODE_WORD(c, k) (((unsigned*)TB(c, a_node))[((unsigned)(k) << 5) + (c).l])
+#define ANODE(c, i) (TB(c, a_node)[((((unsigned)(i) >> 2) << 5) + (c).l) * 4u + ((unsigned)(i) & 3u)])
 
 // register-resident boolean state of one env
 template <int TW> struct St {
@@ -70,7 +75,6 @@ template <int TW> struct St {
     // conservative lower bounds (never too high, +inf when the set is empty) that let a step skip whole scans:
     double xfin;    // <= time_finish of every feasible, unfinished task
     double xamin;   // <= earliest member arrival of every non-feasible task that has members
-    double xasg;    // <= time_start awaited by every watched agent
     double xret;    // <= arrival at the depot of every agent that went there and is not `returned` yet
     double xlast;   // == max over agents of arrival_time[-1] (an agent's arrivals never decrease: it decides at or after its last one)
 };
@@ -131,7 +135,7 @@ template <int TW> __device__ __forceinline__ void ld_state(const TC& c, St<TW>& 
     st.route = EL(c, am_route, 1, 0); st.assigned = EL(c, am_assigned, 1, 0); st.returned = EL(c, am_returned, 1, 0);
     st.member = EL(c, am_member, 1, 0); st.depot = EL(c, am_depot, 1, 0); st.touched = EL(c, am_touched, 1, 0);
     st.watch = EL(c, am_watch, 1, 0);
-    st.xfin = EL(c, x_fin, 1, 0); st.xamin = EL(c, x_amin, 1, 0); st.xasg = EL(c, x_asg, 1, 0);
+    st.xfin = EL(c, x_fin, 1, 0); st.xamin = EL(c, x_amin, 1, 0);
     st.xret = EL(c, x_ret, 1, 0); st.xlast = EL(c, x_last, 1, 0);
 }
 template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St<TW>& o, const St<TW>& st) {
@@ -152,7 +156,6 @@ template <int TW> __device__ __forceinline__ void st_state(const TC& c, const St
     if (o.watch != st.watch) EL(c, am_watch, 1, 0) = st.watch;
     if (o.xfin != st.xfin) EL(c, x_fin, 1, 0) = st.xfin;
     if (o.xamin != st.xamin) EL(c, x_amin, 1, 0) = st.xamin;
-    if (o.xasg != st.xasg) EL(c, x_asg, 1, 0) = st.xasg;
     if (o.xret != st.xret) EL(c, x_ret, 1, 0) = st.xret;
     if (o.xlast != st.xlast) EL(c, x_last, 1, 0) = st.xlast;
 }
@@ -433,21 +436,15 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which, const NF& node_of,
                                                                          const TaskR* known = nullptr, u64 movers = 0, double arrival = 0.0) {
     const int A = c.A;
-    if (now >= st.xasg) {                                                     // watch: load-only pass, only when somebody can become assigned
-        u64 asg = 0; double nx = CUDART_INF;
-        for (u64 m = st.watch & ~which; m;) {
-            u64 chunk = 0; int q = 0;
-            for (u64 mm = m; mm && q < SCR_TMP; mm &= mm - 1, ++q) { chunk |= mm & (0 - mm); cp_async8(&TMPV(c, q), &EL(c, a_ts, A, ctz64(mm))); }
-            m &= ~chunk; cp_async_wait_all();
-            q = 0;
-            for (u64 mm = chunk; mm; mm &= mm - 1, ++q) { const double ts = TMPV(c, q); if (now >= ts) asg |= mm & (0 - mm); else nx = ts < nx ? ts : nx; }
-        }
-        st.assigned |= asg; st.watch &= ~asg; st.xasg = nx;
-    }
+    // `assigned` of a member of a feasible task that has not started yet (:232-233) turns true at the first call with now >= time_start.
+    // Nothing in the step reads it before the agent moves again, so that moment is not looked for: the agent keeps its WATCH bit and
+    // a_ts = time_start, and every reader -- the observation kernels, k_export, the agent's next move -- takes
+    //     assigned || (watch && now >= time_start)
+    // (the clock only moves forward, so the first call that would have set it and any later look agree).
     auto member_of_feasible = [&](u64 bit, int i, double ts, double tf) {     // :229-233
         set_nd(c, i, tf);                                                     // :231 time_finish
         if (now >= ts) st.assigned |= bit;                                    // :232-233 (otherwise unchanged: Q5)
-        else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = ts; st.xasg = ts < st.xasg ? ts : st.xasg; }
+        else if (!(st.assigned & bit)) { st.watch |= bit; EL(c, a_ts, A, i) = ts; }
     };
     u64 rest = 0;                                                             // :209
     for (u64 q = which & st.route; q; q &= q - 1) {                           // first the agents that need nothing from memory
@@ -532,12 +529,14 @@ template <int TW> __device__ __forceinline__ bool t_all_returned_and_finished(co
 // lexicographically smallest location (np.unique(axis=0) order).  Pending agents never move while they are pending,
 // so re-evaluating this after every decision walks the groups in the reference order.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending) {
+template <class NF> __device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending, const NF& node_of) {
     if ((pending & (pending - 1)) == 0) return pending;                       // zero or one decider
     double bx = CUDART_INF, by = CUDART_INF; u64 g = 0;
-    for_bits4<double2>(pending, 0, [&](int i) { return AREC2(c, i, 0); }, [&](u64 bit, int, double2 p) {
-        if (lex_less(p.x, p.y, bx, by)) { bx = p.x; by = p.y; g = bit; } else if (p.x == bx && p.y == by) g |= bit;
-    });
+    for (u64 m = pending; m; m &= m - 1) {                                    // one dependent lookup per decider: the coordinate of the node it stands at
+        const u64 bit = m & (0 - m);
+        double x, y; node_xy(c, node_of(ctz64(m)), x, y);                     // (an agent that never moved has node = depot)
+        if (lex_less(x, y, bx, by)) { bx = x; by = y; g = bit; } else if (x == bx && y == by) g |= bit;
+    }
     return g;
 }
 
@@ -549,7 +548,7 @@ template <class NF> __device__ __forceinline__ u64 f_current_group(const TC& c, 
     const unsigned first = node_of(ctz64(pending));
     bool same = true;
     for (u64 m = pending & (pending - 1); m; m &= m - 1) same = same && node_of(ctz64(m)) == first;
-    return same ? pending : t_current_group(c, pending);
+    return same ? pending : t_current_group(c, pending, node_of);
 }
 
 
@@ -569,7 +568,11 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     const int j = action - 1;
     const bool to_task = action != 0, feas = to_task && tbit<TW>(st.feas, j), nonempty = to_task && tbit<TW>(st.ne, j);
     // ---- every load first (nothing below can be hoisted above a byte store by the compiler)
-    const double2 ld = AREC2(c, i, 1);                                        // {last arrival, travel_dist}
+    const double2 ld = AREC2(c, i);                                           // {last arrival, travel_dist}
+    if (st.watch & bit) {                                                     // leaving a feasible task it was waiting to start: settle `assigned` (lazy, see t_agent_update)
+        if (now >= EL(c, a_ts, c.A, i)) st.assigned |= bit;
+        st.watch &= ~bit;
+    }
     double2 aobs = make_double2(0.0, 0.0);                                    // observation cache (AOBS2)
     if (to_task) { if (feas) aobs = TINFO2(c, j); else aobs.y = 0.0 + EL(c, s_dur, T, j); }
     int n = 0; u64 ids = 0; double amin = CUDART_INF, amax = -CUDART_INF;
@@ -579,8 +582,7 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
         if (!feas) { const double2 mm = TINFO2(c, j); amin = mm.x; amax = mm.y; }   // {earliest, latest} member arrival of a waiting coalition
     }
     const double arrival = now + tt;                                          // :318
-    AREC2(c, i, 1) = make_double2(arrival, ld.y + d);                         // :317-318
-    AREC2(c, i, 0) = make_double2(tx, ty);                                    // :320
+    AREC2(c, i) = make_double2(arrival, ld.y + d);                            // :317-318 (:320 location = the node's coordinate, not stored)
     ANODE(c, i) = (unsigned char)(to_task ? (unsigned)j : DCM_NODE_DEPOT);   // :314
     st.route |= bit; st.touched |= bit;
     st.xlast = arrival > st.xlast ? arrival : st.xlast;
@@ -610,13 +612,13 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
 // ---------------------------------------------------------------------------------------------------------------
 // built-in policies, evaluated on the state the observation shows
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ int t_policy_action(const TC& c, const St<TW>& st, int leader, int policy, unsigned word) {
+template <int TW> __device__ __forceinline__ int t_policy_action(const TC& c, const St<TW>& st, unsigned node_of_leader, int policy, unsigned word) {
     int n_open = 0;
 #pragma unroll
     for (int w = 0; w < TW; ++w) n_open += __popcll(st.open[w]);
     if (n_open == 0) return 0;                                                // only the depot is unmasked
     if (policy == 2) {                                                        // greedy nearest (fp64 squared distance, lowest id on ties)
-        const double Lx = AREC(c, leader, AR_X), Ly = AREC(c, leader, AR_Y);
+        double Lx, Ly; node_xy(c, node_of_leader, Lx, Ly);
         double bd = CUDART_INF; int bj = -1;
 #pragma unroll
         for (int w = 0; w < TW; ++w) for (u64 mm = st.open[w]; mm; mm &= mm - 1) {
@@ -751,9 +753,9 @@ template <int TW, class NF> __device__ __forceinline__ void t_update_and_advance
 template <int TW> __device__ __forceinline__ void obs_agent_row(const TC& c, const St<TW>& st, double now, double Lx, double Ly, int i, float* r) {
     const u64 bit = 1ull << i;
     double travel_t = 0.0, wait = 0.0, remain = 0.0;
-    const double ax = AREC(c, i, AR_X), ay = AREC(c, i, AR_Y);
+    const unsigned k = ANODE(c, i);
+    double ax, ay; node_xy(c, k, ax, ay);
     if ((st.route & bit) && !(st.depot & bit)) {                              // :168
-        const unsigned k = ANODE(c, i);
         const double arr = AREC(c, i, AR_LAST);
         const bool feas = tbit<TW>(st.feas, (int)k);
         const double ts = feas ? TINFO(c, k, 0) : 0.0;                        // time_start is 0 until the task is feasible (Q6)

@@ -115,6 +115,95 @@ class BatchedRollout:
         return ep
 
 
+class GraphedRollout(BatchedRollout):
+    """BatchedRollout whose decision loop -- policy forward, sampling, experience recording, dcm_step -- is captured ONCE in a CUDA graph
+    of `unroll` decisions and replayed: the loop issues hundreds of small kernels per decision, and at a few thousand envs the eager
+    version is bound by their launches, not by the GPU.  dcm_step is asynchronous on the caller's stream and synchronises
+    nothing, so it is captured like any other kernel launch (its fork to the episode stream and the join become graph edges).
+
+    The env writes each observation into one of two fixed ping-pong slots (graph nodes have fixed addresses); a captured index_copy_
+    files it into the episode buffer at a decision counter that lives on the device.  `unroll` is even: the env alternates two
+    ended-episode counters from pass to pass, and a replay must leave that parity where the capture found it.  Sampling uses the default
+    CUDA generator (graph-safe Philox offsets); seed it with torch.cuda.manual_seed."""
+
+    def __init__(self, env: BatchedTaskEnv, horizon: int, record: bool = True, check_every: int = 16, unroll: int = 8):
+        assert unroll >= 2 and unroll % 2 == 0
+        horizon = -(-int(horizon) // unroll) * unroll                # whole replays
+        super().__init__(env, horizon, record, check_every)
+        B, A, T, dev = env.B, env.A, env.T, env.device
+        self.unroll = unroll
+        self.pp = [(torch.zeros(B, A, 6, dtype=torch.float32, device=dev), torch.zeros(B, T + 1, 5, dtype=torch.float32, device=dev),
+                    torch.ones(B, T + 1, dtype=torch.uint8, device=dev)) for _ in range(2)]
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._graphs = {}
+
+    def _decision(self, net, mode, amp, s):
+        env = self.env
+        a, k, m = self.pp[s]
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            logp = net(k, a, m.view(torch.bool))
+        act = sample_actions(logp.float()) if mode == "sample" else greedy_actions(logp)
+        if self.record:
+            self.agent_obs.index_copy_(0, self.t_dev, a.unsqueeze(0)); self.task_obs.index_copy_(0, self.t_dev, k.unsqueeze(0))
+            self.mask.index_copy_(0, self.t_dev, m.unsqueeze(0)); self.action.index_copy_(0, self.t_dev, act.unsqueeze(0))
+            self.leader.index_copy_(0, self.t_dev, env.leader.unsqueeze(0))
+            self.active.index_copy_(0, self.t_dev, torch.logical_not(env.done).unsqueeze(0))
+        env.set_output_buffers(*self.pp[1 - s])
+        env.step(act)
+        self.t_dev.add_(1)
+
+    def _graph(self, net, mode, amp):
+        key = (id(net), mode, bool(amp))
+        if key not in self._graphs:
+            env = self.env
+            side = torch.cuda.Stream(device=env.device)
+            side.wait_stream(torch.cuda.current_stream(env.device))
+            with torch.cuda.stream(side):                            # warm-up off the capture: allocator, cuBLAS handles, the env's one-time setup
+                env.set_output_buffers(*self.pp[0])
+                env.reset()
+                self.t_dev.zero_()
+                for u in range(2):
+                    self._decision(net, mode, amp, u % 2)
+            torch.cuda.current_stream(env.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            self.t_dev.zero_()
+            with torch.cuda.graph(g):
+                for u in range(self.unroll):
+                    self._decision(net, mode, amp, u % 2)
+            self._graphs[key] = g
+        return self._graphs[key]
+
+    @torch.no_grad()
+    def run(self, net, mode: str = "sample", generator=None, amp: bool = False, replay=None, keep_logp: bool = False) -> Episodes:
+        assert replay is None and not keep_logp and generator is None, "the graphed loop draws from the default CUDA generator and replays nothing"
+        env = self.env
+        assert not env.auto_reset
+        was_training = net.training
+        net.eval()
+        g = self._graph(net, mode, amp)
+        env.set_output_buffers(*self.pp[0])
+        env.reset()
+        self.t_dev.zero_()
+        t = 0
+        while t < self.horizon:
+            g.replay()
+            t += self.unroll
+            if t % self.check_every < self.unroll and bool(env.done.all()):
+                break
+        ended = env.done.clone()
+        metrics = env.episode_metrics()
+        if not bool(ended.all()):
+            live = env.compute_metrics()                             # horizon cut: scored -current_time (see BatchedRollout.run)
+            metrics = torch.where(ended.unsqueeze(1), metrics, live)
+        if was_training:
+            net.train()
+        ep = Episodes(reward=metrics[:, 0].clone(), metrics=metrics, ended=ended, length=t)
+        if self.record:
+            ep.agent_obs, ep.task_obs, ep.mask = self.agent_obs[:t], self.task_obs[:t], self.mask[:t]
+            ep.action, ep.leader, ep.active = self.action[:t], self.leader[:t], self.active[:t]
+        return ep
+
+
 def clone_instances(src: BatchedTaskEnv, dst: BatchedTaskEnv) -> None:
     """copy.deepcopy(self.env) of worker.py:33 for a batch: the baseline env plays the same instances."""
     inst = src.get_instances()

@@ -121,6 +121,7 @@ class TrainerConfig:
     # advantage is reward - greedy reward of the CURRENT policy and the t-test baseline swap (driver.py:219-279) never reaches the loss.
     # "frozen" is what the reference's variable names suggest: the separately kept baseline network.
     baseline_net: str = "local"
+    graph_rollout: bool = True       # replay the decision loop from a CUDA graph (rollout.GraphedRollout); False = eager loop, explicit generator
     seed: int = 0
     eval_instances: int = EVAL_INSTANCES
 
@@ -128,7 +129,7 @@ class TrainerConfig:
 class ReinforceTrainer:
     def __init__(self, cfg: TrainerConfig, device: int = 0):
         from .batched_env import BatchedTaskEnv
-        from .rollout import BatchedRollout
+        from .rollout import BatchedRollout, GraphedRollout
         from .sharding import shard_range
         self.cfg = cfg
         self.rank, self.world = world()
@@ -146,15 +147,19 @@ class ReinforceTrainer:
         self.env = BatchedTaskEnv(B, cfg.agents, cfg.tasks, seed=cfg.seed, first_gid=first_gid, **kw)
         self.base_env = BatchedTaskEnv(B, cfg.agents, cfg.tasks, seed=cfg.seed + 1, first_gid=first_gid, **kw)
         horizon = cfg.horizon or 4 * (cfg.agents + cfg.tasks)
-        self.rollout = BatchedRollout(self.env, horizon, record=True)
-        self.base_rollout = BatchedRollout(self.base_env, horizon, record=False)
+        Rollout = GraphedRollout if cfg.graph_rollout else BatchedRollout
+        self.rollout = Rollout(self.env, horizon, record=True)
+        self.base_rollout = Rollout(self.base_env, horizon, record=False)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(cfg.seed * 1000003 + self.rank)
+        if cfg.graph_rollout:                                        # the graphed loop samples from the default CUDA generator
+            with torch.cuda.device(self.device):
+                torch.cuda.manual_seed(cfg.seed * 1000003 + self.rank)
         # held-out instances for the baseline test (driver.py:119): their own generator stream
         E = max(1, cfg.eval_instances // self.world)
         self.eval_env = BatchedTaskEnv(E, cfg.agents, cfg.tasks, seed=cfg.seed + 7919, first_gid=self.rank * E, **kw)
         self.eval_env.generate(max_duration=5.0)
-        self.eval_rollout = BatchedRollout(self.eval_env, horizon, record=False)
+        self.eval_rollout = Rollout(self.eval_env, horizon, record=False)
         self.baseline_value = None
 
     # ---- one training iteration: play, score against the baseline, update ------------------------------------------------
@@ -163,7 +168,7 @@ class ReinforceTrainer:
         cfg = self.cfg
         self.env.generate(max_duration=5.0)                          # fresh instances (the reference builds a new TaskEnv per episode, worker.py:32)
         clone_instances(self.env, self.base_env)
-        ep = self.rollout.run(self.net, "sample", self.gen, amp=cfg.amp)
+        ep = self.rollout.run(self.net, "sample", None if cfg.graph_rollout else self.gen, amp=cfg.amp)
         base = self.base_rollout.run(self.net if cfg.baseline_net == "local" else self.baseline, "greedy", amp=cfg.amp)     # worker.py:89, :200-235
         # every episode trains, as in the reference (worker.py:87-101): one the horizon cut is scored -current_time like a MAX_TIME cut
         valid = torch.ones_like(ep.ended)

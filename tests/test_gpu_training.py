@@ -234,3 +234,42 @@ def test_trainer_iteration_two_ranks_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res["identical"] and res["updates"] >= 1 and res["grad_allreduces"] == res["updates"]
+
+
+def test_graphed_rollout_records_what_the_env_did():
+    """rollout.GraphedRollout (the decision loop replayed from a CUDA graph, dcm_step captured with its stream fork / join): what it
+    records must replay, decision by decision, on a second env through the eager path."""
+    from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.policy import AttentionNet
+    from dcmrta_b200.rollout import GraphedRollout, clone_instances
+    B, A, T = 300, 10, 20
+    torch.manual_seed(0)
+    net = AttentionNet(6, 5, 32).cuda()
+    env = BatchedTaskEnv(B, A, T, auto_reset=False, seed=5)
+    env.generate()
+    ro = GraphedRollout(env, horizon=4 * (A + T), record=True, check_every=8, unroll=4)
+    torch.cuda.manual_seed(7)
+    ep = ro.run(net, "sample")                                 # (the first call also builds the graph: two eager warm-up decisions draw as well)
+    assert bool(ep.ended.all())
+    n_dec = ep.active.sum(0)
+    assert torch.equal(n_dec.double(), ep.metrics[:, 7])
+    assert not bool((ep.mask.gather(2, ep.action.long().unsqueeze(2)).squeeze(2).bool() & ep.active).any())
+    env2 = BatchedTaskEnv(B, A, T, auto_reset=False, seed=5)
+    clone_instances(env, env2)
+    env2.reset(leaders=ep.leader[0])
+    for t in range(ep.length):
+        act = ep.active[t]
+        assert torch.equal(env2.agent_obs[act], ep.agent_obs[t][act]), t
+        assert torch.equal(env2.task_obs[act], ep.task_obs[t][act]), t
+        assert torch.equal(env2.mask_u8[act], ep.mask[t][act]), t
+        more = t + 1 < ep.length
+        nxt = torch.where(ep.active[t + 1], ep.leader[t + 1], torch.full_like(ep.leader[0], -1)) if more else torch.full_like(ep.leader[0], -1)
+        env2.step(ep.action[t], next_leaders=nxt)
+    assert torch.equal(env2.episode_metrics(), ep.metrics)
+    # the same graph again (the env's Philox streams have moved on to the next episode index, so the episode differs): still a whole,
+    # self-consistent record
+    again = ro.run(net, "sample")
+    assert bool(again.ended.all()) and bool(again.active[0].all())
+    assert torch.equal(again.active.sum(0).double(), again.metrics[:, 7])
+    assert not bool((again.mask.gather(2, again.action.long().unsqueeze(2)).squeeze(2).bool() & again.active).any())
+    env.close(); env2.close()

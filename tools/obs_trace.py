@@ -21,8 +21,10 @@ EB = 148 * int(os.environ.get("DCM_EPISODE_GRID", "8")) + 8   # warps of k_episo
 pc = lambda x: np.percentile(x, [0, 10, 50, 90, 99, 100]).round(2)
 for p in range(PASSES):
     env.step(policy="random"); torch.cuda.synchronize()
-    buf = np.zeros(NT * 8 + 4 * EB, np.uint64)
-    check(lib().dcm_debug_pass_trace(env._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+    full = np.zeros(NT * 64 * 4, np.uint64)
+    check(lib().dcm_debug_pass_trace(env._h, full.ctypes.data_as(C.c_void_p), full.size))
+    buf = full[:NT * 8 + 4 * EB]
+    ks0, ks1 = int(full[-2]), int(full[-1])                     # k_step: earliest block entry, latest warp exit
     tr = buf[:NT * 8].reshape(NT, 8)
     ep = buf[NT * 8:].reshape(EB, 4).astype(np.int64)
     ep = ep[ep[:, 0] > 0]
@@ -31,7 +33,11 @@ for p in range(PASSES):
     tr = (tr & np.uint64((1 << 63) - 1)).astype(np.int64)
     t0 = tr[:, 0].min()
     t = (tr - t0) / 1e3
-    line = "pass %d: k_obs_tile span %.1f us (%d of %d tiles copied env by env)" % (p, t[:, 3].max(), int(slow.sum()), NT)
+    line = "pass %d: k_step %.1f us, gap to first obs block %.1f us; k_obs_tile span %.1f us (%d of %d tiles copied env by env)" % (
+        p, (ks1 - ks0) / 1e3, (int(t0) - ks1) / 1e3, t[:, 3].max(), int(slow.sum()), NT)
+    if p > 0:
+        line += "; previous pass end -> this k_step start %.1f us" % ((ks0 - prev_end) / 1e3)
+    prev_end = int(t0) + int(t[:, 3].max() * 1e3)
     if len(ep):
         e0, e1 = (ep[:, 0] - t0) / 1e3, (ep[:, 1] - t0) / 1e3
         per_sm = np.bincount(ep[:, 2], minlength=148)
