@@ -47,6 +47,7 @@ struct StepArgs {
     int* next_leader; float* reward; unsigned char* done; int* used_action;
     unsigned* elist; unsigned* ecount; unsigned* ecount_next;   // ended-env list of this pass (k_episode_list), its counter, and the next pass's counter to clear
     unsigned long long* trace;                                  // DCM_PASS_TRACE=1: [0] earliest block entry, [1] latest block exit of k_step (globaltimer ns)
+    int use_nds;                                                // next_decision scratch in shared memory (handles with A <= STEP_NDS_MAX_AGENTS)
 };
 
 struct ObsArgs { const int* leader; /* [B] or NULL = the env's current leader */ float* agent_obs; float* task_obs; unsigned char* mask;
@@ -114,10 +115,10 @@ template <int TW> __device__ __forceinline__ void st_state_all(const TC& c, cons
 // are the rare paths: a re-visit, a removal, the waiting-coalition scan when the earliest waiting member may give up.
 template <int TW>
 __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F, int b, double* nds, unsigned* nws, double* tmp) {
-    TC c = make_tc(E, b); c.nds = nds; c.nws = nws; c.tmp = tmp;
+    TC c = make_tc(E, b); c.nds = F.use_nds ? nds : nullptr; c.nws = nws; c.tmp = tmp;
     const int A = c.A, T = c.T;
     // ---- round 1
-    for (int i = 0; i < A; ++i) cp_async8(&nds[(unsigned)i * SCR_STRIDE], &EL(c, a_nd, A, i));
+    if (F.use_nds) for (int i = 0; i < A; ++i) cp_async8(&nds[(unsigned)i * SCR_STRIDE], &EL(c, a_nd, A, i));
     for (int k = 0; k < (A + 3) >> 2; ++k) cp_async4(&nws[(unsigned)k * SCR_STRIDE], &ANODE_WORD(c, k));
     unsigned flags = EL(c, flags, 1, 0) & ~ENV_FRESH;
     St<TW> st; ld_state(c, st);
@@ -142,9 +143,8 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     uint4 b0 = make_uint4(0, 0, 0, 0);
     bool have_b0 = false;
     int action;
-    const unsigned lnode = node_of(leader);                                   // where the leader -- and its whole group -- stands
-    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, lnode, 1, b0.x); }
-    else if (F.policy == 2) action = t_policy_action(c, st, lnode, 2, 0);
+    if (F.policy == 1) { b0 = draw_block(rng, episode, n_steps, 0); have_b0 = true; action = t_policy_action(c, st, leader, 1, b0.x); }
+    else if (F.policy == 2) action = t_policy_action(c, st, leader, 2, 0);
     else action = ext_action;
     if (action < 0 || action > T) { flags |= ENV_ERR_ACTION; ok = false; }
     const bool to_task = ok && action != 0; const int j = to_task ? action - 1 : 0;
@@ -153,7 +153,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     double tx = 0.0, ty = 0.0; double2 Lp = make_double2(0.0, 0.0), ti = make_double2(0.0, 0.0);
     TaskR tr;
     if (ok) {
-        node_xy(c, lnode, Lp.x, Lp.y);                                        // the group's location = the coordinate of the node it stands at
+        Lp = AREC2(c, leader, 0);
         if (to_task) {
             tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j);
             tr.dur = EL(c, s_dur, T, j); tr.req = (int)EL(c, s_req, T, j); tr.status = (int)EL(c, t_status, T, j);
@@ -193,9 +193,10 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         double reward = 0.0; int nm = 0; u64 movers = 0;
         auto move = [&](int i) {                                              // agent_step (:300-324)
             const u64 bit = 1ull << i;
+            AREC2(c, i, 0) = make_double2(tx, ty);                            // :320
             AREC(c, i, AR_LAST) = arrival;                                    // :318
             atomicAdd(&AREC(c, i, AR_DIST), d);                               // :317 travel_dist += d: a reduction, no load
-            ANODE(c, i) = (unsigned char)target; scratch_set_node(nws, i, target);   // :314, :320 (the location is the node's coordinate)
+            ANODE(c, i) = (unsigned char)target; scratch_set_node(nws, i, target);   // :314
             st.route |= bit; st.touched |= bit; pending &= ~bit; movers |= bit;
             // a mover that was waiting for its feasible task to start (WATCH) decides at that task's time_finish >= time_start: `assigned`
             // has turned true meanwhile (lazy, see t_agent_update)
@@ -253,7 +254,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         }
         reward_out = __double2float_rn(reward / (double)nm);                  // :337-341
         ++n_steps; EL(c, total, 1, 0) = total + 1;
-        t_update_and_advance<TW>(c, st, now, pending, flags, node_of, &tr, movers, arrival);    // worker.py:74-76, then :85 / :45-51 while nobody is pending
+        t_update_and_advance<TW>(c, st, now, pending, flags, node_of, tr, movers, arrival);    // worker.py:74-76, then :85 / :45-51 while nobody is pending
         if (flags & ENV_DONE) { leader = -1; group = 0; }                     // episode accounting / restart: k_episode
         else {
             group = f_current_group(c, node_of, pending);                     // task_env.py:291-298
@@ -286,16 +287,22 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
 }
 
 // per-thread scratch of the fused step: [SCR_TMP][64] staging doubles, [A][64] next_decision, [ANB/4][64] node-id words
-__host__ __device__ inline size_t step_smem_bytes(int A, int ANB) { return (size_t)STEP_THREADS * (8 * (size_t)(SCR_TMP + A) + (size_t)ANB); }
+// (the next_decision rows only for handles with A <= STEP_NDS_MAX_AGENTS: the scratch is carved from the L1 the step's sparse accesses
+// live on -- measured at 65,536 envs: 20A/50T 122.2 us with it / 123.0 without, 30A/100T 244.0 with / 230.9 without, profiles/r09_nds_scratch.txt)
+#define STEP_NDS_MAX_AGENTS 24
+__host__ __device__ inline size_t step_smem_bytes(int A, int ANB, bool nds) { return (size_t)STEP_THREADS * (8 * (size_t)(SCR_TMP + (nds ? A : 0)) + (size_t)ANB); }
 
 template <int TW>
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(const __grid_constant__ EnvArgs E, const __grid_constant__ StepArgs F) {
     extern __shared__ __align__(16) unsigned char step_smem[];
     const int b = blockIdx.x * STEP_THREADS + threadIdx.x;
     unsigned flags = 0;
+    // programmatic dependent launch: the observation kernel that follows in the stream may become resident (and run its prologue) as SM
+    // resources free up; it waits for this grid to complete (griddepcontrol.wait) before it touches the state
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (F.trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(F.trace, t); }
     double* const tmp = (double*)step_smem + threadIdx.x; double* const nds = tmp + SCR_TMP * STEP_THREADS;
-    if (b < E.S.B) flags = step_env<TW>(E, F, b, nds, (unsigned*)(nds - threadIdx.x + (size_t)STEP_THREADS * E.S.A) + threadIdx.x, tmp);
+    if (b < E.S.B) flags = step_env<TW>(E, F, b, nds, (unsigned*)(nds - threadIdx.x + (size_t)STEP_THREADS * (F.use_nds ? E.S.A : 0)) + threadIdx.x, tmp);
     if (F.elist) {                                                            // envs whose episode just ended: one warp-aggregated append per warp that has any
         const bool need = (flags & ENV_DONE) && !(flags & ENV_ACCOUNTED);
         const unsigned m = __ballot_sync(0xffffffffu, need), lane = threadIdx.x & 31u;
@@ -376,7 +383,7 @@ __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& 
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int i = lane + 32 * r; const bool in = i < A; const int ii = in ? i : 0;
-        a_nd_v[r] = in ? EL(c, a_nd, A, ii) : CUDART_NAN; const double2 ld = AREC2(c, ii);
+        a_nd_v[r] = in ? EL(c, a_nd, A, ii) : CUDART_NAN; const double2 ld = AREC2(c, ii, 1);
         a_last[r] = in ? ld.x : 0.0; a_dist[r] = ld.y; a_nab_v[r] = in ? (int)EL(c, a_nab, A, ii) : 0;
     }
     double acc0 = 0.0, acc1 = 0.0;
@@ -512,7 +519,7 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
         if (O->agent_obs) for (int k = lane; k < 6 * A; k += 32) O->agent_obs[(size_t)be * 6 * A + k] = 0.f;   // :165-180 nobody has a route
     }
     for (int i = lane; i < A; i += 32) {
-        AREC2(c, i) = make_double2(0.0, 0.0);
+        AREC2(c, i, 0) = make_double2(dx, dy); AREC2(c, i, 1) = make_double2(0.0, 0.0);
         EL(c, a_nd, A, i) = 0.0; ANODE(c, i) = DCM_NODE_DEPOT; EL(c, a_nab, A, i) = 0;
     }
     // ---- first slot (worker.py:45-51): every agent decides at t = 0 from the depot, nothing to update; one group
@@ -625,7 +632,7 @@ __device__ __forceinline__ void obs_unit(const EnvArgs& E, const ObsArgs& O, uns
     const unsigned valid = __ballot_sync(0xffffffffu, ok);
     if (!valid) return;
     double Lx = 0, Ly = 0;
-    if (ok) node_xy(c, ANODE(c, leader), Lx, Ly);                             // the leader's location = the coordinate of the node it stands at
+    if (ok) { const double2 p = AREC2(c, leader, 0); Lx = p.x; Ly = p.y; }
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK;
     if (chunk < NA) {                                                         // ---- agent rows (:165-180)
         if (!O.agent_obs) return;
@@ -636,16 +643,15 @@ __device__ __forceinline__ void obs_unit(const EnvArgs& E, const ObsArgs& O, uns
 #pragma unroll
             for (int w = 0; w < TW; ++w) feas[w] = EL(c, m_feas, TW, w);
             const u64 route = EL(c, am_route, 1, 0), depot = EL(c, am_depot, 1, 0), assigned = EL(c, am_assigned, 1, 0), watch = EL(c, am_watch, 1, 0);
-            const double now = EL(c, now, 1, 0), dpx = EL(c, s_dep, 2, 0), dpy = EL(c, s_dep, 2, 1);
+            const double now = EL(c, now, 1, 0);
 #pragma unroll
-            for (int h = 0; h < OBS_AGENTS_PER_CHUNK; h += 5) {               // five agents per batch: records and node ids, then one gather level
+            for (int h = 0; h < OBS_AGENTS_PER_CHUNK; h += 5) {               // five agents per batch: 15 + 10 loads in flight
                 double2 xy[5], ld[5], ti[5]; double du[5]; unsigned kk[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); ld[q] = AREC2(c, i); kk[q] = ANODE(c, i); }
+                for (int q = 0; q < 5; ++q) { const int i = c0 + (h + q < na ? h + q : 0); xy[q] = AREC2(c, i, 0); ld[q] = AREC2(c, i, 1); kk[q] = ANODE(c, i); }
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {                                   // what the node says: its coordinate = the agent's location; the task's times
+                for (int q = 0; q < 5; ++q) {                                   // one gather per agent that stands at a task, none otherwise
                     const bool at_task = kk[q] != DCM_NODE_DEPOT; const unsigned k = at_task ? kk[q] : 0u; const bool fe = at_task && tbit<TW>(feas, (int)k);
-                    xy[q] = at_task ? make_double2(EL(c, s_tx, T, k), EL(c, s_ty, T, k)) : make_double2(dpx, dpy);
                     ti[q] = fe ? TINFO2(c, k) : make_double2(0.0, 0.0); du[q] = (at_task && !fe) ? EL(c, s_dur, T, k) : 0.0;
                 }
 #pragma unroll
@@ -741,14 +747,12 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(const __grid_constant__ Env
 // fit twice in an SM's shared memory use k_obs.
 // ---------------------------------------------------------------------------------------------------------------
 #define OBS_TILE_MAX_WARPS 8
-struct ObsTileSmem { unsigned oA, oT, oM, iX, iY, iR, iO, iS, iQ, iN, bar, total; };
+struct ObsTileSmem { unsigned oA, oT, oM, iX, iY, iR, iO, iS, iQ, bar, total; };
 __host__ __device__ inline ObsTileSmem obs_tile_smem(int A, int T) {
-    const unsigned ANB = A <= 32 ? 32u : 64u;
     ObsTileSmem L; unsigned o = 0;
     auto take = [&](unsigned bytes) { const unsigned at = o; o += (bytes + 15u) & ~15u; return at; };
     L.oA = take(32u * 6 * A * 4); L.oT = take(32u * 5 * (T + 1) * 4); L.oM = take(32u * (T + 1));
-    L.iX = take(256u * T); L.iY = take(256u * T); L.iR = take(512u * A); L.iO = take(512u * A); L.iS = take(32u * T); L.iQ = take(32u * T);
-    L.iN = take(32u * ANB);
+    L.iX = take(256u * T); L.iY = take(256u * T); L.iR = take(1024u * A); L.iO = take(512u * A); L.iS = take(32u * T); L.iQ = take(32u * T);
     L.bar = take(8); L.total = o;
     return L;
 }
@@ -778,17 +782,15 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
     const double* iX = (const double*)(obs_smem + L.iX); const double* iY = (const double*)(obs_smem + L.iY);
     const double2* iR = (const double2*)(obs_smem + L.iR); const double2* iO = (const double2*)(obs_smem + L.iO);
     const signed char* iS = (const signed char*)(obs_smem + L.iS); const unsigned char* iQ = obs_smem + L.iQ;
-    const unsigned char* iN = obs_smem + L.iN; const unsigned ANB = (unsigned)E.S.ANB;      // node ids, [ANB/4 words][32 lanes][4]
     const unsigned bar = smem_u32(obs_smem + L.bar);
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
     const unsigned nA = 6u * A, nT = 5u * (T + 1), nM = (unsigned)(T + 1);
     auto clock_ns = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     auto issue_loads = [&](unsigned tile) {                                   // thread 0: the tile's rows, one contiguous span per array
         const TC c0 = make_tc(E, (int)(tile * 32));                           // lane 0 of the tile
-        const unsigned bytes = 256u * T * 2 + 512u * A + 512u * A + 32u * T * 2 + 32u * ANB;
+        const unsigned bytes = 256u * T * 2 + 1024u * A + 512u * A + 32u * T * 2;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        bulk_load(obs_smem + L.iR, &AREC2(c0, 0), 512u * A, bar);
-        bulk_load(obs_smem + L.iN, &ANODE(c0, 0), 32u * ANB, bar);
+        bulk_load(obs_smem + L.iR, &AREC2(c0, 0, 0), 1024u * A, bar);
         bulk_load(obs_smem + L.iO, &AOBS2(c0, 0), 512u * A, bar);
         bulk_load(obs_smem + L.iX, &EL(c0, s_tx, T, 0), 256u * T, bar);
         bulk_load(obs_smem + L.iY, &EL(c0, s_ty, T, 0), 256u * T, bar);
@@ -800,6 +802,7 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");                        // the step kernel's writes are complete and visible (no-op without a programmatic launch)
     if (threadIdx.x == 0 && blockIdx.x < NT) issue_loads(blockIdx.x);
     // The block walks tiles blockIdx.x, + gridDim.x, ...  Default grid: one block per tile (a single trip).  With two persistent
     // blocks per SM (DCM_OBS_PERSISTENT=1) the inputs of tile i + 1 land while the TMA engine still reads the staged output of
@@ -816,20 +819,12 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
         int leader = -1; unsigned ended = 0;
         if (b < B) { leader = O.leader ? O.leader[b] : EL(c, leader, 1, 0); if (O.skip_ended) ended = EL(c, ended, 1, 0); }
         u64 open[TW]; u64 route = 0, depot = 0, assigned = 0, watch = 0; double now = 0.0, dpx = 0.0, dpy = 0.0; float dq[OBS_ROWS_PER_CHUNK];
-        auto agent_scalars = [&]() {
-            route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); watch = EL(c, am_watch, 1, 0); now = EL(c, now, 1, 0);
-            dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1);
-        };
-        // an agent's location is the coordinate of the node it stands at (the staged task coordinates, or the depot)
-        auto node_pos = [&](unsigned i) -> double2 {
-            const unsigned k = iN[((((i >> 2) << 5) + lane) << 2) + (i & 3u)];
-            return k == DCM_NODE_DEPOT ? make_double2(dpx, dpy) : make_double2(iX[(k << 5) + lane], iY[(k << 5) + lane]);
-        };
+        auto agent_scalars = [&]() { route = EL(c, am_route, 1, 0); depot = EL(c, am_depot, 1, 0); assigned = EL(c, am_assigned, 1, 0); watch = EL(c, am_watch, 1, 0); now = EL(c, now, 1, 0); };
         auto task_scalars = [&](int chunk) {
             const int r0 = (chunk - NA) * OBS_ROWS_PER_CHUNK;
 #pragma unroll
             for (int w = 0; w < TW; ++w) open[w] = EL(c, m_open, TW, w);
-            dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1);
+            if (r0 == 0 || O.skip_ended == 2) { dpx = EL(c, s_dep, 2, 0); dpy = EL(c, s_dep, 2, 1); }
 #pragma unroll
             for (int q = 0; q < OBS_ROWS_PER_CHUNK; ++q) { const int jj = r0 + q; dq[q] = EL(c, s_dur32, T, (jj > 0 && jj <= T) ? jj - 1 : 0); }
         };
@@ -853,17 +848,17 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
                 if (!ok) continue;
                 const int c0 = chunk * OBS_AGENTS_PER_CHUNK;
                 const int na = A - c0 < OBS_AGENTS_PER_CHUNK ? A - c0 : OBS_AGENTS_PER_CHUNK;
-                const double2 Lp = node_pos((unsigned)leader);
+                const double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
                 float* mine = sA + lane * 6 * A + 6 * c0;
 #pragma unroll 5
                 for (int q = 0; q < na; ++q) {
                     const int i = c0 + q; const u64 bit = 1ull << i; const unsigned at = ((unsigned)i << 5) + lane;
                     double travel_t = 0.0, wait = 0.0, remain = 0.0;
                     if (fresh) { float2* r = (float2*)(mine + 6 * q); r[0] = r[1] = r[2] = make_float2(0.f, 0.f); continue; }
-                    const double2 xy = node_pos((unsigned)i);
+                    const double2 xy = iR[at << 1];
                     const double2 tt = iO[at];                                // {time_start or 0 (Q6), fl(time_start + time)}
                     if ((route & bit) && !(depot & bit)) {                    // :168
-                        const double arr = iR[at].x;
+                        const double arr = iR[(at << 1) + 1].x;
                         const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;                         // :169
                         if (now <= tt.x) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }     // :170
                         if (now >= tt.x) { const double qv = tt.y - now; remain = qv < 0.0 ? 0.0 : qv; }  // :171
@@ -883,8 +878,8 @@ __global__ void __launch_bounds__(32 * OBS_TILE_MAX_WARPS, 3) k_obs_tile(const _
             bool any_open = false;
 #pragma unroll
             for (int w = 0; w < TW; ++w) any_open = any_open || open[w] != 0;
-            double2 Lp = fresh ? make_double2(dpx, dpy) : node_pos((unsigned)leader);
-            if (fresh) any_open = true;                                       // everybody stands at the depot, every task is open
+            double2 Lp = iR[(((unsigned)leader << 5) + lane) << 1];
+            if (fresh) { Lp = make_double2(dpx, dpy); any_open = true; }       // everybody stands at the depot, every task is open
             float* mine = sT + lane * 5 * (T + 1) + 5 * r0;
             unsigned char* mm = sM + lane * (T + 1) + r0;
 #pragma unroll
@@ -962,7 +957,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant
         for (int i = 0; i < c.A; ++i) out[i] = -1;
         u64 rest = G.deciders_in[b]; int rank = 0;
         while (rest) {
-            const u64 g = t_current_group(c, rest, NodeFromMemory{c});
+            const u64 g = t_current_group(c, rest);
             for (u64 m = g; m; m &= m - 1) out[__ffsll((long long)m) - 1] = (signed char)rank;
             rest &= ~g; ++rank;
         }
@@ -986,8 +981,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_granular(const __grid_constant
             for (int k = 0; k < n; ++k) {
                 const int i = G.members[(size_t)b * G.mstride + k];
                 if (i < 0 || i >= c.A) { flags |= ENV_ERR_ACTION; continue; }
-                double ax, ay; node_xy(c, ANODE(c, i), ax, ay);
-                double d, tt; travel(c, ax, ay, tx, ty, d, tt);
+                double d, tt; travel(c, AREC(c, i, AR_X), AREC(c, i, AR_Y), tx, ty, d, tt);
                 t_agent_step(c, st, now, i, action, tx, ty, d, tt, flags);
                 reward += -tt;                                                // task_env.py:337-339
             }
@@ -1040,8 +1034,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_routes(const __grid_constant__
             if (p < len) { act = routes[((size_t)b * c.A + a) * rstride + p]; pos[a] = (unsigned char)(p + 1); }
             if (act < 0 || act > c.T) { flags |= ENV_ERR_ACTION; act = 0; }
             double tx, ty; node_xy(c, act == 0 ? DCM_NODE_DEPOT : (unsigned)(act - 1), tx, ty);
-            double ax, ay; node_xy(c, ANODE(c, a), ax, ay);
-            double dd, tt; travel(c, ax, ay, tx, ty, dd, tt);
+            double dd, tt; travel(c, AREC(c, a, AR_X), AREC(c, a, AR_Y), tx, ty, dd, tt);
             t_agent_step(c, st, now, a, act, tx, ty, dd, tt, flags);          // :585 agent_step
             t_task_update(c, st, now, nullptr); t_agent_update(c, st, now, st.route);   // :586-587
             ++n_steps;
@@ -1166,7 +1159,8 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
     }
     for (int i = 0; i < A; ++i) {
         const unsigned node = (r + L.o_anode)[i]; const unsigned af = (r + L.o_aflags)[i]; const u64 bit = 1ull << i;
-        AREC2(c, i) = make_double2(((const double*)(r + L.o_alast))[i], ((const double*)(r + L.o_adist))[i]);
+        double x, y; node_xy(c, node, x, y);
+        AREC2(c, i, 0) = make_double2(x, y); AREC2(c, i, 1) = make_double2(((const double*)(r + L.o_alast))[i], ((const double*)(r + L.o_adist))[i]);
         EL(c, a_nd, A, i) = ((const double*)(r + L.o_and))[i];
         EL(c, a_nab, A, i) = ((const unsigned short*)(r + L.o_anab))[i]; ANODE(c, i) = (unsigned char)node;
         if (node != DCM_NODE_DEPOT) {                                         // observation cache (AOBS2)
@@ -1236,7 +1230,7 @@ struct dcm_env {
     bool obs_ready, obs_tile, obs_resets;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs); it also writes restarted envs' observations
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
     // DCM_* experiment switches, read ONCE in dcm_create (never on the step path)
-    bool sw_obs_reset_by_episode, sw_obs_chunked, sw_episode_carveout_default; int epi_warps, epi_per_sm;
+    bool sw_obs_reset_by_episode, sw_obs_chunked, sw_episode_carveout_default, sw_step_no_nds, sw_no_pdl; int epi_warps, epi_per_sm;
     // dcm_step_host runs on its own stream: it must start after the asynchronous work earlier calls queued on the CALLER's stream
     cudaStream_t last_stream; bool last_pending; cudaEvent_t ev_order;
     uint64_t launches;
@@ -1283,7 +1277,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     size_t off = 0;
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(K, elem) + 255) / 256 * 256; return o; };
     const int MCB = 8; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
-    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 16), o_a_obs = carve(A, 16),
+    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32), o_a_obs = carve(A, 16),
                  o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
                  o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dur32 = carve(T, 4), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
                  o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
@@ -1313,7 +1307,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     {   // every other experiment switch, once per handle
         auto on = [](const char* name) { const char* g = getenv(name); return g && g[0] == '1'; };
         v->sw_obs_reset_by_episode = on("DCM_OBS_RESET_BY_EPISODE"); v->obs_persistent = on("DCM_OBS_PERSISTENT");   // persistent: measured slower than one block per tile, DESIGN.md section 4
-        v->sw_obs_chunked = on("DCM_OBS_CHUNKED"); v->sw_episode_carveout_default = on("DCM_EPISODE_CARVEOUT_DEFAULT");
+        v->sw_obs_chunked = on("DCM_OBS_CHUNKED"); v->sw_episode_carveout_default = on("DCM_EPISODE_CARVEOUT_DEFAULT"); v->sw_step_no_nds = on("DCM_STEP_NO_NDS"); v->sw_no_pdl = on("DCM_NO_PDL");
         v->epi_warps = 2; { const char* gw = getenv("DCM_EPISODE_WARPS"); if (gw && atoi(gw) >= 1 && atoi(gw) <= EPI_LIST_MAX_WARPS) v->epi_warps = atoi(gw); }   // envs (warps) per block
         v->epi_per_sm = 8; { const char* gg = getenv("DCM_EPISODE_GRID"); if (gg && atoi(gg) > 0) v->epi_per_sm = atoi(gg); }                                  // warps per SM
     }
@@ -1422,7 +1416,7 @@ int dcm_get_instances(dcm_env* v, double* task_xy, double* depot_xy, int32_t* re
 }
 
 // the step path's observation builder: k_obs_tile when two tiles fit in an SM's shared memory, else (or with DCM_OBS_CHUNKED=1) k_obs
-static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
+static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s, bool programmatic = false) {
     const int A = v->E.S.A, T = v->E.S.T;
     const int NA = (A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
     const int warps = NA + NR < OBS_TILE_MAX_WARPS ? NA + NR : OBS_TILE_MAX_WARPS;
@@ -1430,9 +1424,15 @@ static int launch_obs_tile(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
     const int use_bulk = (((uintptr_t)O.agent_obs | (uintptr_t)O.task_obs | (uintptr_t)O.mask) & 15u) == 0;
     int grid = v->E.S.NT;                                                    // one block per tile (DCM_OBS_PERSISTENT=1: two persistent blocks per SM walk the tiles)
     if (v->obs_persistent && grid > 2 * v->sm_count) grid = 2 * v->sm_count;
-    if (v->E.S.TW == 1) k_obs_tile<1><<<grid, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
-    else if (v->E.S.TW == 2) k_obs_tile<2><<<grid, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
-    else k_obs_tile<4><<<grid, 32 * warps, smem, s>>>(v->E, O, use_bulk, v->d_trace);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * warps); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr; memset(&attr, 0, sizeof attr);
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
+    if (programmatic && !v->sw_no_pdl) { cfg.attrs = &attr; cfg.numAttrs = 1; }   // after k_step in dcm_step: resident early, waits in griddepcontrol.wait
+    unsigned long long* trace = v->d_trace;
+    if (v->E.S.TW == 1) CK(cudaLaunchKernelEx(&cfg, k_obs_tile<1>, v->E, O, use_bulk, trace));
+    else if (v->E.S.TW == 2) CK(cudaLaunchKernelEx(&cfg, k_obs_tile<2>, v->E, O, use_bulk, trace));
+    else CK(cudaLaunchKernelEx(&cfg, k_obs_tile<4>, v->E, O, use_bulk, trace));
     CK(cudaGetLastError());
     v->launches++;
     return DCM_OK;
@@ -1465,9 +1465,9 @@ static int prepare_obs(dcm_env* v) {
     return DCM_OK;
 }
 
-static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s) {
+static int launch_obs(dcm_env* v, const ObsArgs& O, cudaStream_t s, bool programmatic = false) {
     { const int rc = prepare_obs(v); if (rc) return rc; }
-    if (v->obs_tile) return launch_obs_tile(v, O, s);
+    if (v->obs_tile) return launch_obs_tile(v, O, s, programmatic);
     const int tiles_per_block = OBS_THREADS / 32;
     const int NA = (v->E.S.A + OBS_AGENTS_PER_CHUNK - 1) / OBS_AGENTS_PER_CHUNK, NR = (v->E.S.T + 1 + OBS_ROWS_PER_CHUNK - 1) / OBS_ROWS_PER_CHUNK;
     const dim3 grid((v->E.S.NT + tiles_per_block - 1) / tiles_per_block, NA + NR);
@@ -1540,7 +1540,8 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
         CK(cudaMemsetAsync(F.trace, 0xff, sizeof(unsigned long long), s)); CK(cudaMemsetAsync(F.trace + 1, 0, sizeof(unsigned long long), s));
     }
     {
-        const int grid = grid_env(v, STEP_THREADS); const size_t smem = step_smem_bytes(v->E.S.A, v->E.S.ANB);
+        F.use_nds = v->E.S.A <= STEP_NDS_MAX_AGENTS && !v->sw_step_no_nds;
+        const int grid = grid_env(v, STEP_THREADS); const size_t smem = step_smem_bytes(v->E.S.A, v->E.S.ANB, F.use_nds != 0);
         if (v->E.S.TW == 1) k_step<1><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
         else if (v->E.S.TW == 2) k_step<2><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
         else k_step<4><<<grid, STEP_THREADS, smem, s>>>(v->E, F);
@@ -1570,7 +1571,7 @@ int dcm_step(dcm_env* v, const int32_t* action, const int32_t* followers, int fs
     int rc = use_list ? launch_episode_list(v, P, ecount, v->side) : launch_episode(v, P, v->side);
     if (rc) return rc;
     CK(cudaEventRecord(v->ev_join, v->side));
-    rc = launch_obs(v, O, s);
+    rc = launch_obs(v, O, s, true);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(s, v->ev_join, 0));
     return DCM_OK;

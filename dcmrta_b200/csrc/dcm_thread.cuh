@@ -55,11 +55,13 @@ struct TC {
 #define SARR(c, j, sl) (TB(c, t_slot_arr)[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
 #define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * 8u + (unsigned)(sl)])                        // member id of slot s (8 id bytes per task and lane)
 #define TINFO(c, j, k) (TB(c, t_info)[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
-// agent record {arrival_time[-1], travel_dist}.  An agent's location is not stored: it is always the coordinate of the node it stands
-// at (task_env.py:93, :134, :320), so whoever needs it looks the node up (node_xy / the observation kernels' staged task coordinates)
-#define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 1) + (f)])
-enum { AR_LAST = 0, AR_DIST = 1 };
-#define AREC2(c, i) (((double2*)TB(c, a_rec))[LANE_ROW(c, (c).A, i)])                                     // {last, dist}
+// agent record {x, y, arrival_time[-1], travel_dist}: one 32-byte sector.  The location is always the coordinate of the node the agent
+// stands at (task_env.py:93, :134, :320) and could be looked up there; it is STORED because the observation kernels then read it with
+// the record instead of through a dependent node -> coordinate gather (measured: without it k_obs_tile 51 -> 54 us, the chunked k_obs
+// of the large shapes 122 -> 163 us at 30A/100T; profiles/r09_xy_by_node.txt)
+#define AREC(c, i, f) (TB(c, a_rec)[(LANE_ROW(c, (c).A, i) << 2) + (f)])
+enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
+#define AREC2(c, i, h) (((double2*)TB(c, a_rec))[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
 #define AOBS2(c, i) (((double2*)TB(c, a_obs))[LANE_ROW(c, (c).A, i)])                                    // observation cache, see dcm_soa.h
 #define TINFO2(c, j) (((double2*)TB(c, t_info))[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
 // route[-1] of the agents of one env, one byte each, four agents per 32-bit word, words row-major [ANB/4][32 lanes]: a warp reads word k of
@@ -260,15 +262,15 @@ template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c,
 // `expect_removal`: the caller already knows that the earliest member gives up (the waiting-coalition scan), so the member slots are
 // loaded together with the head instead of one round trip later.  Returns the earliest member arrival of the task afterwards, +inf when
 // it no longer waits (feasible, or empty) -- the caller keeps the per-env bound St::xamin exact with it.
-template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of, TaskR* pre = nullptr,
-                                                                        bool expect_removal = false) {
+template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of, TaskR& pre,
+                                                                        bool use_pre, bool expect_removal = false) {
     const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
     TaskR r;
     bool have_slots = false;
     auto stage_slots = [&]() { for (int s = 0; s < c.MC; ++s) cp_async8(&TMPV(c, s), &SARR(c, j, s)); have_slots = true; };   // slots past the count hold stale values that are never used
-    if (pre && pre->j == j) r = *pre;
+    use_pre = use_pre && pre.j == j;                                          // (`pre` is a reference to a local of the caller, never a selected pointer: it must stay in registers)
+    if (use_pre) r = pre;
     else {
-        pre = nullptr;
         if (expect_removal) stage_slots();
         r.n = EL(c, t_nmem, T, j); r.status = (int)EL(c, t_status, T, j); r.req = (int)EL(c, s_req, T, j);      // :250
         r.ids = *(const u64*)&SMEM(c, j, 0); r.dur = EL(c, s_dur, T, j);
@@ -294,7 +296,7 @@ template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const 
                 const unsigned m = idb(s);
                 if (node_of((int)m) == (unsigned)j) st.touched |= 1ull << m;
             }
-            if (pre) { pre->feas = true; pre->ts = mx; pre->tf = tf; }
+            if (use_pre) { pre.feas = true; pre.ts = mx; pre.tf = tf; }
             amin_after = CUDART_INF;
         } else removal = true;
     } else removal = now - r.amin >= c.W;                                     // :269 for the earliest member (Q1: false when fl(arr+W) rounded down)
@@ -341,7 +343,7 @@ template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const 
 // task_update call examines them, :272 is the else-branch) and states that did not come from the fused protocol
 // (dcm_import_state, granular calls) until their first slot start; a slot without deciders runs the full scan.
 template <int TW, class NF> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly, const NF& node_of,
-                                                                        bool slot_start = false, u64 dec = 0, TaskR* pre = nullptr) {
+                                                                        bool slot_start, u64 dec, TaskR& pre, bool use_pre) {
     const int T = c.T;
     // ---- load-only pass: which tasks need a full evaluation, which feasible tasks have finished.  Both scans are skipped
     //      while the clock has not reached the per-env lower bounds (fl(now - x) >= W and now >= x are monotone in x).
@@ -398,7 +400,7 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
 #pragma unroll
     for (int w = 0; w < TW; ++w)
         for (u64 mm = hot[w]; mm; mm &= mm - 1) {
-            const double am = t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of, pre, (expired[w] & mm & (0 - mm)) != 0);
+            const double am = t_eval_task<TW>(c, st, now, 64 * w + ctz64(mm), newly, node_of, pre, use_pre, (expired[w] & mm & (0 - mm)) != 0);
             new_amin = am < new_amin ? am : new_amin;
         }
     // After a scan the bound is EXACT again, evaluated tasks included: the next call at the same clock does not scan unless a member
@@ -421,7 +423,8 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
 }
 
 template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<TW>& st, double now, unsigned char* newly) {
-    t_task_update<TW>(c, st, now, newly, NodeFromMemory{c});
+    TaskR none;
+    t_task_update<TW>(c, st, now, newly, NodeFromMemory{c}, false, 0, none, false);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -434,7 +437,7 @@ template <int TW> __device__ __forceinline__ void t_task_update(const TC& c, St<
 // just joined -- with `movers` = the agents that moved in this decision, all arriving at `arrival`.  Agents that stand at that task,
 // and agents at the depot, are then updated without touching memory; the others take the general path (loads batched by four).
 template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which, const NF& node_of,
-                                                                         const TaskR* known = nullptr, u64 movers = 0, double arrival = 0.0) {
+                                                                         const TaskR& known, bool use_known, u64 movers, double arrival) {
     const int A = c.A;
     // `assigned` of a member of a feasible task that has not started yet (:232-233) turns true at the first call with now >= time_start.
     // Nothing in the step reads it before the agent moves again, so that moment is not looked for: the agent keeps its WATCH bit and
@@ -450,12 +453,12 @@ template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const
     for (u64 q = which & st.route; q; q &= q - 1) {                           // first the agents that need nothing from memory
         const u64 bit = q & (0 - q); const int i = ctz64(q);
         if (st.depot & bit) { st.watch &= ~bit; set_nd(c, i, CUDART_NAN); continue; }          // :212, :226
-        if (!known || known->j < 0 || node_of(i) != (unsigned)known->j) { rest |= bit; continue; }
-        const bool fj = tbit<TW>(st.feas, known->j);
+        if (!use_known || known.j < 0 || node_of(i) != (unsigned)known.j) { rest |= bit; continue; }
+        const bool fj = tbit<TW>(st.feas, known.j);
         const bool fm = fj && (st.member & bit);
-        if ((fj && !known->feas) || (!fm && !(movers & bit))) { rest |= bit; continue; }   // {time_start, time_finish} / its last arrival are in memory
+        if ((fj && !known.feas) || (!fm && !(movers & bit))) { rest |= bit; continue; }   // {time_start, time_finish} / its last arrival are in memory
         st.watch &= ~bit;
-        if (fm) member_of_feasible(bit, i, known->ts, known->tf);
+        if (fm) member_of_feasible(bit, i, known.ts, known.tf);
         else { set_nd(c, i, arrival + c.W); st.assigned &= ~bit; }            // :235 / :238
     }
     // general path, five agents per trip: {time_start, time_finish} of the task each stands at and its last arrival, then the stores
@@ -479,7 +482,8 @@ template <int TW, class NF> __device__ __forceinline__ void t_agent_update(const
 }
 
 template <int TW> __device__ __forceinline__ void t_agent_update(const TC& c, St<TW>& st, double now, u64 which) {
-    t_agent_update<TW>(c, st, now, which, NodeFromMemory{c});
+    TaskR none;
+    t_agent_update<TW>(c, st, now, which, NodeFromMemory{c}, none, false, 0ull, 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -529,14 +533,12 @@ template <int TW> __device__ __forceinline__ bool t_all_returned_and_finished(co
 // lexicographically smallest location (np.unique(axis=0) order).  Pending agents never move while they are pending,
 // so re-evaluating this after every decision walks the groups in the reference order.
 // ---------------------------------------------------------------------------------------------------------------
-template <class NF> __device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending, const NF& node_of) {
+__device__ __forceinline__ u64 t_current_group(const TC& c, u64 pending) {
     if ((pending & (pending - 1)) == 0) return pending;                       // zero or one decider
     double bx = CUDART_INF, by = CUDART_INF; u64 g = 0;
-    for (u64 m = pending; m; m &= m - 1) {                                    // one dependent lookup per decider: the coordinate of the node it stands at
-        const u64 bit = m & (0 - m);
-        double x, y; node_xy(c, node_of(ctz64(m)), x, y);                     // (an agent that never moved has node = depot)
-        if (lex_less(x, y, bx, by)) { bx = x; by = y; g = bit; } else if (x == bx && y == by) g |= bit;
-    }
+    for_bits4<double2>(pending, 0, [&](int i) { return AREC2(c, i, 0); }, [&](u64 bit, int, double2 p) {
+        if (lex_less(p.x, p.y, bx, by)) { bx = p.x; by = p.y; g = bit; } else if (p.x == bx && p.y == by) g |= bit;
+    });
     return g;
 }
 
@@ -548,7 +550,7 @@ template <class NF> __device__ __forceinline__ u64 f_current_group(const TC& c, 
     const unsigned first = node_of(ctz64(pending));
     bool same = true;
     for (u64 m = pending & (pending - 1); m; m &= m - 1) same = same && node_of(ctz64(m)) == first;
-    return same ? pending : t_current_group(c, pending, node_of);
+    return same ? pending : t_current_group(c, pending);
 }
 
 
@@ -568,7 +570,7 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
     const int j = action - 1;
     const bool to_task = action != 0, feas = to_task && tbit<TW>(st.feas, j), nonempty = to_task && tbit<TW>(st.ne, j);
     // ---- every load first (nothing below can be hoisted above a byte store by the compiler)
-    const double2 ld = AREC2(c, i);                                           // {last arrival, travel_dist}
+    const double2 ld = AREC2(c, i, 1);                                        // {last arrival, travel_dist}
     if (st.watch & bit) {                                                     // leaving a feasible task it was waiting to start: settle `assigned` (lazy, see t_agent_update)
         if (now >= EL(c, a_ts, c.A, i)) st.assigned |= bit;
         st.watch &= ~bit;
@@ -582,7 +584,8 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
         if (!feas) { const double2 mm = TINFO2(c, j); amin = mm.x; amax = mm.y; }   // {earliest, latest} member arrival of a waiting coalition
     }
     const double arrival = now + tt;                                          // :318
-    AREC2(c, i) = make_double2(arrival, ld.y + d);                            // :317-318 (:320 location = the node's coordinate, not stored)
+    AREC2(c, i, 1) = make_double2(arrival, ld.y + d);                         // :317-318
+    AREC2(c, i, 0) = make_double2(tx, ty);                                    // :320
     ANODE(c, i) = (unsigned char)(to_task ? (unsigned)j : DCM_NODE_DEPOT);   // :314
     st.route |= bit; st.touched |= bit;
     st.xlast = arrival > st.xlast ? arrival : st.xlast;
@@ -612,13 +615,13 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
 // ---------------------------------------------------------------------------------------------------------------
 // built-in policies, evaluated on the state the observation shows
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ int t_policy_action(const TC& c, const St<TW>& st, unsigned node_of_leader, int policy, unsigned word) {
+template <int TW> __device__ __forceinline__ int t_policy_action(const TC& c, const St<TW>& st, int leader, int policy, unsigned word) {
     int n_open = 0;
 #pragma unroll
     for (int w = 0; w < TW; ++w) n_open += __popcll(st.open[w]);
     if (n_open == 0) return 0;                                                // only the depot is unmasked
     if (policy == 2) {                                                        // greedy nearest (fp64 squared distance, lowest id on ties)
-        double Lx, Ly; node_xy(c, node_of_leader, Lx, Ly);
+        const double Lx = AREC(c, leader, AR_X), Ly = AREC(c, leader, AR_Y);
         double bd = CUDART_INF; int bj = -1;
 #pragma unroll
         for (int w = 0; w < TW; ++w) for (u64 mm = st.open[w]; mm; mm &= mm - 1) {
@@ -726,11 +729,11 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
 // `arrival`), every later trip a slot start.  (Two inlined copies made the step kernel 146 kB of SASS; its warps were stalled on
 // instruction fetch 12 % of the time, profiles/r08c.)
 template <int TW, class NF> __device__ __forceinline__ void t_update_and_advance(const TC& c, St<TW>& st, double& now, u64& pending, unsigned& flags, const NF& node_of,
-                                                                                TaskR* pre, u64 movers, double arrival) {
+                                                                                TaskR& pre, u64 movers, double arrival) {
     int empty_slots = 0; bool slot = false; u64 dec = 0;
     for (;;) {
-        t_task_update<TW>(c, st, now, nullptr, node_of, slot, dec, slot ? nullptr : pre);                      // worker.py:74 / :50
-        t_agent_update<TW>(c, st, now, st.touched, node_of, slot ? nullptr : pre, slot ? 0ull : movers, arrival);   // worker.py:76 / :51
+        t_task_update<TW>(c, st, now, nullptr, node_of, slot, dec, pre, !slot);                                 // worker.py:74 / :50
+        t_agent_update<TW>(c, st, now, st.touched, node_of, pre, !slot, slot ? 0ull : movers, arrival);          // worker.py:76 / :51
         if (pending) return;
         // Nobody could decide in this slot.  One such slot is normal (it marks agents as returned); a second in a row means the
         // state can no longer change and the reference `while` (worker.py:45) would spin forever: stop and flag it.
@@ -753,9 +756,9 @@ template <int TW, class NF> __device__ __forceinline__ void t_update_and_advance
 template <int TW> __device__ __forceinline__ void obs_agent_row(const TC& c, const St<TW>& st, double now, double Lx, double Ly, int i, float* r) {
     const u64 bit = 1ull << i;
     double travel_t = 0.0, wait = 0.0, remain = 0.0;
-    const unsigned k = ANODE(c, i);
-    double ax, ay; node_xy(c, k, ax, ay);
+    const double ax = AREC(c, i, AR_X), ay = AREC(c, i, AR_Y);
     if ((st.route & bit) && !(st.depot & bit)) {                              // :168
+        const unsigned k = ANODE(c, i);
         const double arr = AREC(c, i, AR_LAST);
         const bool feas = tbit<TW>(st.feas, (int)k);
         const double ts = feas ? TINFO(c, k, 0) : 0.0;                        // time_start is 0 until the task is feasible (Q6)

@@ -27,3 +27,14 @@ if [ -n "$do_sweep" ]; then
 import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1A/$2T value %.4g us/pass %.1f frac %.3f' % (d['value'], d['roofline']['launch_us'], d['roofline']['frac']))"
   done
 fi
+if [ -n "$do_smoke" ]; then
+  ( time python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/${tag}_smoke.log 2>&1; tail -4 gpurun_out/${tag}_smoke.log
+fi
+if [ -n "$do_refarm" ]; then
+  timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2>/dev/null | tee gpurun_out/${tag}_bench_reference_arm.json | cut -c1-200
+fi
+if [ -n "$do_sanitize" ]; then bash tools/sanitize.sh $tag; fi
+if [ -n "$do_greedy" ]; then
+  timeout 300 python bench.py --policy greedy --steps 1000 --warmup 100 --no-cpu-baseline 2>/dev/null | tee gpurun_out/${tag}_bench_greedy.json | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('greedy: value %.4g us/pass %.1f frac %.3f e2e %.4g' % (d['value'], d['roofline']['launch_us'], d['roofline']['frac'], d['e2e']['value']))"
+fi

@@ -22,7 +22,7 @@ for shape in "10 20" "20 50" "30 100" "50 200"; do set -- $shape
 done
 if [ -n "$do_train" ]; then
   run --gpus $N --mode rollout --amp --iters 3 | tee -a gpurun_out/${tag}_config5.jsonl | show
-  run --gpus $N --mode rollout --iters 2 | tee -a gpurun_out/${tag}_config5.jsonl | show
-  run --gpus $N --mode train --amp --iters 2 | tee -a gpurun_out/${tag}_config5.jsonl | show
+  run --gpus $N --mode rollout --iters 1 | tee -a gpurun_out/${tag}_config5.jsonl | show
+  run --gpus $N --mode train --amp --iters 1 | tee -a gpurun_out/${tag}_config5.jsonl | show
 fi
 tail -5 gpurun_out/${tag}_err.log 2>/dev/null | cut -c1-300
