@@ -134,6 +134,18 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
+def python_reference_note():
+    """The Python reference cannot run on the GPU box (its tree does not travel): the factor between it and the C port was measured in the
+    build container by tools/time_python_reference.py and is quoted from the committed result."""
+    f = ROOT / "profiles" / "r09_python_reference_rate.json"
+    try:
+        d = json.load(open(f))
+        return (f"the Python reference itself: {d['python_reference_decisions_per_s']:.0f} decisions/s on 1 core in the build container, "
+                f"{d['port_over_python']:.0f}x slower than this port on the same core (tools/time_python_reference.py, {f.name})")
+    except Exception:
+        return "the Python reference ran 455-541 decisions/s/core in the build container (SURVEY.md 6)"
+
+
 def cpu_rollout(A, T, policy, seconds, threads=None, steps_per_thread=None):
     """All host cores, one env pool per thread (ctypes releases the GIL); returns (steps/s, cores, steps, elapsed)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -183,7 +195,7 @@ def run_reference(args):
                    "env_steps_timed": total, "threads": cores},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{total} decisions of the C oracle port (oracle/taskenv_oracle.c) over {cores} threads x 8 envs in {dt:.1f}s; "
-                                   f"1-thread rate {rate1:.0f}/s; the Python reference itself ran 455-541 decisions/s/core in the build container (SURVEY.md 6)"},
+                                   f"1-thread rate {rate1:.0f}/s; " + python_reference_note()},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -311,9 +323,12 @@ def run_ours(args):
             tj = json.load(open(tf))
             traffic = tj.get(f"{A}x{T}x{B}")
             if traffic is not None:
-                traffic_source = tj.get("source", "ncu --set full capture of one steady-state pass of this workload (profiles/), not of the timed passes")
+                traffic_source = tj.get("_source", "ncu --set full capture of one steady-state pass of this workload (profiles/), not of the timed passes")
         except Exception:
             traffic = None
+    dram = {}
+    if traffic is not None:                                          # the same pass against the bytes ncu counted: the honest distance to the HBM limit
+        dram = {"dram_achieved": traffic / per_launch_s / 1e9, "dram_frac": traffic / per_launch_s / 1e9 / peak}
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -334,14 +349,14 @@ def run_ours(args):
         "gpu_launches": launched, "env_steps_timed": total_steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                      "kernel": "one pass = k_step, then k_episode_list (priority side stream) beside k_obs_tile", "algorithmic_bytes_per_env_step": bytes_step, "units_per_launch": B, "peak_source": peak_src,
-                     "launch_us": per_launch_s * 1e6},
+                     "launch_us": per_launch_s * 1e6, **dram},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
         rate, cores, total, dt, rate1 = cpu_rollout(A, T, args.policy, args.cpu_seconds)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{total} decisions of the C oracle port over {cores} threads x 8 synthetic {A}A/{T}T envs in {dt:.1f}s "
-                                          f"(1 thread: {rate1:.0f}/s); the Python reference ran 455-541 decisions/s/core in the build container"}
+                                          f"(1 thread: {rate1:.0f}/s); " + python_reference_note()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
