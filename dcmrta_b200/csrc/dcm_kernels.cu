@@ -1,14 +1,18 @@
-// dcm_kernels.cu -- sm_100a kernels of the TaskEnv step and the C ABI of include/dcmrta.h  (v2: thread-per-env).
+// dcm_kernels.cu -- sm_100a kernels of the TaskEnv step and the C ABI of include/dcmrta.h  (thread-per-env, round 2).
 //
-// Kernels (one thread per env, 32 envs = one tile = one warp; state in tiled struct-of-arrays, see dcm_soa.h):
-//   k_step       dcm_reset / dcm_step: one leader decision per env per launch -- action application, coalition update,
-//                agent update, slot advance, episode accounting + auto-reset, leader choice                (hot path 1/2)
-//   k_obs        observation + mask builder: rows produced per env, transposed through a per-warp shared-memory tile,
-//                written with unit-stride stores straight into the policy's input tensors               (hot path 2/2)
-//   k_granular   the individual TaskEnv methods (facade path)
-//   k_routes     execute_by_route: a whole preset-route episode per env in one launch
-//   k_generate   synthetic instances (generate_env distributions) with Philox
-//   k_pack_static / k_unpack_static / k_export / k_import / k_init / k_sum_steps   plumbing
+// Kernels (state in tiled struct-of-arrays, 32 envs = one tile, see dcm_soa.h):
+//   k_step          dcm_step: one leader decision per env per launch, thread / env -- action application, coalition update, agent
+//                   update, slot advance, leader choice; two rounds of loads, the rest from registers and a per-thread shared-memory
+//                   scratch filled with cp.async (step_env)                                                          (hot path 1/3)
+//   k_episode_list  episode accounting + restart of the envs whose episode just ended, warp / env, beside k_obs_tile  (hot path 2/3)
+//   k_obs_tile      observation + mask builder, block / tile: TMA bulk loads of the tile's arrays, rows from shared memory, TMA bulk
+//                   stores straight into the policy's input tensors; launched programmatically after k_step           (hot path 3/3)
+//   k_obs           the same rows by register-staged chunks (granular dcm_build_obs, shapes whose tile does not fit twice per SM)
+//   k_episode       dcm_reset (and the dense variant of the episode pass)
+//   k_granular      the individual TaskEnv methods (facade path)
+//   k_routes        execute_by_route: a whole preset-route episode per env in one launch
+//   k_generate      synthetic instances (generate_env distributions) with Philox
+//   k_pack_static / k_unpack_static / k_export / k_import / k_init / k_sum_steps / k_sum_episodes   plumbing
 //
 // Build: nvcc -std=c++17 -O3 -fmad=false -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared
 #include <cuda_runtime.h>
