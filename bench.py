@@ -60,7 +60,7 @@ def parse():
                    help="env: the headline metric (step kernels only).  rollout / train: BASELINE configs[4], the same env-steps/s with the "
                         "PyTorch attention policy in the loop (rollout) and with the REINFORCE update + gradient all-reduce (train)")
     p.add_argument("--iters", type=int, default=3, help="--mode rollout/train: timed iterations (one episode per env each)")
-    p.add_argument("--amp", action="store_true", help="--mode rollout/train: bf16 autocast for the rollout forward passes")
+    p.add_argument("--amp", action="store_true", help="--mode rollout/train: the rollouts call a bf16 shadow copy of the policy (the update stays fp32)")
     p.add_argument("--eager", action="store_true", help="--mode rollout/train: eager decision loop instead of the CUDA-graph replay")
     return p.parse_args()
 

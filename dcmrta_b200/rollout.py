@@ -53,6 +53,27 @@ class BatchedRollout:
     def _slot(self, t):
         return t if self.record else t & 1
 
+    def _forward_net(self, net, amp):
+        """The module the decision loop calls.  amp: a bf16 SHADOW COPY of `net` (weights refreshed here, at the start of every run), fed
+        bf16 observations -- not autocast, which keeps LayerNorm in fp32 and casts around every op (14.0 ms per forward of 8,192 envs,
+        32 % of it LayerNorm; profiles/r09_policy_forward_profile.txt).  The update always runs on the fp32 network."""
+        if not amp:
+            return net
+        import copy
+        shadows = self.__dict__.setdefault("_shadows", {})           # one per network object (the trainer alternates policy and baseline)
+        if id(net) not in shadows:
+            shadows[id(net)] = copy.deepcopy(net).to(torch.bfloat16).eval()
+        shadow = shadows[id(net)]
+        with torch.no_grad():
+            torch._foreach_copy_(list(shadow.parameters()), list(net.parameters()))
+        return shadow
+
+    @staticmethod
+    def _logp(fnet, amp, tasks, agents, mask):
+        if amp:
+            return fnet(tasks.to(torch.bfloat16), agents.to(torch.bfloat16), mask).float()
+        return fnet(tasks, agents, mask)
+
     @torch.no_grad()
     def run(self, net, mode: str = "sample", generator: torch.Generator | None = None, amp: bool = False, replay: dict | None = None,
             keep_logp: bool = False) -> Episodes:
@@ -65,6 +86,7 @@ class BatchedRollout:
         assert not env.auto_reset, "rollouts use one episode per env: create the env with auto_reset=False"
         was_training = net.training
         net.eval()
+        fnet = self._forward_net(net, amp)
         s = self._slot(0)
         env.set_output_buffers(self.agent_obs[s], self.task_obs[s], self.mask[s])
         env.reset(leaders=replay["leader"][0] if replay else None)
@@ -73,8 +95,7 @@ class BatchedRollout:
         t = 0
         while t < horizon:
             s = self._slot(t)
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-                logp = net(self.task_obs[s], self.agent_obs[s], self.mask[s].view(torch.bool))
+            logp = self._logp(fnet, amp, self.task_obs[s], self.agent_obs[s], self.mask[s].view(torch.bool))
             if keep_logp:
                 logps.append(logp.float().clone())
             if replay is not None and "action" in replay:
@@ -140,8 +161,7 @@ class GraphedRollout(BatchedRollout):
     def _decision(self, net, mode, amp, s):
         env = self.env
         a, k, m = self.pp[s]
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            logp = net(k, a, m.view(torch.bool))
+        logp = self._logp(net, amp, k, a, m.view(torch.bool))
         act = sample_actions(logp.float()) if mode == "sample" else greedy_actions(logp)
         if self.record:
             self.agent_obs.index_copy_(0, self.t_dev, a.unsqueeze(0)); self.task_obs.index_copy_(0, self.t_dev, k.unsqueeze(0))
@@ -153,6 +173,8 @@ class GraphedRollout(BatchedRollout):
         self.t_dev.add_(1)
 
     def _graph(self, net, mode, amp):
+        """net: the module the loop calls (the bf16 shadow when amp); its parameters keep their addresses, so refreshing them between
+        replays is all an update of the policy needs."""
         key = (id(net), mode, bool(amp))
         if key not in self._graphs:
             env = self.env
@@ -180,7 +202,7 @@ class GraphedRollout(BatchedRollout):
         assert not env.auto_reset
         was_training = net.training
         net.eval()
-        g = self._graph(net, mode, amp)
+        g = self._graph(self._forward_net(net, amp), mode, amp)
         env.set_output_buffers(*self.pp[0])
         env.reset()
         self.t_dev.zero_()

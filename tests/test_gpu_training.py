@@ -273,3 +273,29 @@ def test_graphed_rollout_records_what_the_env_did():
     assert torch.equal(again.active.sum(0).double(), again.metrics[:, 7])
     assert not bool((again.mask.gather(2, again.action.long().unsqueeze(2)).squeeze(2).bool() & again.active).any())
     env.close(); env2.close()
+
+
+def test_bf16_shadow_rollout_follows_the_fp32_weights():
+    """amp=True: the decision loop calls a bf16 shadow copy of the network; the copy is refreshed from the fp32 weights at the start of every
+    run, so a rollout after an update plays the UPDATED policy (also through the CUDA graph, whose nodes keep the shadow's addresses)."""
+    from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.policy import AttentionNet
+    from dcmrta_b200.rollout import GraphedRollout
+    torch.manual_seed(0)
+    net = AttentionNet(6, 5, 32).cuda()
+    env = BatchedTaskEnv(128, 10, 20, auto_reset=False, seed=9)
+    env.generate()
+    ro = GraphedRollout(env, horizon=120, record=True, check_every=8, unroll=4)
+    a = ro.run(net, "greedy", amp=True)
+    assert bool(a.ended.all()) and not bool((a.mask.gather(2, a.action.long().unsqueeze(2)).squeeze(2).bool() & a.active).any())
+    lp32 = net(a.task_obs[0], a.agent_obs[0], a.mask[0].view(torch.bool))
+    agree = (lp32.argmax(1).int() == a.action[0]).float().mean()
+    assert agree > 0.9                                           # bf16 argmax vs fp32 argmax: the same policy up to rounding
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.5)                    # "an update"
+    b = ro.run(net, "greedy", amp=True)
+    lp32b = net(b.task_obs[0], b.agent_obs[0], b.mask[0].view(torch.bool))
+    assert (lp32b.argmax(1).int() == b.action[0]).float().mean() > 0.9      # the shadow follows the new weights ...
+    assert (lp32.argmax(1).int() == b.action[0]).float().mean() < 0.9       # ... not the old ones
+    env.close()
