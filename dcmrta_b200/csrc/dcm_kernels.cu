@@ -75,6 +75,13 @@ __device__ __forceinline__ TC make_tc(const EnvArgs& E, int b) {
     return TC{E.S, (unsigned)b >> 5, (unsigned)b & 31u, (size_t)((unsigned)b >> 5) * E.S.tile_stride, E.S.A, E.S.T, E.S.MC, E.W, E.vel, E.max_time};
 }
 
+// the static part of a task: row-major arrays (observation kernel, policies) and the static sector of its record (the step)
+__device__ __forceinline__ void put_static(const TC& c, int j, double x, double y, unsigned rq, double du) {
+    EL(c, s_tx, c.T, j) = x; EL(c, s_ty, c.T, j) = y; EL(c, s_req, c.T, j) = (unsigned char)rq;
+    EL(c, s_dur, c.T, j) = du; EL(c, s_dur32, c.T, j) = __double2float_rn(du);
+    TXY2(c, j) = make_double2(du, x); TREC(c, j, 6) = y; TREQ(c, j) = (unsigned char)rq;
+}
+
 // on-device instance generation for one env; Philox ctr = (gid_lo, gid_hi, instance#, 0x80000000 + 2*j + b)
 __device__ __forceinline__ double u01(unsigned hi, unsigned lo) {               // 53-bit uniform in [0,1)
     return (double)(((u64)(hi >> 5) << 26) | (u64)(lo >> 6)) * (1.0 / 9007199254740992.0);
@@ -84,10 +91,10 @@ __device__ __noinline__ void t_generate(const TC& c, u64 seed, u64 gid, unsigned
     for (int j = 0; j < c.T; ++j) {
         const uint4 a = philox(g0, g1, instance, 0x80000000u + 2u * j, k0, k1);
         const uint4 b = philox(g0, g1, instance, 0x80000001u + 2u * j, k0, k1);
-        EL(c, s_tx, c.T, j) = u01(a.x, a.y); EL(c, s_ty, c.T, j) = u01(a.z, a.w);          // task_env.py:69
-        EL(c, s_req, c.T, j) = (unsigned char)(1 + pick(b.x, c.s.M));                      // :71
+        const double x = u01(a.x, a.y), y = u01(a.z, a.w);                                 // task_env.py:69
+        const unsigned rq = 1u + (unsigned)pick(b.x, c.s.M);                                 // :71
         const double du = random_duration ? u01(b.y, b.z) * max_duration : max_duration;       // :70
-        EL(c, s_dur, c.T, j) = du; EL(c, s_dur32, c.T, j) = __double2float_rn(du);
+        put_static(c, j, x, y, rq, du);
     }
     const uint4 a = philox(g0, g1, instance, 0xFFFFFFFFu, k0, k1);
     EL(c, s_dep, 2, 0) = u01(a.x, a.y); EL(c, s_dep, 2, 1) = u01(a.z, a.w);                // :67
@@ -159,9 +166,10 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
     if (ok) {
         Lp = AREC2(c, leader, 0);
         if (to_task) {
-            tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j);
-            tr.dur = EL(c, s_dur, T, j); tr.req = (int)EL(c, s_req, T, j); tr.status = (int)EL(c, t_status, T, j);
-            tr.n = EL(c, t_nmem, T, j); tr.ids = *(const u64*)&SMEM(c, j, 0); ti = TINFO2(c, j);    // (stale when the task has no members: not used then)
+            ti = TINFO2(c, j); const ulonglong2 ip = TIDPACK2(c, j);           // the chosen task's record: one 64-byte line
+            const double2 dx = TXY2(c, j); ty = TREC(c, j, 6);
+            tr.dur = dx.x; tx = dx.y; tr.ids = ip.x;                            // (count / ids / times are stale when the task has no members: not used then)
+            tr.n = (int)(ip.y & 0xffu); tr.status = (int)(signed char)((ip.y >> 8) & 0xffu); tr.req = (int)((ip.y >> 16) & 0xffu);
         } else { tx = EL(c, s_dep, 2, 0); ty = EL(c, s_dep, 2, 1); }
     }
     int want = 0; u64 g = group & ~(1ull << leader);                          // task_env.py:328
@@ -242,7 +250,7 @@ __device__ __forceinline__ unsigned step_env(const EnvArgs& E, const StepArgs& F
         st.xlast = arrival > st.xlast ? arrival : st.xlast;
         if (!to_task) st.xret = arrival < st.xret ? arrival : st.xret;
         else {
-            if (n != n0) { EL(c, t_nmem, T, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
+            if (n != n0) { TNMEM(c, j) = (unsigned char)n; tset<TW>(st.ne, j, true); tset<TW>(st.dirty, j, true); }
             if (!feas_j) {
                 if (revisit) {                                                // rare: the slots, in one batch (a loop of dependent loads otherwise)
                     for (int sl = 0; sl < n; ++sl) cp_async8(&TMPV(c, sl), &SARR(c, j, sl));
@@ -376,10 +384,10 @@ __device__ __forceinline__ double w_episode_metrics8(const TC& c, const St<TW>& 
         L.n = 0; L.feas = false; L.ids = 0; L.nab = 0; L.ts = 0.0;
         const bool in = j < T; const int jj = in ? j : 0;
         const bool ne = in && tbit<TW>(st.ne, jj); L.feas = in && tbit<TW>(st.feas, jj);
-        if (ne) { L.n = EL(c, t_nmem, T, jj); L.ids = *(const u64*)&SMEM(c, jj, 0); }
+        if (ne) { L.n = TNMEM(c, jj); L.ids = TIDS(c, jj); }
 #pragma unroll
         for (int s2 = 0; s2 < 8; ++s2) L.a[s2] = (ne && s2 < MC) ? SARR(c, jj, s2) : 0.0;
-        if (in) L.nab = EL(c, t_nab, T, jj);
+        if (in) L.nab = TNAB(c, jj);
         if (L.feas) L.ts = TINFO(c, jj, 0);
     };
     // agents (lane, lane + 32): issue these loads first as well
@@ -506,9 +514,10 @@ __device__ __forceinline__ void episode_env(const EnvArgs& E, const EpiArgs& P, 
             tx = u01(a.x, a.y); ty = u01(a.z, a.w);                            // task_env.py:69
             rq = 1u + (unsigned)pick(b2.x, E.S.M);                            // :71
             du = E.gen_random_duration ? u01(b2.y, b2.z) * E.gen_max_duration : E.gen_max_duration;   // :70
-            EL(c, s_tx, T, j) = tx; EL(c, s_ty, T, j) = ty; EL(c, s_req, T, j) = (unsigned char)rq; EL(c, s_dur, T, j) = du; EL(c, s_dur32, T, j) = __double2float_rn(du);
+            put_static(c, j, tx, ty, rq, du);
         } else { rq = EL(c, s_req, T, j); if (obs) { tx = EL(c, s_tx, T, j); ty = EL(c, s_ty, T, j); du = EL(c, s_dur, T, j); } }
-        EL(c, t_nmem, T, j) = 0; EL(c, t_status, T, j) = (signed char)rq; EL(c, t_nab, T, j) = 0;
+        TPACK(c, j) = ((u64)rq << 8) | ((u64)rq << 16);                        // no member, status = requirement, nobody abandoned (:129-140)
+        EL(c, t_status, T, j) = (signed char)rq;
         if (obs) {
             if (O->task_obs) {
                 float* r = O->task_obs + ((size_t)be * (T + 1) + j + 1) * 5;  // :185-186
@@ -1072,10 +1081,8 @@ __global__ void k_pack_static(const __grid_constant__ EnvArgs E, const double* t
     if (b >= E.S.B) return;
     const TC c = make_tc(E, b);
     for (int j = 0; j < c.T; ++j) {
-        EL(c, s_tx, c.T, j) = task_xy[((size_t)b * c.T + j) * 2]; EL(c, s_ty, c.T, j) = task_xy[((size_t)b * c.T + j) * 2 + 1];
-        EL(c, s_dur, c.T, j) = dur[(size_t)b * c.T + j]; EL(c, s_dur32, c.T, j) = __double2float_rn(dur[(size_t)b * c.T + j]);
         int r = req[(size_t)b * c.T + j]; r = r < 1 ? 1 : (r > c.s.M ? c.s.M : r);
-        EL(c, s_req, c.T, j) = (unsigned char)r;
+        put_static(c, j, task_xy[((size_t)b * c.T + j) * 2], task_xy[((size_t)b * c.T + j) * 2 + 1], (unsigned)r, dur[(size_t)b * c.T + j]);
     }
     EL(c, s_dep, 2, 0) = depot_xy[2 * (size_t)b]; EL(c, s_dep, 2, 1) = depot_xy[2 * (size_t)b + 1];
 }
@@ -1111,10 +1118,10 @@ __global__ void k_export(const __grid_constant__ EnvArgs E, const DcmLayout L, u
     const int T = c.T, A = c.A, Tp = L.Tp;
     const double h_now = EL(c, now, 1, 0);
     for (int j = 0; j < T; ++j) {
-        const bool fe = tbit<TW>(st.feas, j); const int n = tbit<TW>(st.ne, j) ? (int)EL(c, t_nmem, T, j) : 0;
+        const bool fe = tbit<TW>(st.feas, j); const int n = tbit<TW>(st.ne, j) ? (int)TNMEM(c, j) : 0;
         for (int s = 0; s < n; ++s) { ((double*)(r + L.o_arr))[s * Tp + j] = SARR(c, j, s); (r + L.o_mem)[s * Tp + j] = SMEM(c, j, s); }
-        ((double*)(r + L.o_tstart))[j] = fe ? TINFO(c, j, 0) : 0.0; ((unsigned short*)(r + L.o_tnab))[j] = EL(c, t_nab, T, j);
-        (r + L.o_nmem)[j] = (unsigned char)n; ((signed char*)(r + L.o_status))[j] = EL(c, t_status, T, j);
+        ((double*)(r + L.o_tstart))[j] = fe ? TINFO(c, j, 0) : 0.0; ((unsigned short*)(r + L.o_tnab))[j] = TNAB(c, j);
+        (r + L.o_nmem)[j] = (unsigned char)n; ((signed char*)(r + L.o_status))[j] = TSTAT(c, j);
         (r + L.o_tflags)[j] = (unsigned char)((fe ? DCM_TF_FEAS : 0u) | (tbit<TW>(st.fin, j) ? DCM_TF_FIN : 0u) | (tbit<TW>(st.dirty, j) ? DCM_TF_STALE : 0u));
     }
     for (int i = 0; i < A; ++i) {
@@ -1153,11 +1160,11 @@ __global__ void k_import(const __grid_constant__ EnvArgs E, const DcmLayout L, c
         }
         const double ts = ((const double*)(r + L.o_tstart))[j];
         if (tf & DCM_TF_FEAS) {
-            const double tfin = ts + EL(c, s_dur, T, j); TINFO(c, j, 0) = ts; TINFO(c, j, 1) = tfin;
+            const double tfin = ts + TDUR(c, j); TINFO(c, j, 0) = ts; TINFO(c, j, 1) = tfin;
             if (!(tf & DCM_TF_FIN) && tfin < st.xfin) st.xfin = tfin;
         } else { TINFO2(c, j) = make_double2(amin, amax); if (n > 0 && amin < st.xamin) st.xamin = amin; }
-        EL(c, t_nab, T, j) = ((const unsigned short*)(r + L.o_tnab))[j];
-        EL(c, t_nmem, T, j) = (unsigned char)n; EL(c, t_status, T, j) = (signed char)stt;
+        TNAB(c, j) = ((const unsigned short*)(r + L.o_tnab))[j];
+        TNMEM(c, j) = (unsigned char)n; SET_STATUS(c, j, stt);
         tset<TW>(st.feas, j, tf & DCM_TF_FEAS); tset<TW>(st.fin, j, tf & DCM_TF_FIN); tset<TW>(st.dirty, j, tf & DCM_TF_STALE);
         tset<TW>(st.ne, j, n > 0); tset<TW>(st.open, j, !(tf & DCM_TF_FEAS) && stt > 0);
     }
@@ -1281,15 +1288,15 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     size_t off = 0;
     auto carve = [&](int K, size_t elem) { size_t o = off; off += (dcm_soa_bytes(K, elem) + 255) / 256 * 256; return o; };
     const int MCB = 8; S.MCB = MCB; S.ANB = A <= 32 ? 32 : 64;
-    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_slot_mem = carve(T, MCB), o_t_info = carve(T, 16), o_a_rec = carve(A, 32), o_a_obs = carve(A, 16),
+    const size_t o_slot_arr = carve(T, 8 * (size_t)M), o_t_rec = carve(T, 64), o_a_rec = carve(A, 32), o_a_obs = carve(A, 16),
                  o_a_nd = carve(A, 8), o_a_ts = carve(A, 8), o_now = carve(1, 8), o_x_fin = carve(1, 8), o_x_amin = carve(1, 8), o_x_ret = carve(1, 8), o_x_last = carve(1, 8), o_pending = carve(1, 8), o_group = carve(1, 8),
                  o_s_tx = carve(T, 8), o_s_ty = carve(T, 8), o_s_dur = carve(T, 8), o_s_dur32 = carve(T, 4), o_s_dep = carve(2, 8), o_w_agent = carve(A, 8),
                  o_m_feas = carve(TW, 8), o_m_fin = carve(TW, 8), o_m_ne = carve(TW, 8), o_m_open = carve(TW, 8), o_m_dirty = carve(TW, 8),
                  o_am_route = carve(1, 8), o_am_assigned = carve(1, 8), o_am_returned = carve(1, 8), o_am_member = carve(1, 8), o_am_depot = carve(1, 8),
                  o_am_touched = carve(1, 8), o_am_watch = carve(1, 8),
                  o_n_steps = carve(1, 4), o_episode = carve(1, 4), o_flags = carve(1, 4), o_instance = carve(1, 4), o_total = carve(1, 4), o_leader = carve(1, 4),
-                 o_t_nab = carve(T, 2), o_a_nab = carve(A, 2),
-                 o_ended = carve(1, 1), o_t_nmem = carve(T, 1), o_t_status = carve(T, 1), o_a_node = carve(1, S.ANB), o_s_req = carve(T, 1);
+                 o_a_nab = carve(A, 2),
+                 o_ended = carve(1, 1), o_t_status = carve(T, 1), o_a_node = carve(1, S.ANB), o_s_req = carve(T, 1);
     S.tile_stride = off;
     v->arena_bytes = off * (size_t)NT;
     cudaError_t e = cudaMalloc((void**)&v->arena, v->arena_bytes);
@@ -1320,7 +1327,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     { const char* tr = getenv("DCM_PASS_TRACE"); if (e == cudaSuccess && tr && tr[0] == '1') { v->trace_units = (size_t)NT * 64; e = cudaMalloc((void**)&v->d_trace, v->trace_units * 4 * sizeof(unsigned long long)); if (e == cudaSuccess) e = cudaMemset(v->d_trace, 0, v->trace_units * 4 * sizeof(unsigned long long)); } }
     if (e != cudaSuccess) { dcm_destroy(v); return e == cudaErrorMemoryAllocation ? fail(DCM_ERR_NOMEM, "dcm_create: cudaMalloc failed") : fail_cuda(e, "dcm_create"); }
     unsigned char* a = v->arena;
-    S.t_slot_arr = (double*)(a + o_slot_arr); S.t_slot_mem = a + o_slot_mem; S.t_info = (double*)(a + o_t_info); S.a_rec = (double*)(a + o_a_rec); S.a_obs = (double*)(a + o_a_obs);
+    S.t_slot_arr = (double*)(a + o_slot_arr); S.t_rec = (double*)(a + o_t_rec); S.a_rec = (double*)(a + o_a_rec); S.a_obs = (double*)(a + o_a_obs);
     S.a_nd = (double*)(a + o_a_nd); S.a_ts = (double*)(a + o_a_ts); S.now = (double*)(a + o_now); S.x_fin = (double*)(a + o_x_fin); S.x_amin = (double*)(a + o_x_amin); S.x_ret = (double*)(a + o_x_ret); S.x_last = (double*)(a + o_x_last); S.pending = (u64*)(a + o_pending); S.group = (u64*)(a + o_group);
     S.s_tx = (double*)(a + o_s_tx); S.s_ty = (double*)(a + o_s_ty); S.s_dur = (double*)(a + o_s_dur); S.s_dur32 = (float*)(a + o_s_dur32); S.s_dep = (double*)(a + o_s_dep); S.w_agent = (double*)(a + o_w_agent);
     S.m_feas = (u64*)(a + o_m_feas); S.m_fin = (u64*)(a + o_m_fin); S.m_ne = (u64*)(a + o_m_ne); S.m_open = (u64*)(a + o_m_open); S.m_dirty = (u64*)(a + o_m_dirty);
@@ -1328,8 +1335,8 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     S.am_depot = (u64*)(a + o_am_depot); S.am_touched = (u64*)(a + o_am_touched); S.am_watch = (u64*)(a + o_am_watch);
     S.n_steps = (unsigned*)(a + o_n_steps); S.episode = (unsigned*)(a + o_episode); S.flags = (unsigned*)(a + o_flags);
     S.instance = (unsigned*)(a + o_instance); S.total = (unsigned*)(a + o_total); S.leader = (int*)(a + o_leader);
-    S.t_nab = (unsigned short*)(a + o_t_nab); S.a_nab = (unsigned short*)(a + o_a_nab);
-    S.ended = a + o_ended; S.t_nmem = a + o_t_nmem; S.t_status = (signed char*)(a + o_t_status); S.a_node = a + o_a_node; S.s_req = a + o_s_req;
+    S.a_nab = (unsigned short*)(a + o_a_nab);
+    S.ended = a + o_ended; S.t_status = (signed char*)(a + o_t_status); S.a_node = a + o_a_node; S.s_req = a + o_s_req;
     k_init<<<(S.NT * 32 + 127) / 128, 128>>>(v->E);
     e = cudaDeviceSynchronize();
 

@@ -29,12 +29,10 @@ struct DcmSoa {
     size_t tile_stride;   // bytes of one tile's block; every pointer below addresses tile 0, tile t is at + t * tile_stride
     // ---- per task, lane-contiguous ----
     double* t_slot_arr;        // [T][32][MC]   arrival of member slot s (last visit, task_env.py:202-205)
-    unsigned char* t_slot_mem; // [T][32][MCB]  member ids, ordered
-    double* t_info;            // [T][32][2]    feasible: {time_start, time_finish}; otherwise {amin, amax} = earliest / latest arrival over the member slots
-    // ---- per task, row-major ----
-    unsigned char* t_nmem;     // [T]    valid when the non-empty bit is set
-    signed char* t_status;     // [T]    stored status (may be stale, Q3)
-    unsigned short* t_nab;     // [T]    len(abandoned_agent)
+    double* t_rec;             // [T][32][8]    the task record (dcm_thread.cuh TREC): sector 0 {amin | time_start, amax | time_finish, member ids,
+                               //               count | status | requirement | len(abandoned_agent)}, sector 1 {duration, x, y, -}
+    // ---- per task, row-major (what the observation kernel streams) ----
+    signed char* t_status;     // [T]    copy of the record's stored status (may be stale, Q3)
     // ---- task masks (rows: TW) ----
     unsigned long long* m_feas;    // feasible_assignment
     unsigned long long* m_fin;     // finished

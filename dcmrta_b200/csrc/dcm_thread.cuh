@@ -53,8 +53,24 @@ struct TC {
 // lane-contiguous arrays
 #define LANE_ROW(c, K, k) ((void)(K), (size_t)(((unsigned)(k) << 5) + (c).l))
 #define SARR(c, j, sl) (TB(c, t_slot_arr)[LANE_ROW(c, (c).T, j) * (unsigned)(c).MC + (unsigned)(sl)])      // arrival of slot s of task j
-#define SMEM(c, j, sl) (TB(c, t_slot_mem)[LANE_ROW(c, (c).T, j) * 8u + (unsigned)(sl)])                        // member id of slot s (8 id bytes per task and lane)
-#define TINFO(c, j, k) (TB(c, t_info)[(LANE_ROW(c, (c).T, j) << 1) + (k)])                               // 0: time_start | amin, 1: time_finish
+// The TASK RECORD: one 64-byte line per (task, lane) = two 32-byte sectors, one DRAM burst.
+//   sector 0, everything a decision changes:  [0] amin | time_start   [1] amax | time_finish   [2] member ids (8 bytes)
+//                                             [3] count | status << 8 | requirement << 16 | len(abandoned_agent) << 32
+//   sector 1, the static instance again:      [4] duration   [5] x   [6] y   [7] -
+// A decision's round 2 reads the whole line of the chosen task (round 1 read nine scattered sectors of seven arrays for the same
+// fields); a join writes sector 0; the waiting-coalition scan and the evaluation of a task read sector 0.  Row-major copies of what the
+// observation kernel streams with TMA (status, requirement, coordinates, fp32 durations) stay beside it.
+#define TREC(c, j, k) (TB(c, t_rec)[(LANE_ROW(c, (c).T, j) << 3) + (k)])
+#define TINFO(c, j, k) TREC(c, j, k)                                                                    // 0: time_start | amin, 1: time_finish | amax
+#define TIDS(c, j) (((unsigned long long*)TB(c, t_rec))[(LANE_ROW(c, (c).T, j) << 3) + 2])
+#define SMEM(c, j, sl) (((unsigned char*)&TIDS(c, j))[(unsigned)(sl)])                                   // member id of slot s
+#define TPACK(c, j) (((unsigned long long*)TB(c, t_rec))[(LANE_ROW(c, (c).T, j) << 3) + 3])
+#define TNMEM(c, j) (((unsigned char*)&TPACK(c, j))[0])                                                  // valid when the non-empty bit is set
+#define TSTAT(c, j) (((signed char*)&TPACK(c, j))[1])                                                    // stored status (may be stale, Q3); row-major copy: t_status
+#define TREQ(c, j) (((unsigned char*)&TPACK(c, j))[2])
+#define TNAB(c, j) (((unsigned short*)&TPACK(c, j))[2])                                                  // len(abandoned_agent)
+#define TDUR(c, j) TREC(c, j, 4)
+#define TXY2(c, j) (((double2*)TB(c, t_rec))[(LANE_ROW(c, (c).T, j) << 2) + 2])                          // {duration, x}: with TREC(c, j, 6) = y the static sector
 // agent record {x, y, arrival_time[-1], travel_dist}: one 32-byte sector.  The location is always the coordinate of the node the agent
 // stands at (task_env.py:93, :134, :320) and could be looked up there; it is STORED because the observation kernels then read it with
 // the record instead of through a dependent node -> coordinate gather (measured: without it k_obs_tile 51 -> 54 us, the chunked k_obs
@@ -63,7 +79,8 @@ struct TC {
 enum { AR_X = 0, AR_Y = 1, AR_LAST = 2, AR_DIST = 3 };
 #define AREC2(c, i, h) (((double2*)TB(c, a_rec))[(LANE_ROW(c, (c).A, i) << 1) + (h)])                    // h = 0: {x, y}   h = 1: {last, dist}
 #define AOBS2(c, i) (((double2*)TB(c, a_obs))[LANE_ROW(c, (c).A, i)])                                    // observation cache, see dcm_soa.h
-#define TINFO2(c, j) (((double2*)TB(c, t_info))[LANE_ROW(c, (c).T, j)])                                  // {time_start | amin, time_finish}
+#define TINFO2(c, j) (((double2*)TB(c, t_rec))[LANE_ROW(c, (c).T, j) << 2])                              // {time_start | amin, time_finish | amax}
+#define TIDPACK2(c, j) (((ulonglong2*)TB(c, t_rec))[(LANE_ROW(c, (c).T, j) << 2) + 1])                  // {ids, count | status | requirement | abandoned}
 // route[-1] of the agents of one env, one byte each, four agents per 32-bit word, words row-major [ANB/4][32 lanes]: a warp reads word k of
 // its 32 envs with one coalesced access, and the tile's words land in shared memory (cp.async in the step, TMA in k_obs_tile) in a layout
 // whose bank depends on the lane alone
@@ -240,6 +257,9 @@ struct TaskR {
 // route[-1] of an agent: read from memory here; the fused step passes a functor that reads its register copy (Nodes below)
 struct NodeFromMemory { const TC& c; __device__ __forceinline__ unsigned operator()(int m) const { return ANODE(c, m); } };
 
+// stored status of a task: in its record (what the step reads) and in the row-major array the observation kernel streams
+#define SET_STATUS(c, j, v) do { TSTAT(c, j) = (signed char)(v); EL(c, t_status, (c).T, j) = (signed char)(v); } while (0)
+
 // counters of abandonments (u16 per agent / per task, rows of 32 lanes): bumped with a 32-bit reduction on the word that
 // holds the counter of this lane and of its neighbour -- fire-and-forget, where load + add + store would make the warp wait a
 // DRAM round trip for a value nothing in the step reads (only the episode accounting does; the counts stay far below 65,536)
@@ -272,15 +292,16 @@ template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const 
     if (use_pre) r = pre;
     else {
         if (expect_removal) stage_slots();
-        r.n = EL(c, t_nmem, T, j); r.status = (int)EL(c, t_status, T, j); r.req = (int)EL(c, s_req, T, j);      // :250
-        r.ids = *(const u64*)&SMEM(c, j, 0); r.dur = EL(c, s_dur, T, j);
-        const double2 mm = TINFO2(c, j); r.amin = mm.x; r.amax = mm.y;
+        const double2 mm = TINFO2(c, j); const ulonglong2 ip = TIDPACK2(c, j);                                  // sector 0 of the task's record, :250
+        r.amin = mm.x; r.amax = mm.y; r.ids = ip.x;
+        r.n = (int)(ip.y & 0xffu); r.status = (int)(signed char)((ip.y >> 8) & 0xffu); r.req = (int)((ip.y >> 16) & 0xffu);
+        r.dur = TDUR(c, j);
     }
     double amin_after = r.amin;
     const int n = r.n; const u64 ids = r.ids;
     auto idb = [&](int s) -> unsigned { return (unsigned)(ids >> (8 * s)) & 0xffu; };
     const int stt = r.req - n;                                                // :252 (not refreshed after removals: Q3)
-    if (stt != r.status) EL(c, t_status, T, j) = (signed char)stt;
+    if (stt != r.status) SET_STATUS(c, j, stt);
     u64 open = stt > 0 ? bit : 0, feas = 0, ne = bit, dirty = 0;
     bool removal = false;
     if (stt <= 0) {                                                           // :254
@@ -318,7 +339,7 @@ template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const 
             }
         }
         if (nab) {
-            EL(c, t_nmem, T, j) = (unsigned char)wv; bump_u16(&EL(c, t_nab, T, j), (unsigned)nab);
+            TNMEM(c, j) = (unsigned char)wv; bump_u16(&TNAB(c, j), (unsigned)nab);
             TINFO2(c, j) = make_double2(amin, amax);
             if (wv == 0) ne = 0;
             amin_after = amin;                                                // +inf when nobody is left
@@ -382,7 +403,7 @@ template <int TW, class NF> __device__ __forceinline__ void t_task_update(const 
     for (int w = 0; w < TW; ++w) {
         for (u64 mm = st.dirty[w] & ~st.feas[w] & ~st.ne[w]; mm; mm &= mm - 1) {
             const int j = 64 * w + ctz64(mm);
-            EL(c, t_status, T, j) = (signed char)EL(c, s_req, T, j);
+            SET_STATUS(c, j, TREQ(c, j));
             st.open[w] |= mm & (0 - mm);                                      // requirements >= 1
         }
         st.dirty[w] &= ~st.feas[w] & st.ne[w];
@@ -576,11 +597,11 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
         st.watch &= ~bit;
     }
     double2 aobs = make_double2(0.0, 0.0);                                    // observation cache (AOBS2)
-    if (to_task) { if (feas) aobs = TINFO2(c, j); else aobs.y = 0.0 + EL(c, s_dur, T, j); }
+    if (to_task) { if (feas) aobs = TINFO2(c, j); else aobs.y = 0.0 + TDUR(c, j); }
     int n = 0; u64 ids = 0; double amin = CUDART_INF, amax = -CUDART_INF;
     if (nonempty) {
-        n = EL(c, t_nmem, T, j);
-        ids = *(const u64*)&SMEM(c, j, 0);
+        n = TNMEM(c, j);
+        ids = TIDS(c, j);
         if (!feas) { const double2 mm = TINFO2(c, j); amin = mm.x; amax = mm.y; }   // {earliest, latest} member arrival of a waiting coalition
     }
     const double arrival = now + tt;                                          // :318
@@ -602,7 +623,7 @@ template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<T
         }
     } else if (n < c.MC) {
         SMEM(c, j, n) = (unsigned char)i; SARR(c, j, n) = arrival;
-        EL(c, t_nmem, T, j) = (unsigned char)(n + 1);
+        TNMEM(c, j) = (unsigned char)(n + 1);
         if (!feas) {
             if (n == 0) { amin = arrival; amax = arrival; } else { amin = arrival < amin ? arrival : amin; amax = arrival > amax ? arrival : amax; }
             TINFO2(c, j) = make_double2(amin, amax); st.xamin = arrival < st.xamin ? arrival : st.xamin;
@@ -671,9 +692,9 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
     const int T = c.T, A = c.A;
     for (int i = 0; i < A; ++i) EL(c, w_agent, A, i) = 0.0;                   // :345-346
     auto task_sum = [&](int j) -> double {                                    // task['sum_waiting_time'] :349-357
-        const double w_ab = (double)EL(c, t_nab, T, j) * c.W;
+        const double w_ab = (double)TNAB(c, j) * c.W;
         if (!tbit<TW>(st.ne, j)) return w_ab;
-        const int n = EL(c, t_nmem, T, j);
+        const int n = TNMEM(c, j);
         double mx = SARR(c, j, 0);
         for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; }
         const bool feas = tbit<TW>(st.feas, j);
@@ -686,7 +707,7 @@ template <int TW> __device__ __noinline__ double t_episode_metrics(const TC& c, 
 #pragma unroll
     for (int w = 0; w < TW; ++w) for (u64 mm = st.ne[w]; mm; mm &= mm - 1) {
         const int j = 64 * w + ctz64(mm);
-        const int n = EL(c, t_nmem, T, j);
+        const int n = TNMEM(c, j);
         double mx = SARR(c, j, 0);
         for (int s = 1; s < n; ++s) { const double a = SARR(c, j, s); mx = a > mx ? a : mx; }
         const bool feas = (st.feas[w] >> (j & 63)) & 1ull;

@@ -286,16 +286,21 @@ def test_bf16_shadow_rollout_follows_the_fp32_weights():
     env = BatchedTaskEnv(128, 10, 20, auto_reset=False, seed=9)
     env.generate()
     ro = GraphedRollout(env, horizon=120, record=True, check_every=8, unroll=4)
+    import copy
+
+    def bf16_argmax(n, ep):                                      # what a bf16 copy of network `n` picks at the first decision of episode `ep`
+        nb = copy.deepcopy(n).to(torch.bfloat16).eval()
+        with torch.no_grad():
+            lp = nb(ep.task_obs[0].to(torch.bfloat16), ep.agent_obs[0].to(torch.bfloat16), ep.mask[0].view(torch.bool)).float()
+        return lp.argmax(1).int()
     a = ro.run(net, "greedy", amp=True)
     assert bool(a.ended.all()) and not bool((a.mask.gather(2, a.action.long().unsqueeze(2)).squeeze(2).bool() & a.active).any())
-    lp32 = net(a.task_obs[0], a.agent_obs[0], a.mask[0].view(torch.bool))
-    agree = (lp32.argmax(1).int() == a.action[0]).float().mean()
-    assert agree > 0.9                                           # bf16 argmax vs fp32 argmax: the same policy up to rounding
+    assert torch.equal(bf16_argmax(net, a), a.action[0])          # the loop played the bf16 copy of the CURRENT weights
+    old = copy.deepcopy(net)
     with torch.no_grad():
         for p in net.parameters():
             p.add_(torch.randn_like(p) * 0.5)                    # "an update"
-    b = ro.run(net, "greedy", amp=True)
-    lp32b = net(b.task_obs[0], b.agent_obs[0], b.mask[0].view(torch.bool))
-    assert (lp32b.argmax(1).int() == b.action[0]).float().mean() > 0.9      # the shadow follows the new weights ...
-    assert (lp32.argmax(1).int() == b.action[0]).float().mean() < 0.9       # ... not the old ones
+    b = ro.run(net, "greedy", amp=True)                          # same graph, same shadow object, refreshed weights
+    assert torch.equal(bf16_argmax(net, b), b.action[0])          # the shadow follows the new weights ...
+    assert (bf16_argmax(old, b) == b.action[0]).float().mean() < 0.9      # ... not the old ones
     env.close()
