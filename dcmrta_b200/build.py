@@ -8,7 +8,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-SO = PKG / "libdcmrta_b200.so"
+SO = Path(os.environ["DCM_LIB"]).resolve() if os.environ.get("DCM_LIB") else PKG / "libdcmrta_b200.so"
 SOURCES = [CSRC / "dcm_kernels.cu"]
 HEADERS = [CSRC / "dcm_thread.cuh", CSRC / "dcm_soa.h", CSRC / "dcm_layout.h", PKG.parent / "include" / "dcmrta.h"]
 
@@ -28,6 +28,8 @@ def nvcc() -> str:
 
 
 def stale() -> bool:
+    if os.environ.get("DCM_LIB"):                    # development: load exactly this prebuilt library (A/B of build variants on one GPU visit)
+        return False
     if not SO.exists():
         return True
     t = SO.stat().st_mtime
