@@ -1,8 +1,11 @@
-// dcm_thread.cuh -- thread-per-env device functions of the TaskEnv step for sm_100a (v4).
+// dcm_thread.cuh -- thread-per-env device functions of the TaskEnv step for sm_100a.
 //
 // One thread simulates one env; the 32 envs of a tile are simulated by the 32 lanes of one warp.  The boolean state of
-// an env lives in 64-bit masks held in registers (struct St); loops run over set bits only; load-only passes are kept
-// free of stores so that the compiler can batch their loads (the kernel is latency-bound, not bandwidth-bound).
+// an env lives in 64-bit masks held in registers (struct St); loops run over set bits only.  The kernel that runs these
+// functions is latency-bound, not bandwidth-bound: a decision is organised as two unconditional rounds of loads (step_env,
+// dcm_kernels.cu), per-task data is one 64-byte record (TREC), per-thread arrays that need dynamic indexing live in a
+// shared-memory scratch (TC::nds / nws / tmp) filled with cp.async, and data-dependent gathers are staged there and consumed
+// by rolled loops.
 //
 // All event-clock arithmetic is fp64 in the exact operation order of the reference; the file
 // is compiled with -fmad=false and the one fused multiply-add the reference performs (inside np.linalg.norm) is
@@ -113,18 +116,6 @@ template <class V, class L, class U> __device__ __forceinline__ void for_bits4(u
         const int j0 = base + ctz64(b0), j1 = b1 ? base + ctz64(b1) : j0, j2 = b2 ? base + ctz64(b2) : j0, j3 = b3 ? base + ctz64(b3) : j0;
         const V v0 = load(j0), v1 = load(j1), v2 = load(j2), v3 = load(j3);
         use(b0, j0, v0); if (b1) use(b1, j1, v1); if (b2) use(b2, j2, v2); if (b3) use(b3, j3, v3);
-    }
-}
-// the same, N at a time
-template <int N, class V, class L, class U> __device__ __forceinline__ void for_bitsN(u64 m, int base, L load, U use) {
-    while (m) {
-        u64 bb[N]; int jj[N]; V v[N];
-#pragma unroll
-        for (int q = 0; q < N; ++q) { bb[q] = m & (0 - m); m ^= bb[q]; jj[q] = (q == 0 || bb[q]) ? base + ctz64(bb[q]) : jj[0]; }
-#pragma unroll
-        for (int q = 0; q < N; ++q) v[q] = load(jj[q]);
-#pragma unroll
-        for (int q = 0; q < N; ++q) if (bb[q]) use(bb[q], jj[q], v[q]);
     }
 }
 template <int TW> __device__ __forceinline__ u64 all_tasks(int T, int w) {
@@ -284,7 +275,7 @@ template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c,
 // it no longer waits (feasible, or empty) -- the caller keeps the per-env bound St::xamin exact with it.
 template <int TW, class NF> __device__ __forceinline__ double t_eval_task(const TC& c, St<TW>& st, double now, int j, unsigned char* newly, const NF& node_of, TaskR& pre,
                                                                         bool use_pre, bool expect_removal = false) {
-    const int T = c.T, w = j >> 6; const u64 bit = 1ull << (j & 63);
+    const int w = j >> 6; const u64 bit = 1ull << (j & 63);
     TaskR r;
     bool have_slots = false;
     auto stage_slots = [&]() { for (int s = 0; s < c.MC; ++s) cp_async8(&TMPV(c, s), &SARR(c, j, s)); have_slots = true; };   // slots past the count hold stale values that are never used
@@ -586,7 +577,6 @@ __device__ __forceinline__ void travel(const TC& c, double ax, double ay, double
 }
 template <int TW> __device__ __forceinline__ void t_agent_step(const TC& c, St<TW>& st, double now, int i, int action, double tx, double ty,
                                                               double d, double tt, unsigned& flags) {
-    const int T = c.T;
     const u64 bit = 1ull << i;
     const int j = action - 1;
     const bool to_task = action != 0, feas = to_task && tbit<TW>(st.feas, j), nonempty = to_task && tbit<TW>(st.ne, j);
@@ -767,40 +757,6 @@ template <int TW, class NF> __device__ __forceinline__ void t_update_and_advance
         if ((flags & ENV_FINISHED) || !(now < c.max_time)) { flags |= ENV_DONE; return; }     // worker.py:45
         pending = dec; now = t; slot = true;                                  // worker.py:47-49
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// observation rows of one env, produced by its thread into a per-warp shared-memory tile and streamed out with
-// unit-stride stores (k_obs).  mask (task_env.py:192-200 + worker.py:58-61), agent rows (:165-180), task rows
-// (:182-190), cast to fp32 (worker.py:62,64).
-// ---------------------------------------------------------------------------------------------------------------
-template <int TW> __device__ __forceinline__ void obs_agent_row(const TC& c, const St<TW>& st, double now, double Lx, double Ly, int i, float* r) {
-    const u64 bit = 1ull << i;
-    double travel_t = 0.0, wait = 0.0, remain = 0.0;
-    const double ax = AREC(c, i, AR_X), ay = AREC(c, i, AR_Y);
-    if ((st.route & bit) && !(st.depot & bit)) {                              // :168
-        const unsigned k = ANODE(c, i);
-        const double arr = AREC(c, i, AR_LAST);
-        const bool feas = tbit<TW>(st.feas, (int)k);
-        const double ts = feas ? TINFO(c, k, 0) : 0.0;                        // time_start is 0 until the task is feasible (Q6)
-        const double tf = feas ? TINFO(c, k, 1) : 0.0 + EL(c, s_dur, c.T, k); // fl(time_start + time)
-        const double v = arr - now; travel_t = v < 0.0 ? 0.0 : v;             // :169
-        if (now <= ts) { const double wv = now - arr; wait = wv < 0.0 ? 0.0 : wv; }   // :170
-        if (now >= ts) { const double q = tf - now; remain = q < 0.0 ? 0.0 : q; }     // :171
-    }
-    r[0] = __double2float_rn(travel_t); r[1] = __double2float_rn(remain); r[2] = __double2float_rn(wait);   // :176-177
-    r[3] = __double2float_rn(Lx - ax); r[4] = __double2float_rn(Ly - ay); r[5] = (st.assigned & bit) ? 1.0f : 0.0f;
-}
-// task row jj (0 = depot)
-__device__ __forceinline__ void obs_task_row(const TC& c, double Lx, double Ly, int jj, float* r) {
-    if (jj == 0) {                                                            // :188 depot row
-        r[0] = 0.f; r[1] = 0.f; r[2] = 0.f;
-        r[3] = __double2float_rn(EL(c, s_dep, 2, 0) - Lx); r[4] = __double2float_rn(EL(c, s_dep, 2, 1) - Ly);
-        return;
-    }
-    const int j = jj - 1;
-    r[0] = (float)(int)EL(c, t_status, c.T, j); r[1] = (float)EL(c, s_req, c.T, j); r[2] = __double2float_rn(EL(c, s_dur, c.T, j));   // :185
-    r[3] = __double2float_rn(EL(c, s_tx, c.T, j) - Lx); r[4] = __double2float_rn(EL(c, s_ty, c.T, j) - Ly);                       // :186
 }
 
 }  // namespace dcm

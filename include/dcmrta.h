@@ -14,7 +14,7 @@
  *     one is asynchronous on it and performs no host synchronisation.  Calls taking host pointers synchronise.
  *   - a handle owns ALL state in HBM (allocated once in dcm_create), is bound to one device, and is not
  *     thread-safe; distinct handles are independent.
- *   - B envs, A agents (<= 64), T tasks (<= 254), M = max coalition size = member slots per task (<= 16).  Requirements
+ *   - B envs, A agents (<= 64), T tasks (<= 254), M = max coalition size = member slots per task (<= 8).  Requirements
  *     must lie in [1, M].  Legal (unmasked) actions never put more than M agents on a task; preset routes can, so a
  *     handle used for dcm_execute_by_route should be created with M = the largest coalition the routes may form
  *     (DCM_ENV_ERR_OVERFLOW is raised per env otherwise).
