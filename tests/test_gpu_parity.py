@@ -226,6 +226,7 @@ def test_inkernel_policy_matches_oracle_on_synthetic(policy):
                 o.fused_reset()
             assert lead[q] == o.leader, (policy, sample[q], k)
     assert min(episodes) >= 2
+    assert env.total_episodes() >= sum(episodes)                     # dcm_total_episodes: every accounted episode of the batch (bench.py's phase report)
     met = env.episode_metrics()[sample].cpu().numpy()
     for q in range(len(sample)):
         gold = np.array([last_metrics[q][key] for key in METRIC_KEYS])
