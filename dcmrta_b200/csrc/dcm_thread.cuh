@@ -245,7 +245,7 @@ struct TaskR {
 // A non-dirty task with members therefore costs one load and one compare; everything else is evaluated exactly as written
 // in the reference, including Q2 (skip after removal) and Q3 (status not refreshed after removals).
 // ---------------------------------------------------------------------------------------------------------------
-// route[-1] of an agent: read from memory here; the fused step passes a functor that reads its register copy (Nodes below)
+// route[-1] of an agent: read from memory here; the fused step passes a functor that reads its shared-memory copy (NodeFromScratch)
 struct NodeFromMemory { const TC& c; __device__ __forceinline__ unsigned operator()(int m) const { return ANODE(c, m); } };
 
 // stored status of a task: in its record (what the step reads) and in the row-major array the observation kernel streams
@@ -264,11 +264,11 @@ template <int TW, class NF> __device__ __forceinline__ void abandon(const TC& c,
     if (node_of((int)m) == (unsigned)j) st.member &= ~(1ull << m);           // it no longer belongs to the task it stands at
 }
 
-// Evaluation of one non-feasible task that has members (task_env.py:250-271).  `pre`: the head of the task's record when the caller
-// holds it in registers (the fused step, for the task that was just joined), else it is loaded here in one batch.  Only the two
+// Evaluation of one non-feasible task that has members (task_env.py:250-271).  `pre` (with use_pre): the head of the task's record when
+// the caller holds it in registers (the fused step, for the task that was just joined), else sector 0 of the record is loaded here.  Only the two
 // rare outcomes read the member slots (one more batch, then registers only): members leave because the coalition is complete but
 // spread over more than max_waiting_time (:260-265, iterates a copy: Q4), or because they have waited long enough (:266-271,
-// mutates the list it iterates: Q2).  On return *pre, if given, says whether the task is feasible now and carries {time_start,
+// mutates the list it iterates: Q2).  On return `pre`, when it was used, says whether the task is feasible now and carries {time_start,
 // time_finish}; its count / ids / arrivals are stale after a removal (nobody uses them afterwards).
 // `expect_removal`: the caller already knows that the earliest member gives up (the waiting-coalition scan), so the member slots are
 // loaded together with the head instead of one round trip later.  Returns the earliest member arrival of the task afterwards, +inf when
