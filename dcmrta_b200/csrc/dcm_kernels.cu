@@ -1241,9 +1241,10 @@ struct dcm_env {
     bool obs_ready, obs_tile, obs_resets;   // k_obs_tile applies to this handle's shape (DCM_OBS_CHUNKED=1: always k_obs); it also writes restarted envs' observations
     unsigned* d_elist; unsigned* d_ecount; unsigned pass_no; bool dense_episode;   // ended-env list [B] + two alternating counters (k_episode_list)
     // DCM_* experiment switches, read ONCE in dcm_create (never on the step path)
-    bool sw_obs_reset_by_episode, sw_obs_chunked, sw_episode_carveout_default, sw_step_no_nds, sw_no_pdl; int epi_warps, epi_per_sm;
+    bool sw_obs_reset_by_episode, sw_obs_chunked, sw_episode_carveout_default, sw_step_no_nds, sw_no_pdl, sw_no_zero_copy; int epi_warps, epi_per_sm;
     // dcm_step_host runs on its own stream: it must start after the asynchronous work earlier calls queued on the CALLER's stream
     cudaStream_t last_stream; bool last_pending; cudaEvent_t ev_order;
+    const int32_t* host_action_seen; const int32_t* host_action_dev;   // dcm_step_host: the caller's action buffer and, when it is pinned, its device alias
     uint64_t launches;
 };
 
@@ -1318,7 +1319,7 @@ int dcm_create(dcm_env** out, int device, int B, int A, int T, int M, uint32_t f
     {   // every other experiment switch, once per handle
         auto on = [](const char* name) { const char* g = getenv(name); return g && g[0] == '1'; };
         v->sw_obs_reset_by_episode = on("DCM_OBS_RESET_BY_EPISODE"); v->obs_persistent = on("DCM_OBS_PERSISTENT");   // persistent: measured slower than one block per tile, DESIGN.md section 4
-        v->sw_obs_chunked = on("DCM_OBS_CHUNKED"); v->sw_episode_carveout_default = on("DCM_EPISODE_CARVEOUT_DEFAULT"); v->sw_step_no_nds = on("DCM_STEP_NO_NDS"); v->sw_no_pdl = on("DCM_NO_PDL");
+        v->sw_obs_chunked = on("DCM_OBS_CHUNKED"); v->sw_episode_carveout_default = on("DCM_EPISODE_CARVEOUT_DEFAULT"); v->sw_step_no_nds = on("DCM_STEP_NO_NDS"); v->sw_no_pdl = on("DCM_NO_PDL"); v->sw_no_zero_copy = on("DCM_NO_ZERO_COPY");
         v->epi_warps = 2; { const char* gw = getenv("DCM_EPISODE_WARPS"); if (gw && atoi(gw) >= 1 && atoi(gw) <= EPI_LIST_MAX_WARPS) v->epi_warps = atoi(gw); }   // envs (warps) per block
         v->epi_per_sm = 8; { const char* gg = getenv("DCM_EPISODE_GRID"); if (gg && atoi(gg) > 0) v->epi_per_sm = atoi(gg); }                                  // warps per SM
     }
@@ -1614,9 +1615,22 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
         CK(cudaStreamWaitEvent(s, v->ev_order, 0));
         v->last_pending = false;
     }
-    if (action) CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
+    // Actions in PINNED host memory are read in place: under unified addressing the step kernel's first round of loads fetches them over
+    // PCIe (one coalesced 128-byte read per warp, beside its reads of the state) instead of waiting for a 256 kB copy to land first.
+    // Pageable memory is staged through d_action.  The attribute query is cached per buffer.
+    const int32_t* act_d = v->d_action;
+    if (action) {
+        if (action != v->host_action_seen) {
+            cudaPointerAttributes pa; v->host_action_seen = action; v->host_action_dev = nullptr;
+            if (!v->sw_no_zero_copy && cudaPointerGetAttributes(&pa, action) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+                v->host_action_dev = (const int32_t*)pa.devicePointer;
+            cudaGetLastError();
+        }
+        if (v->host_action_dev) act_d = v->host_action_dev;
+        else CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
+    }
     v->forked = false;
-    rc = dcm_step(v, v->d_action, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
+    rc = dcm_step(v, act_d, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
     if (rc) return rc;
     // next_leader, reward and done are final when k_step ends (ev_fork; k_step also knows the first leader of an episode the
     // episode kernel is about to restart): they travel to the host while the episode and observation kernels run

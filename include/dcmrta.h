@@ -118,8 +118,8 @@ int dcm_step(dcm_env* env, const int32_t* action_d, const int32_t* followers_d, 
              float* agent_obs_d, float* task_obs_d, uint8_t* mask_d,
              int32_t* next_leader_d, float* reward_d, uint8_t* done_d, int32_t* used_action_d, void* stream);
 
-/* Same call with HOST buffers (pageable or pinned): actions are copied in, outputs copied out, the call returns when the
- * outputs are valid.  Any output pointer may be NULL (then it is not copied).  next_leader, reward and done are final when the
+/* Same call with HOST buffers (pageable or pinned): actions are copied in -- or, from pinned memory, read in place by the step
+ * kernel --, outputs copied out, the call returns when the outputs are valid.  Any output pointer may be NULL (then it is not copied).  next_leader, reward and done are final when the
  * step kernel ends and are copied on a second stream while the episode and observation kernels still run.  The call runs on a
  * stream of the handle; it first waits (on the device, through an event) for the asynchronous work earlier calls on this handle
  * queued on the caller's stream -- dcm_reset / dcm_generate / dcm_load_instances / dcm_step / granular calls -- so no host

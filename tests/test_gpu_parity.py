@@ -321,10 +321,17 @@ def test_step_host_matches_device_step(variant, monkeypatch):
     out = {"next_leader": np.empty(B, np.int32), "reward": np.empty(B, np.float32), "done": np.empty(B, np.uint8),
            "agent_obs": np.empty((B, A, 6), np.float32), "task_obs": np.empty((B, T + 1, 5), np.float32), "mask": np.empty((B, T + 1), np.uint8)}
     restarts = 0
+    import torch
+    pinned = torch.empty(B, dtype=torch.int32).pin_memory()
     for k in range(450):
         dev.step(policy="random")
         acts = np.ascontiguousarray(dev.used_action.cpu().numpy().astype(np.int32))
-        host.step_host(acts, out)
+        if k % 2:                                                              # pinned buffer: the step kernel reads the actions in place; pageable: staged copy
+            import torch
+            pinned[:] = torch.from_numpy(acts)
+            host.step_host(pinned, out)
+        else:
+            host.step_host(acts, out)
         assert np.array_equal(out["next_leader"], dev.leader.cpu().numpy()), k
         assert np.array_equal(out["reward"], dev.reward.cpu().numpy()), k
         assert np.array_equal(out["done"], dev.done_u8.cpu().numpy()), k
