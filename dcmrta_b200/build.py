@@ -27,13 +27,30 @@ def nvcc() -> str:
     return exe
 
 
+def source_hash() -> str:
+    """sha256 over the sources, headers and flags the library is built from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in SOURCES + HEADERS:
+        h.update(p.name.encode()); h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+HASH = Path(str(SO) + ".hash")
+
+
 def stale() -> bool:
+    """The library is rebuilt when the CONTENT of its sources changed since it was built (a hash written beside it), not when file
+    times say so: a snapshot copied to another box (gpurun, a checkout) does not keep them, and N ranks recompiling for 70 s for
+    nothing is not a start-up cost anybody wants."""
     if os.environ.get("DCM_LIB"):                    # development: load exactly this prebuilt library (A/B of build variants on one GPU visit)
         return False
     if not SO.exists():
         return True
-    t = SO.stat().st_mtime
-    return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
+    if not HASH.exists():                            # a library from before the hash file: fall back to file times
+        t = SO.stat().st_mtime
+        return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
+    return HASH.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -60,6 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                 tmp.unlink(missing_ok=True)
                 raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
             os.replace(tmp, SO)
+            HASH.write_text(source_hash() + "\n")
             if verbose:
                 print(r.stderr)
         finally:
