@@ -1244,7 +1244,6 @@ struct dcm_env {
     bool sw_obs_reset_by_episode, sw_obs_chunked, sw_episode_carveout_default, sw_step_no_nds, sw_no_pdl, sw_no_zero_copy; int epi_warps, epi_per_sm;
     // dcm_step_host runs on its own stream: it must start after the asynchronous work earlier calls queued on the CALLER's stream
     cudaStream_t last_stream; bool last_pending; cudaEvent_t ev_order;
-    const int32_t* host_action_seen; const int32_t* host_action_dev;   // dcm_step_host: the caller's action buffer and, when it is pinned, its device alias
     uint64_t launches;
 };
 
@@ -1617,17 +1616,13 @@ int dcm_step_host(dcm_env* v, const int32_t* action, int policy, float* agent_ob
     }
     // Actions in PINNED host memory are read in place: under unified addressing the step kernel's first round of loads fetches them over
     // PCIe (one coalesced 128-byte read per warp, beside its reads of the state) instead of waiting for a 256 kB copy to land first.
-    // Pageable memory is staged through d_action.  The attribute query is cached per buffer.
+    // Pageable memory is staged through d_action.  (The attribute query is repeated per call: a cached answer could outlive the buffer.)
     const int32_t* act_d = v->d_action;
     if (action) {
-        if (action != v->host_action_seen) {
-            cudaPointerAttributes pa; v->host_action_seen = action; v->host_action_dev = nullptr;
-            if (!v->sw_no_zero_copy && cudaPointerGetAttributes(&pa, action) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
-                v->host_action_dev = (const int32_t*)pa.devicePointer;
-            cudaGetLastError();
-        }
-        if (v->host_action_dev) act_d = v->host_action_dev;
-        else CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s));
+        cudaPointerAttributes pa;
+        if (!v->sw_no_zero_copy && cudaPointerGetAttributes(&pa, action) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            act_d = (const int32_t*)pa.devicePointer;
+        else { cudaGetLastError(); CK(cudaMemcpyAsync(v->d_action, action, B * 4, cudaMemcpyHostToDevice, s)); }
     }
     v->forked = false;
     rc = dcm_step(v, act_d, nullptr, 0, nullptr, policy, v->d_agent, v->d_task, v->d_mask, v->d_leader, v->d_reward, v->d_done, nullptr, s);
