@@ -3,20 +3,25 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA path through the C ABI)
   python bench.py --impl reference [...]                          the reference's CPU implementation of the path
-  torchrun --nproc-per-node N bench.py --gpus N ...               N > 1 (one rank per GPU, env shards, no collective on the data path)
+  torchrun --nproc-per-node N bench.py --gpus N ...               N > 1 (one rank per GPU, env shards, no collective on the data path);
+                                                                  launched plainly with --gpus N > 1 it re-executes itself under torchrun
+  python bench.py --total-envs 1048576 --agents A --tasks T --gpus N     BASELINE configs[3]: a fixed job sharded evenly (strong scaling)
+  python bench.py --mode rollout|train [--amp] --gpus N                   BASELINE configs[4]: the attention policy in the loop
 
 A "step" is one pass of the hot path over one batch: ONE leader decision for every env of the batch (dcm_step:
 apply the choice, coalition/feasibility update, agent update, slot advance, leader choice, observation + mask for the
 next leader), B env-steps per GPU per step.  Workload = BASELINE.json configs[2]: 65,536 synthetic 20A/50T envs per GPU,
-uniform-random policy over unmasked actions (in-kernel Philox), auto-reset, fp64 event clock, fp32 observations.
+uniform-random policy over unmasked actions (in-kernel Philox), auto-reset, fp64 event clock, fp32 observations.  The timed passes
+always see the STEADY STATE: an untimed pre-roll (--preroll, 400 passes) desynchronises the envs after the reset, and config.phase
+reports how many episodes ended per timed pass.
 
   value        whole-job env-steps/s, state resident in HBM (CUDA events, max over ranks)
-  e2e          same metric through the host-buffer C-ABI call (dcm_step_host): actions H2D from pinned memory,
-               reward/done/next-leader D2H every step, observations written to the device-resident policy buffers
+  e2e          same metric through the host-buffer C-ABI call (dcm_step_host): actions from pinned host memory (read in place by the
+               step kernel), reward/done/next-leader D2H every step, observations written to the device-resident policy buffers
   e2e_full_obs as e2e but the observations and mask are also copied to pinned host memory every step (PCIe-bound)
   roofline     HBM: algorithmic bytes/step (w=8) x B / average duration of one pass (k_step, then k_episode_list on a
                side stream beside k_obs_tile; CUDA events on the launching stream, which joins the side stream before the next pass)
-               vs MEASURED_PEAKS.json; traffic = ncu DRAM bytes of the same pass
+               vs MEASURED_PEAKS.json; traffic / dram_frac = the DRAM bytes ncu counted for one steady-state pass (profiles/traffic.json)
   cpu_baseline the C oracle port of the reference TaskEnv on the host cores, bounded sample of the same workload
 """
 from __future__ import annotations
