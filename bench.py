@@ -66,6 +66,8 @@ def parse():
                         "PyTorch attention policy in the loop (rollout) and with the REINFORCE update + gradient all-reduce (train)")
     p.add_argument("--iters", type=int, default=3, help="--mode rollout/train: timed iterations (one episode per env each)")
     p.add_argument("--amp", action="store_true", help="--mode rollout/train: the rollouts call a bf16 shadow copy of the policy (the update stays fp32)")
+    p.add_argument("--fused", action="store_true", help="--mode rollout/train: the rollouts call policy_fused.FusedPolicy (bf16 GEMMs + the sm_100a "
+                   "kernels of include/dcmrta_policy.h between them); the update stays fp32 PyTorch")
     p.add_argument("--eager", action="store_true", help="--mode rollout/train: eager decision loop instead of the CUDA-graph replay")
     return p.parse_args()
 
@@ -381,7 +383,8 @@ def run_training(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.envs if args.envs != 65536 else 8192
-    cfg = TrainerConfig(agents=args.agents, tasks=args.tasks, envs_per_rank=B, amp=args.amp, seed=1234, eval_instances=max(world, 64),
+    amp = "fused" if args.fused else args.amp
+    cfg = TrainerConfig(agents=args.agents, tasks=args.tasks, envs_per_rank=B, amp=amp, seed=1234, eval_instances=max(world, 64),
                         graph_rollout=not args.eager)
     tr = ReinforceTrainer(cfg, device=local)
 
@@ -412,9 +415,9 @@ def run_training(args):
             "metric": f"env-steps/sec at {args.agents}A/{args.tasks}T with the attention policy in the loop ({args.mode})",
             "value": float(cnt.item()) / (float(t.item()) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.iters, "warmup": 1,
             "ms_per_step": float(t.item()) / args.iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 env / " + ("bf16" if args.amp else "fp32") + " policy", "data": "synthetic",
+            "dtype": "f64 env / " + ("bf16 fused-kernel" if args.fused else "bf16" if args.amp else "fp32") + " policy", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[4]: {B} synthetic {args.agents}A/{args.tasks}T envs per GPU, one episode per env per iteration, "
-                                   f"AttentionNet(128) in PyTorch, mode={args.mode}, decision loop " + ("eager" if args.eager else "replayed from a CUDA graph"), "envs_per_gpu": B, "iterations": args.iters,
+                                   f"AttentionNet(128) in PyTorch" + (", rollout forward = torch.mm GEMMs + libdcmrta_policy.so kernels" if args.fused else "") + f", mode={args.mode}, decision loop " + ("eager" if args.eager else "replayed from a CUDA graph"), "envs_per_gpu": B, "iterations": args.iters,
                        "parallelism": f"env shards x{world}" + (", one flat NCCL gradient all-reduce per update" if args.mode == "train" else "")},
             "env_steps_timed": float(cnt.item())}), flush=True)
     if world > 1:

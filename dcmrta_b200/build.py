@@ -1,4 +1,5 @@
-"""dcmrta_b200/build.py -- compile the CUDA extension in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""dcmrta_b200/build.py -- compile the CUDA libraries in-tree with nvcc for sm_100a (cross-compiles without a GPU):
+libdcmrta_b200.so (the env step, include/dcmrta.h) and libdcmrta_policy.so (the policy's rollout-forward kernels, include/dcmrta_policy.h)."""
 from __future__ import annotations
 
 import os
@@ -19,6 +20,12 @@ NVCC_FLAGS = [
     "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
 ]
 
+# the policy kernels: bf16 activations, fp32 arithmetic with contraction allowed (nothing there has to round like NumPy)
+POLICY_SO = PKG / "libdcmrta_policy.so"
+POLICY_SOURCES = [CSRC / "policy_kernels.cu"]
+POLICY_HEADERS = [PKG.parent / "include" / "dcmrta_policy.h"]
+POLICY_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-shared"]
+
 
 def nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -27,11 +34,11 @@ def nvcc() -> str:
     return exe
 
 
-def source_hash() -> str:
-    """sha256 over the sources, headers and flags the library is built from."""
+def source_hash(files=None, flags=None) -> str:
+    """sha256 over the sources, headers and flags a library is built from (default: libdcmrta_b200.so)."""
     import hashlib
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for p in SOURCES + HEADERS:
+    h = hashlib.sha256(" ".join(NVCC_FLAGS if flags is None else flags).encode())
+    for p in (SOURCES + HEADERS if files is None else files):
         h.update(p.name.encode()); h.update(p.read_bytes())
     return h.hexdigest()
 
@@ -85,5 +92,38 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return SO
 
 
+def policy_stale() -> bool:
+    h = Path(str(POLICY_SO) + ".hash")
+    return not POLICY_SO.exists() or not h.exists() or h.read_text().strip() != source_hash(POLICY_SOURCES + POLICY_HEADERS, POLICY_FLAGS)
+
+
+def build_policy(force: bool = False, verbose: bool = False) -> Path:
+    """libdcmrta_policy.so, with the same discipline as build(): content hash, file lock, temporary file + os.replace()."""
+    if not (force or policy_stale()):
+        return POLICY_SO
+    import fcntl
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not policy_stale():
+                return POLICY_SO
+            tmp = POLICY_SO.with_name(f".{POLICY_SO.name}.{os.getpid()}.tmp")
+            cmd = [nvcc(), *POLICY_FLAGS, "-o", str(tmp), *map(str, POLICY_SOURCES)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, POLICY_SO)
+            Path(str(POLICY_SO) + ".hash").write_text(source_hash(POLICY_SOURCES + POLICY_HEADERS, POLICY_FLAGS) + "\n")
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return POLICY_SO
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_policy(force=True, verbose=True))

@@ -1,0 +1,417 @@
+// dcmrta_b200/csrc/policy_kernels.cu -- libdcmrta_policy.so (include/dcmrta_policy.h): the memory-bound pieces of the attention policy's
+// no-grad rollout forward as single sm_100a kernels.  The dense GEMMs stay in cuBLASLt (torch.mm); what PyTorch runs around them as
+// several eager kernels each (head split / permute copies, a flash kernel at head dimension 16, add + LayerNorm, sigmoid + mul, the
+// pointer's tanh / masked_fill / log_softmax) is one pass over the activations here.  Everything is HBM-bound SIMT work on bf16 rows:
+// 16-byte loads and stores, fp32 arithmetic, warp shuffles; no tensor cores (head dimension 16, at most ~200 keys).
+//
+// Activations: bf16, row-major, row = env * n + token, embedding 128 (parameters.py:9), 8 heads of 16 (attention.py:251-258).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dcmrta_policy.h"
+
+namespace {
+
+constexpr int E = 128, H = 8, D = 16, HID = 512;
+constexpr int ATT_MAX_NK = 220, Q1_MAX_NK = 256, PTR_MAX_N = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess) snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof g_err, "%s", what);
+    return code;
+}
+
+int launched(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(-4, what, e);
+}
+
+int sm_count() {                                                              // of the current device, asked once per device
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- bf16 <-> fp32 on packed words ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+    f[0] = lo(u.x); f[1] = hi(u.x); f[2] = lo(u.y); f[3] = hi(u.y); f[4] = lo(u.z); f[5] = hi(u.z); f[6] = lo(u.w); f[7] = hi(u.w);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {                 // a -> low half (the lower address), round to nearest even
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float wmaxf(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- embedding: nn.Linear(KIN, 128) on fp32 observation rows -> bf16 ----------------------------------------------------------------
+// warp per row, lane <-> 4 output columns whose weights stay in registers; one 8-byte store per lane = one 256-byte row per warp
+template <int KIN>
+__global__ void __launch_bounds__(256) k_embed(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                               uint2* __restrict__ out, long rows) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long)gridDim.x * 8;
+    float wr[4][KIN], bs[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        bs[c] = bias[lane * 4 + c];
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) wr[c][k] = w[(lane * 4 + c) * KIN + k];
+    }
+    for (long r = warp; r < rows; r += nwarps) {
+        float xv[KIN];
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) xv[k] = __ldg(x + r * KIN + k);
+        float y[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            y[c] = bs[c];
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) y[c] = fmaf(xv[k], wr[c][k], y[c]);
+        }
+        out[r * 32 + lane] = make_uint2(pack2(y[0], y[1]), pack2(y[2], y[3]));
+    }
+}
+
+// ---- multi-head attention, no mask: block per env, warp per head, lane per query -----------------------------------------------------
+// K and V of the env (all heads) are staged once in shared memory as fp32 [head][key][16]; every lane of a warp then reads the SAME
+// key row (a shared-memory broadcast) and keeps its own query, running maximum, denominator and 16 accumulators in registers: an
+// online softmax over the keys in chunks of four, nothing but the 32-byte head slices of Q / out touches global memory again.
+__global__ void __launch_bounds__(256) k_attention(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
+                                                   const uint16_t* __restrict__ v, int ldkv, uint16_t* __restrict__ out, int ldo,
+                                                   int nq, int nk, float scale_log2e) {
+    extern __shared__ float4 smem4[];
+    const int nkp = (nk + 3) & ~3;                                            // key rows padded to whole chunks (zero rows, score forced down)
+    float* Ks = reinterpret_cast<float*>(smem4);
+    float* Vs = Ks + H * nkp * D;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int idx = tid; idx < nkp * 16; idx += 256) {                         // 16 chunks of 8 bf16 per key row: chunk c = head c / 2, half c % 2
+        const int t = idx >> 4, c = idx & 15, h = c >> 1, d0 = (c & 1) * 8;
+        float kf[8], vf[8];
+        if (t < nk) {
+            const size_t row = (size_t)b * nk + t;
+            unpack8(__ldg(reinterpret_cast<const uint4*>(k + row * ldkv) + c), kf);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(v + row * ldkv) + c), vf);
+        } else {
+#pragma unroll
+            for (int d = 0; d < 8; ++d) kf[d] = vf[d] = 0.f;
+        }
+        float4* kd = reinterpret_cast<float4*>(Ks + (h * nkp + t) * D + d0);
+        float4* vd = reinterpret_cast<float4*>(Vs + (h * nkp + t) * D + d0);
+        kd[0] = make_float4(kf[0], kf[1], kf[2], kf[3]); kd[1] = make_float4(kf[4], kf[5], kf[6], kf[7]);
+        vd[0] = make_float4(vf[0], vf[1], vf[2], vf[3]); vd[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
+    }
+    __syncthreads();
+    const int h = tid >> 5, lane = tid & 31;
+    const float4* Kh = reinterpret_cast<const float4*>(Ks + h * nkp * D);
+    const float4* Vh = reinterpret_cast<const float4*>(Vs + h * nkp * D);
+    for (int i = lane; i < nq; i += 32) {
+        const size_t row = (size_t)b * nq + i;
+        float qf[16];
+        const uint4* qp = reinterpret_cast<const uint4*>(q + row * ldq + h * D);
+        unpack8(__ldg(qp), qf); unpack8(__ldg(qp + 1), qf + 8);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) qf[d] *= scale_log2e;                     // softmax in base 2: exp(s) = 2^(s log2 e)
+        float m = -1e30f, l = 0.f, acc[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+        for (int t0 = 0; t0 < nkp; t0 += 4) {
+            float s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 k0 = Kh[(t0 + u) * 4], k1 = Kh[(t0 + u) * 4 + 1], k2 = Kh[(t0 + u) * 4 + 2], k3 = Kh[(t0 + u) * 4 + 3];
+                float a = qf[0] * k0.x;
+                a = fmaf(qf[1], k0.y, a); a = fmaf(qf[2], k0.z, a); a = fmaf(qf[3], k0.w, a);
+                a = fmaf(qf[4], k1.x, a); a = fmaf(qf[5], k1.y, a); a = fmaf(qf[6], k1.z, a); a = fmaf(qf[7], k1.w, a);
+                a = fmaf(qf[8], k2.x, a); a = fmaf(qf[9], k2.y, a); a = fmaf(qf[10], k2.z, a); a = fmaf(qf[11], k2.w, a);
+                a = fmaf(qf[12], k3.x, a); a = fmaf(qf[13], k3.y, a); a = fmaf(qf[14], k3.z, a); a = fmaf(qf[15], k3.w, a);
+                s[u] = (t0 + u < nk) ? a : -1e30f;
+            }
+            const float mn = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), m);
+            const float corr = ex2(m - mn);                                   // 0 in the first chunk (m = -1e30), where l and acc are 0 anyway
+            m = mn; l *= corr;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[d] *= corr;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float p = ex2(s[u] - m);                                // padded keys: 2^(-1e30) = 0
+                l += p;
+                const float4 v0 = Vh[(t0 + u) * 4], v1 = Vh[(t0 + u) * 4 + 1], v2 = Vh[(t0 + u) * 4 + 2], v3 = Vh[(t0 + u) * 4 + 3];
+                acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
+                acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+                acc[8] = fmaf(p, v2.x, acc[8]); acc[9] = fmaf(p, v2.y, acc[9]); acc[10] = fmaf(p, v2.z, acc[10]); acc[11] = fmaf(p, v2.w, acc[11]);
+                acc[12] = fmaf(p, v3.x, acc[12]); acc[13] = fmaf(p, v3.y, acc[13]); acc[14] = fmaf(p, v3.z, acc[14]); acc[15] = fmaf(p, v3.w, acc[15]);
+            }
+        }
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d] *= inv;
+        uint4* op = reinterpret_cast<uint4*>(out + row * ldo + h * D);
+        op[0] = pack8(acc); op[1] = pack8(acc + 8);
+    }
+}
+
+// ---- one query per env (global decoders), optional key mask: block per env, warp per head, lane per key -------------------------------
+__global__ void __launch_bounds__(256) k_attention_q1(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
+                                                      const uint16_t* __restrict__ v, int ldkv, const uint8_t* __restrict__ mask,
+                                                      uint16_t* __restrict__ out, int ldo, int nk, float scale_log2e) {
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float qf[16];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)b * ldq + h * D);
+        unpack8(__ldg(qp), qf); unpack8(__ldg(qp + 1), qf + 8);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) qf[d] *= scale_log2e;
+    }
+    constexpr int R = Q1_MAX_NK / 32;
+    float s[R];
+    float m = -1e30f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int t = r * 32 + lane;
+        s[r] = -1e30f;                                                        // no such key, or forbidden (attention.py:130-133)
+        if (t < nk && !(mask && mask[(size_t)b * nk + t])) {
+            float kf[16];
+            const uint4* kp = reinterpret_cast<const uint4*>(k + ((size_t)b * nk + t) * ldkv + h * D);
+            unpack8(__ldg(kp), kf); unpack8(__ldg(kp + 1), kf + 8);
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) a = fmaf(qf[d], kf[d], a);
+            s[r] = a;
+        }
+        m = fmaxf(m, s[r]);
+    }
+    m = wmaxf(m);
+    uint4* op = reinterpret_cast<uint4*>(out + (size_t)b * ldo + h * D);
+    if (m < -1e29f) {                                                         // every key forbidden: the query attends to nothing (attention.py:137-140)
+        if (lane == 0) { op[0] = make_uint4(0, 0, 0, 0); op[1] = make_uint4(0, 0, 0, 0); }
+        return;
+    }
+    float l = 0.f, acc[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int t = r * 32 + lane;
+        if (s[r] > -1e29f) {
+            const float p = ex2(s[r] - m);
+            l += p;
+            float vf[16];
+            const uint4* vp = reinterpret_cast<const uint4*>(v + ((size_t)b * nk + t) * ldkv + h * D);
+            unpack8(__ldg(vp), vf); unpack8(__ldg(vp + 1), vf + 8);
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[d] = fmaf(p, vf[d], acc[d]);
+        }
+    }
+    l = wsum(l);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = wsum(acc[d]);
+    if (lane == 0) {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d] *= inv;
+        op[0] = pack8(acc); op[1] = pack8(acc + 8);
+    }
+}
+
+// ---- out = LayerNorm(x + res) * gamma + beta: warp per row, lane <-> 4 columns ---------------------------------------------------------
+__global__ void __launch_bounds__(256) k_add_layernorm(const uint2* x, const uint2* res, const float4* __restrict__ gamma,
+                                                       const float4* __restrict__ beta, uint2* out, long rows, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long)gridDim.x * 8;
+    const float4 g = gamma[lane], bt = beta[lane];
+    for (long r = warp; r < rows; r += nwarps) {
+        const uint2 a = x[r * 32 + lane], c = res[r * 32 + lane];
+        float v0 = lo(a.x) + lo(c.x), v1 = hi(a.x) + hi(c.x), v2 = lo(a.y) + lo(c.y), v3 = hi(a.y) + hi(c.y);
+        const float mean = wsum((v0 + v1) + (v2 + v3)) * (1.f / E);
+        v0 -= mean; v1 -= mean; v2 -= mean; v3 -= mean;
+        const float var = wsum((v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3)) * (1.f / E);   // biased, as nn.LayerNorm
+        const float rstd = rsqrtf(var + eps);
+        out[r * 32 + lane] = make_uint2(pack2(fmaf(v0 * rstd, g.x, bt.x), fmaf(v1 * rstd, g.y, bt.y)),
+                                        pack2(fmaf(v2 * rstd, g.z, bt.z), fmaf(v3 * rstd, g.w, bt.w)));
+    }
+}
+
+// ---- out = sigmoid(wv[:, :512]) * wv[:, 512:]: thread per 8 columns -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gate(const uint4* __restrict__ wv, uint4* __restrict__ out, long chunks) {
+    const long stride = (long)gridDim.x * 256;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < chunks; i += stride) {
+        const long r = i >> 6; const int c = (int)(i & 63);                   // 64 chunks of 8 per 512-wide half row
+        float a[8], b[8], y[8];
+        unpack8(__ldg(wv + r * 128 + c), a); unpack8(__ldg(wv + r * 128 + 64 + c), b);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) y[d] = b[d] / (1.f + __expf(-a[d]));
+        out[i] = pack8(y);
+    }
+}
+
+// ---- pointer head: warp per env; the 128-wide dot products are warp-cooperative (one coalesced 256-byte row per load) ---------------------
+__global__ void __launch_bounds__(256) k_pointer(const uint2* __restrict__ qk, const uint2* __restrict__ feat, const uint8_t* __restrict__ mask,
+                                                 float* __restrict__ logp, int B, int n, float norm, float clip) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const uint2 qw = __ldg(qk + (size_t)b * 32 + lane);
+    const float q0 = lo(qw.x), q1 = hi(qw.x), q2 = lo(qw.y), q3 = hi(qw.y);
+    constexpr int R = PTR_MAX_N / 32;
+    float u[R];
+    const uint2* fb = feat + (size_t)b * n * 32;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        u[r] = -1e30f;                                                        // no such key: out of the softmax
+        if (r * 32 < n) {                                                     // warp-uniform
+            const int cnt = min(32, n - r * 32);
+            for (int tt = 0; tt < cnt; tt += 4) {                             // four rows in flight
+                float d[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = r * 32 + min(tt + j, cnt - 1);
+                    const uint2 f = __ldg(fb + (size_t)t * 32 + lane);
+                    d[j] = fmaf(q3, hi(f.y), fmaf(q2, lo(f.y), fmaf(q1, hi(f.x), q0 * lo(f.x))));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dot = wsum(d[j]);
+                    if (tt + j < cnt && lane == tt + j) u[r] = dot;
+                }
+            }
+            const int t = r * 32 + lane;
+            if (t < n) {
+                u[r] = clip * tanhf(norm * u[r]);                             // attention.py:73-74
+                if (mask && mask[(size_t)b * n + t]) u[r] = -1e4f;            // :78-80 (stays inside the softmax, as in the reference)
+            }
+        }
+    }
+    float m = -1e30f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) m = fmaxf(m, u[r]);
+    m = wmaxf(m);
+    float l = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (r * 32 + lane < n) l += expf(u[r] - m);
+    l = wsum(l);
+    const float lse = m + logf(l);
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (r * 32 + lane < n) logp[(size_t)b * n + r * 32 + lane] = u[r] - lse;
+}
+
+int row_grid(long rows) {                                                     // 8 rows (warps) per block, at most 8 resident blocks per SM
+    const long want = (rows + 7) / 8, cap = (long)sm_count() * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dcmp_embed(const float* x, const float* w, const float* bias, uint16_t* out, long rows, int k_in, void* stream) {
+    if (!x || !w || !bias || !out || rows < 0) return fail(-1, "dcmp_embed: null pointer or negative row count");
+    if (!aligned16(out)) return fail(-1, "dcmp_embed: out must be 16-byte aligned");
+    if (k_in != 5 && k_in != 6) return fail(-2, "dcmp_embed: k_in must be 5 (task rows) or 6 (agent rows)");
+    if (rows == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_embed: no CUDA device (there is no CPU fallback)");
+    const cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (k_in == 5) k_embed<5><<<row_grid(rows), 256, 0, s>>>(x, w, bias, reinterpret_cast<uint2*>(out), rows);
+    else k_embed<6><<<row_grid(rows), 256, 0, s>>>(x, w, bias, reinterpret_cast<uint2*>(out), rows);
+    return launched("k_embed");
+}
+
+int dcmp_attention(const uint16_t* q, int ldq, const uint16_t* k, const uint16_t* v, int ldkv, uint16_t* out, int ldo, int B, int nq, int nk,
+                   float scale, void* stream) {
+    if (!q || !k || !v || !out) return fail(-1, "dcmp_attention: null pointer");
+    if (B < 0 || nq < 1 || nk < 1 || nk > ATT_MAX_NK) return fail(-2, "dcmp_attention: need B >= 0, nq >= 1, 1 <= nk <= 220");
+    if ((ldq | ldkv | ldo) & 7 || ldq < E || ldkv < E || ldo < E || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out))
+        return fail(-1, "dcmp_attention: row strides must be multiples of 8 elements (>= 128) and pointers 16-byte aligned");
+    if (B == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_attention: no CUDA device (there is no CPU fallback)");
+    const int nkp = (nk + 3) & ~3;
+    const size_t smem = (size_t)2 * H * nkp * D * sizeof(float);
+    static bool opted[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!opted[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * H * ATT_MAX_NK * D * (int)sizeof(float));
+        if (e != cudaSuccess) return fail(-4, "cudaFuncSetAttribute(k_attention)", e);
+        opted[dev] = true;
+    }
+    k_attention<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
+    return launched("k_attention");
+}
+
+int dcmp_attention_q1(const uint16_t* q, int ldq, const uint16_t* k, const uint16_t* v, int ldkv, const uint8_t* mask, uint16_t* out, int ldo,
+                      int B, int nk, float scale, void* stream) {
+    if (!q || !k || !v || !out) return fail(-1, "dcmp_attention_q1: null pointer");
+    if (B < 0 || nk < 1 || nk > Q1_MAX_NK) return fail(-2, "dcmp_attention_q1: need B >= 0, 1 <= nk <= 256");
+    if ((ldq | ldkv | ldo) & 7 || ldq < E || ldkv < E || ldo < E || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out))
+        return fail(-1, "dcmp_attention_q1: row strides must be multiples of 8 elements (>= 128) and pointers 16-byte aligned");
+    if (B == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_attention_q1: no CUDA device (there is no CPU fallback)");
+    k_attention_q1<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, mask, out, ldo, nk, scale * LOG2E);
+    return launched("k_attention_q1");
+}
+
+int dcmp_add_layernorm(const uint16_t* x, const uint16_t* res, const float* gamma, const float* beta, uint16_t* out, long rows, float eps,
+                       void* stream) {
+    if (!x || !res || !gamma || !beta || !out || rows < 0) return fail(-1, "dcmp_add_layernorm: null pointer or negative row count");
+    if (!aligned16(x) || !aligned16(res) || !aligned16(out) || !aligned16(gamma) || !aligned16(beta))
+        return fail(-1, "dcmp_add_layernorm: pointers must be 16-byte aligned");
+    if (rows == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_add_layernorm: no CUDA device (there is no CPU fallback)");
+    k_add_layernorm<<<row_grid(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint2*>(x), reinterpret_cast<const uint2*>(res), reinterpret_cast<const float4*>(gamma),
+        reinterpret_cast<const float4*>(beta), reinterpret_cast<uint2*>(out), rows, eps);
+    return launched("k_add_layernorm");
+}
+
+int dcmp_gate(const uint16_t* wv, uint16_t* out, long rows, void* stream) {
+    if (!wv || !out || rows < 0) return fail(-1, "dcmp_gate: null pointer or negative row count");
+    if (!aligned16(wv) || !aligned16(out)) return fail(-1, "dcmp_gate: pointers must be 16-byte aligned");
+    if (rows == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_gate: no CUDA device (there is no CPU fallback)");
+    const long chunks = rows * (HID / 8);
+    const long want = (chunks + 255) / 256, cap = (long)sm_count() * 8;
+    k_gate<<<(int)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(wv),
+                                                                                          reinterpret_cast<uint4*>(out), chunks);
+    return launched("k_gate");
+}
+
+int dcmp_pointer(const uint16_t* qk, const uint16_t* feat, const uint8_t* mask, float* logp, int B, int n, float norm, float clip, void* stream) {
+    if (!qk || !feat || !logp) return fail(-1, "dcmp_pointer: null pointer");
+    if (B < 0 || n < 1 || n > PTR_MAX_N) return fail(-2, "dcmp_pointer: need B >= 0, 1 <= n <= 256");
+    if (!aligned16(qk) || !aligned16(feat)) return fail(-1, "dcmp_pointer: pointers must be 16-byte aligned");
+    if (B == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_pointer: no CUDA device (there is no CPU fallback)");
+    k_pointer<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint2*>(qk), reinterpret_cast<const uint2*>(feat),
+                                                                         mask, logp, B, n, norm, clip);
+    return launched("k_pointer");
+}
+
+const char* dcmp_last_error(void) { return g_err; }
+const char* dcmp_version(void) { return "dcmrta_policy 1 (sm_100a)"; }
+
+}  // extern "C"

@@ -54,11 +54,19 @@ class BatchedRollout:
         return t if self.record else t & 1
 
     def _forward_net(self, net, amp):
-        """The module the decision loop calls.  amp: a bf16 SHADOW COPY of `net` (weights refreshed here, at the start of every run), fed
+        """The module the decision loop calls.  amp = "fused": policy_fused.FusedPolicy.  amp = True: a bf16 SHADOW COPY of `net` (weights refreshed here, at the start of every run), fed
         bf16 observations -- not autocast, which keeps LayerNorm in fp32 and casts around every op (14.0 ms per forward of 8,192 envs,
         32 % of it LayerNorm; profiles/r09_policy_forward_profile.txt).  The update always runs on the fp32 network."""
         if not amp:
             return net
+        if amp == "fused":
+            # the same parameters behind the inference path of policy_fused.py: bf16 GEMMs + one sm_100a kernel for everything between
+            # two GEMMs (include/dcmrta_policy.h); re-laid-out weights refreshed here, into buffers that keep their addresses
+            from .policy_fused import FusedPolicy
+            fused = self.__dict__.setdefault("_fused", {})
+            if id(net) not in fused:
+                fused[id(net)] = FusedPolicy(net)
+            return fused[id(net)].refresh()
         import copy
         shadows = self.__dict__.setdefault("_shadows", {})           # one per network object (the trainer alternates policy and baseline)
         if id(net) not in shadows:
@@ -70,12 +78,14 @@ class BatchedRollout:
 
     @staticmethod
     def _logp(fnet, amp, tasks, agents, mask):
+        if amp == "fused":
+            return fnet(tasks, agents, mask)                         # fp32 observations in (the embedding kernel reads them), fp32 logp out
         if amp:
             return fnet(tasks.to(torch.bfloat16), agents.to(torch.bfloat16), mask).float()
         return fnet(tasks, agents, mask)
 
     @torch.no_grad()
-    def run(self, net, mode: str = "sample", generator: torch.Generator | None = None, amp: bool = False, replay: dict | None = None,
+    def run(self, net, mode: str = "sample", generator: torch.Generator | None = None, amp: bool | str = False, replay: dict | None = None,
             keep_logp: bool = False) -> Episodes:
         """Play one episode per env with `net` (sampling: worker.py:70; greedy: worker.py:222).  The env must not auto-reset.
 
@@ -175,7 +185,7 @@ class GraphedRollout(BatchedRollout):
     def _graph(self, net, mode, amp):
         """net: the module the loop calls (the bf16 shadow when amp); its parameters keep their addresses, so refreshing them between
         replays is all an update of the policy needs."""
-        key = (id(net), mode, bool(amp))
+        key = (id(net), mode, amp)
         if key not in self._graphs:
             env = self.env
             side = torch.cuda.Stream(device=env.device)
@@ -196,7 +206,7 @@ class GraphedRollout(BatchedRollout):
         return self._graphs[key]
 
     @torch.no_grad()
-    def run(self, net, mode: str = "sample", generator=None, amp: bool = False, replay=None, keep_logp: bool = False) -> Episodes:
+    def run(self, net, mode: str = "sample", generator=None, amp: bool | str = False, replay=None, keep_logp: bool = False) -> Episodes:
         assert replay is None and not keep_logp and generator is None, "the graphed loop draws from the default CUDA generator and replays nothing"
         env = self.env
         assert not env.auto_reset

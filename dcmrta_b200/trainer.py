@@ -115,7 +115,8 @@ class TrainerConfig:
     max_coalition: int = COALITION_SIZE
     max_time: float = MAX_TIME
     updates_per_iteration: int = 0   # 0 = one pass over the collected decisions
-    amp: bool = False                # rollouts call a bf16 shadow copy of the network (rollout._forward_net); the update stays fp32
+    amp: bool | str = False          # True: rollouts call a bf16 shadow copy of the network (rollout._forward_net); "fused": the inference path of
+                                     # policy_fused.py (bf16 GEMMs + the sm_100a kernels of include/dcmrta_policy.h); the update stays fp32
     # Which network plays the greedy episode the advantage is measured against.  "local" is what the reference DOES: baseline_test
     # (worker.py:222) calls self.local_net -- the network that just sampled -- and never the `local_baseline` it was handed, so the
     # advantage is reward - greedy reward of the CURRENT policy and the t-test baseline swap (driver.py:219-279) never reaches the loss.

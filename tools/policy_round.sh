@@ -1,0 +1,18 @@
+#!/bin/bash
+# tools/policy_round.sh <tag> [train]: one GPU visit for the policy-in-the-loop rows (BASELINE configs[4]) -- the GPU tests of
+# policy_fused.py, the per-kernel profile of one forward of 8,192 envs (bf16 shadow module vs FusedPolicy), the rollout bench lines.
+tag=$1; shift
+mkdir -p gpurun_out
+for opt in "$@"; do eval "do_$opt=1"; done
+( time timeout 300 python -m pytest tests/test_policy_fused.py -m gpu -x -q ) > gpurun_out/${tag}_pytest_policy_fused.log 2>&1; tail -15 gpurun_out/${tag}_pytest_policy_fused.log
+timeout 300 python tools/prof_policy.py 8192 shadow fused > gpurun_out/${tag}_policy_forward_profile.txt 2>&1; grep "ms per forward" gpurun_out/${tag}_policy_forward_profile.txt
+for flags in "--fused" "--fused --eager" "--amp"; do
+  timeout 300 python bench.py --mode rollout $flags --iters 3 2>gpurun_out/${tag}_rollout.err | tee -a gpurun_out/${tag}_config5.jsonl | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('rollout $flags:', d['dtype'], 'value %.4g' % d['value'], 'ms/iter %.1f' % d['ms_per_step'])"
+done
+if [ -n "$do_train" ]; then
+  timeout 400 python bench.py --mode train --fused --iters 2 2>>gpurun_out/${tag}_rollout.err | tee -a gpurun_out/${tag}_config5.jsonl | cut -c1-160
+fi
