@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/dcmrta_policy.h"
 
@@ -177,6 +178,91 @@ __global__ void __launch_bounds__(256) k_attention(const uint16_t* __restrict__ 
     }
 }
 
+// ---- multi-head attention, no mask, on the tensor cores: block per env, warp per head -------------------------------------------------
+// Head dimension 16 is exactly one k-step of mma.m16n8k16: S = Q K^T for 16 queries x 64 keys is 8 MMAs, O += P V another 8, with P
+// handed from the accumulator layout to the A-operand layout in registers (two adjacent 16x8 accumulator tiles are one 16x16 A tile).
+// Fragments are loaded straight from global memory (the 32-byte head slice of a row is one sector; K and V of one (env, head) are 3 kB and
+// stay in L1 across the query tiles); online softmax over key blocks of 64, so any nk.  No shared memory, no block barrier.
+// (tcgen05 has nothing to offer a 51 x 51 x 16 problem: its smallest tile is M = 64 with operands staged through shared memory by TMA.)
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ld32(const uint16_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+
+__global__ void __launch_bounds__(256) k_attention_mma(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
+                                                       const uint16_t* __restrict__ v, int ldkv, uint16_t* __restrict__ out, int ldo,
+                                                       int nq, int nk, float scale_log2e) {
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const uint16_t* qb = q + (size_t)b * nq * ldq + h * D;
+    const uint16_t* kb = k + (size_t)b * nk * ldkv + h * D;
+    const uint16_t* vb = v + (size_t)b * nk * ldkv + h * D;
+    uint16_t* ob = out + (size_t)b * nq * ldo + h * D;
+    for (int m0 = 0; m0 < nq; m0 += 16) {
+        const int r0 = m0 + g, r1 = r0 + 8;                                   // the two query rows this lane holds pieces of
+        uint32_t a[4];                                                        // A fragment: {row r0, dims 2tg..}, {r1, same}, {r0, dims 8+2tg..}, {r1, same}
+        a[0] = r0 < nq ? ld32(qb + (size_t)r0 * ldq + tg * 2) : 0u; a[1] = r1 < nq ? ld32(qb + (size_t)r1 * ldq + tg * 2) : 0u;
+        a[2] = r0 < nq ? ld32(qb + (size_t)r0 * ldq + tg * 2 + 8) : 0u; a[3] = r1 < nq ? ld32(qb + (size_t)r1 * ldq + tg * 2 + 8) : 0u;
+        float mrun0 = -1e30f, mrun1 = -1e30f, l0 = 0.f, l1 = 0.f;              // running maxima (quad-uniform), per-lane partial denominators
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // O accumulators: dims 8nt + 2tg + {0,1}, rows r0 (0,1) and r1 (2,3)
+        for (int k0 = 0; k0 < nk; k0 += 64) {
+            float s[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                                     // S tile j: keys k0 + 8j .. + 7; B fragment = K[key 8j + g][dims 2tg.., 8 + 2tg..]
+                const int key = k0 + 8 * j + g;
+                uint32_t b0 = 0u, b1 = 0u;
+                if (key < nk) { b0 = ld32(kb + (size_t)key * ldkv + tg * 2); b1 = ld32(kb + (size_t)key * ldkv + tg * 2 + 8); }
+                s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+                if (k0 + 8 * j < nk) mma16816(s[j], a, b0, b1);               // warp-uniform
+            }
+            float mx0 = -1e30f, mx1 = -1e30f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kc = k0 + 8 * j + tg * 2;                           // this lane's two key columns of tile j
+                s[j][0] = kc < nk ? s[j][0] * scale_log2e : -1e30f; s[j][1] = kc + 1 < nk ? s[j][1] * scale_log2e : -1e30f;
+                s[j][2] = kc < nk ? s[j][2] * scale_log2e : -1e30f; s[j][3] = kc + 1 < nk ? s[j][3] * scale_log2e : -1e30f;
+                mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(mrun0, mx0), mn1 = fmaxf(mrun1, mx1);
+            const float c0 = ex2(mrun0 - mn0), c1 = ex2(mrun1 - mn1);          // 0 on the first block, where everything it scales is 0
+            mrun0 = mn0; mrun1 = mn1; l0 *= c0; l1 *= c1;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                                     // keys past nk: 2^(-1e30 - m) = 0
+                s[j][0] = ex2(s[j][0] - mn0); s[j][1] = ex2(s[j][1] - mn0); s[j][2] = ex2(s[j][2] - mn1); s[j][3] = ex2(s[j][3] - mn1);
+                l0 += s[j][0] + s[j][1]; l1 += s[j][2] + s[j][3];
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {                                  // O += P V, 16 keys per step: accumulator tiles 2kk, 2kk + 1 -> one A fragment
+                if (k0 + 16 * kk < nk) {                                      // warp-uniform
+                    uint32_t pa[4];
+                    pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]); pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+                    pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]); pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+                    const int key0 = k0 + 16 * kk + tg * 2;                   // B fragment = V[keys key0, key0 + 1 | key0 + 8, key0 + 9][dim 8nt + g]
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const uint16_t* vp = vb + (size_t)key0 * ldkv + nt * 8 + g;
+                        const uint32_t v00 = key0 < nk ? __ldg(vp) : 0, v01 = key0 + 1 < nk ? __ldg(vp + ldkv) : 0;
+                        const uint32_t v10 = key0 + 8 < nk ? __ldg(vp + 8 * (size_t)ldkv) : 0, v11 = key0 + 9 < nk ? __ldg(vp + 9 * (size_t)ldkv) : 0;
+                        mma16816(o[nt], pa, v00 | (v01 << 16), v10 | (v11 << 16));
+                    }
+                }
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            if (r0 < nq) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * ldo + nt * 8 + tg * 2) = pack2(o[nt][0] * i0, o[nt][1] * i0);
+            if (r1 < nq) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * ldo + nt * 8 + tg * 2) = pack2(o[nt][2] * i1, o[nt][3] * i1);
+        }
+    }
+}
+
 // ---- one query per env (global decoders), optional key mask: block per env, warp per head, lane per key -------------------------------
 __global__ void __launch_bounds__(256) k_attention_q1(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
                                                       const uint16_t* __restrict__ v, int ldkv, const uint8_t* __restrict__ mask,
@@ -316,9 +402,9 @@ __global__ void __launch_bounds__(256) k_pointer(const uint2* __restrict__ qk, c
 #pragma unroll
     for (int r = 0; r < R; ++r) if (r * 32 + lane < n) l += expf(u[r] - m);
     l = wsum(l);
-    const float lse = m + logf(l);
+    const float logl = logf(l);
 #pragma unroll
-    for (int r = 0; r < R; ++r) if (r * 32 + lane < n) logp[(size_t)b * n + r * 32 + lane] = u[r] - lse;
+    for (int r = 0; r < R; ++r) if (r * 32 + lane < n) logp[(size_t)b * n + r * 32 + lane] = (u[r] - m) - logl;   // in this order: -1e4 entries keep their low bits
 }
 
 int row_grid(long rows) {                                                     // 8 rows (warps) per block, at most 8 resident blocks per SM
@@ -358,6 +444,11 @@ int dcmp_attention(const uint16_t* q, int ldq, const uint16_t* k, const uint16_t
         const cudaError_t e = cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * H * ATT_MAX_NK * D * (int)sizeof(float));
         if (e != cudaSuccess) return fail(-4, "cudaFuncSetAttribute(k_attention)", e);
         opted[dev] = true;
+    }
+    static const bool simt = getenv("DCMP_ATTENTION_SIMT") != nullptr;       // development A/B: the CUDA-core kernel
+    if (!simt) {
+        k_attention_mma<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
+        return launched("k_attention_mma");
     }
     k_attention<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
     return launched("k_attention");

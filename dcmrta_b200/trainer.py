@@ -149,8 +149,8 @@ class ReinforceTrainer:
         self.base_env = BatchedTaskEnv(B, cfg.agents, cfg.tasks, seed=cfg.seed + 1, first_gid=first_gid, **kw)
         horizon = cfg.horizon or 4 * (cfg.agents + cfg.tasks)
         Rollout = GraphedRollout if cfg.graph_rollout else BatchedRollout
-        self.rollout = Rollout(self.env, horizon, record=True)
-        self.base_rollout = Rollout(self.base_env, horizon, record=False)
+        self.rollout = Rollout(self.env, horizon, record=True, check_every=8)      # every pass past the longest episode is a wasted forward
+        self.base_rollout = Rollout(self.base_env, horizon, record=False, check_every=8)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(cfg.seed * 1000003 + self.rank)
         if cfg.graph_rollout:                                        # the graphed loop samples from the default CUDA generator
@@ -160,7 +160,7 @@ class ReinforceTrainer:
         E = max(1, cfg.eval_instances // self.world)
         self.eval_env = BatchedTaskEnv(E, cfg.agents, cfg.tasks, seed=cfg.seed + 7919, first_gid=self.rank * E, **kw)
         self.eval_env.generate(max_duration=5.0)
-        self.eval_rollout = Rollout(self.eval_env, horizon, record=False)
+        self.eval_rollout = Rollout(self.eval_env, horizon, record=False, check_every=8)
         self.baseline_value = None
 
     # ---- one training iteration: play, score against the baseline, update ------------------------------------------------

@@ -147,7 +147,7 @@ def test_kernel_attention(B, nq, nk):
     out = torch.full((B * nq, 128), 7.0, dtype=torch.bfloat16, device="cuda")
     CudaOps().attention(qkv[:, 128:256], kv[:, :128], kv[:, 128:], out, B, nq, nk)
     ref = TorchOps().attention(qkv[:, 128:256], kv[:, :128], kv[:, 128:], torch.empty(B * nq, 128, device="cuda"), B, nq, nk)
-    _close(out, ref, 2e-3, "attention")
+    _close(out, ref, 4e-3, "attention")                 # P is rounded to bf16 before P V (the A operand of the second MMA)
 
 
 @pytest.mark.gpu
