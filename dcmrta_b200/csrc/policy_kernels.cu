@@ -9,14 +9,13 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <stdlib.h>
 
 #include "../../include/dcmrta_policy.h"
 
 namespace {
 
 constexpr int E = 128, H = 8, D = 16, HID = 512;
-constexpr int ATT_MAX_NK = 220, Q1_MAX_NK = 256, PTR_MAX_N = 256;
+constexpr int ATT_MAX_NK = 400, Q1_MAX_NK = 256, PTR_MAX_N = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
 thread_local char g_err[256] = "";
@@ -100,89 +99,15 @@ __global__ void __launch_bounds__(256) k_embed(const float* __restrict__ x, cons
     }
 }
 
-// ---- multi-head attention, no mask: block per env, warp per head, lane per query -----------------------------------------------------
-// K and V of the env (all heads) are staged once in shared memory as fp32 [head][key][16]; every lane of a warp then reads the SAME
-// key row (a shared-memory broadcast) and keeps its own query, running maximum, denominator and 16 accumulators in registers: an
-// online softmax over the keys in chunks of four, nothing but the 32-byte head slices of Q / out touches global memory again.
-__global__ void __launch_bounds__(256) k_attention(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
-                                                   const uint16_t* __restrict__ v, int ldkv, uint16_t* __restrict__ out, int ldo,
-                                                   int nq, int nk, float scale_log2e) {
-    extern __shared__ float4 smem4[];
-    const int nkp = (nk + 3) & ~3;                                            // key rows padded to whole chunks (zero rows, score forced down)
-    float* Ks = reinterpret_cast<float*>(smem4);
-    float* Vs = Ks + H * nkp * D;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    for (int idx = tid; idx < nkp * 16; idx += 256) {                         // 16 chunks of 8 bf16 per key row: chunk c = head c / 2, half c % 2
-        const int t = idx >> 4, c = idx & 15, h = c >> 1, d0 = (c & 1) * 8;
-        float kf[8], vf[8];
-        if (t < nk) {
-            const size_t row = (size_t)b * nk + t;
-            unpack8(__ldg(reinterpret_cast<const uint4*>(k + row * ldkv) + c), kf);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(v + row * ldkv) + c), vf);
-        } else {
-#pragma unroll
-            for (int d = 0; d < 8; ++d) kf[d] = vf[d] = 0.f;
-        }
-        float4* kd = reinterpret_cast<float4*>(Ks + (h * nkp + t) * D + d0);
-        float4* vd = reinterpret_cast<float4*>(Vs + (h * nkp + t) * D + d0);
-        kd[0] = make_float4(kf[0], kf[1], kf[2], kf[3]); kd[1] = make_float4(kf[4], kf[5], kf[6], kf[7]);
-        vd[0] = make_float4(vf[0], vf[1], vf[2], vf[3]); vd[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
-    }
-    __syncthreads();
-    const int h = tid >> 5, lane = tid & 31;
-    const float4* Kh = reinterpret_cast<const float4*>(Ks + h * nkp * D);
-    const float4* Vh = reinterpret_cast<const float4*>(Vs + h * nkp * D);
-    for (int i = lane; i < nq; i += 32) {
-        const size_t row = (size_t)b * nq + i;
-        float qf[16];
-        const uint4* qp = reinterpret_cast<const uint4*>(q + row * ldq + h * D);
-        unpack8(__ldg(qp), qf); unpack8(__ldg(qp + 1), qf + 8);
-#pragma unroll
-        for (int d = 0; d < 16; ++d) qf[d] *= scale_log2e;                     // softmax in base 2: exp(s) = 2^(s log2 e)
-        float m = -1e30f, l = 0.f, acc[16];
-#pragma unroll
-        for (int d = 0; d < 16; ++d) acc[d] = 0.f;
-        for (int t0 = 0; t0 < nkp; t0 += 4) {
-            float s[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 k0 = Kh[(t0 + u) * 4], k1 = Kh[(t0 + u) * 4 + 1], k2 = Kh[(t0 + u) * 4 + 2], k3 = Kh[(t0 + u) * 4 + 3];
-                float a = qf[0] * k0.x;
-                a = fmaf(qf[1], k0.y, a); a = fmaf(qf[2], k0.z, a); a = fmaf(qf[3], k0.w, a);
-                a = fmaf(qf[4], k1.x, a); a = fmaf(qf[5], k1.y, a); a = fmaf(qf[6], k1.z, a); a = fmaf(qf[7], k1.w, a);
-                a = fmaf(qf[8], k2.x, a); a = fmaf(qf[9], k2.y, a); a = fmaf(qf[10], k2.z, a); a = fmaf(qf[11], k2.w, a);
-                a = fmaf(qf[12], k3.x, a); a = fmaf(qf[13], k3.y, a); a = fmaf(qf[14], k3.z, a); a = fmaf(qf[15], k3.w, a);
-                s[u] = (t0 + u < nk) ? a : -1e30f;
-            }
-            const float mn = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), m);
-            const float corr = ex2(m - mn);                                   // 0 in the first chunk (m = -1e30), where l and acc are 0 anyway
-            m = mn; l *= corr;
-#pragma unroll
-            for (int d = 0; d < 16; ++d) acc[d] *= corr;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float p = ex2(s[u] - m);                                // padded keys: 2^(-1e30) = 0
-                l += p;
-                const float4 v0 = Vh[(t0 + u) * 4], v1 = Vh[(t0 + u) * 4 + 1], v2 = Vh[(t0 + u) * 4 + 2], v3 = Vh[(t0 + u) * 4 + 3];
-                acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
-                acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
-                acc[8] = fmaf(p, v2.x, acc[8]); acc[9] = fmaf(p, v2.y, acc[9]); acc[10] = fmaf(p, v2.z, acc[10]); acc[11] = fmaf(p, v2.w, acc[11]);
-                acc[12] = fmaf(p, v3.x, acc[12]); acc[13] = fmaf(p, v3.y, acc[13]); acc[14] = fmaf(p, v3.z, acc[14]); acc[15] = fmaf(p, v3.w, acc[15]);
-            }
-        }
-        const float inv = 1.f / l;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) acc[d] *= inv;
-        uint4* op = reinterpret_cast<uint4*>(out + row * ldo + h * D);
-        op[0] = pack8(acc); op[1] = pack8(acc + 8);
-    }
-}
-
 // ---- multi-head attention, no mask, on the tensor cores: block per env, warp per head -------------------------------------------------
 // Head dimension 16 is exactly one k-step of mma.m16n8k16: S = Q K^T for 16 queries x 64 keys is 8 MMAs, O += P V another 8, with P
 // handed from the accumulator layout to the A-operand layout in registers (two adjacent 16x8 accumulator tiles are one 16x16 A tile).
-// Fragments are loaded straight from global memory (the 32-byte head slice of a row is one sector; K and V of one (env, head) are 3 kB and
-// stay in L1 across the query tiles); online softmax over key blocks of 64, so any nk.  No shared memory, no block barrier.
+// K and V rows of the env (all heads, 256 bytes per row) are staged in shared memory with coalesced 16-byte loads, rows padded to 272
+// bytes so that the fragment reads (8 rows x 4 words per instruction) hit 32 different banks; Q fragments come straight from global
+// memory (a 32-byte head slice per row), the next query tile's while this one is computed.  Online softmax over key blocks of 64, so
+// any nk that fits in shared memory.
+// History (profiles/r13_policy_experiments.txt): a CUDA-core version (lane per query, K / V broadcast from shared memory) and a first
+// tensor-core version that loaded every fragment from global memory per query tile both took 298 us for 8,192 envs of 51 x 51.
 // (tcgen05 has nothing to offer a 51 x 51 x 16 problem: its smallest tile is M = 64 with operands staged through shared memory by TMA.)
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -190,30 +115,71 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t ld32(const uint16_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 
-__global__ void __launch_bounds__(256) k_attention_mma(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
-                                                       const uint16_t* __restrict__ v, int ldkv, uint16_t* __restrict__ out, int ldo,
-                                                       int nq, int nk, float scale_log2e) {
+constexpr int KV_LD = 136;                                                   // shared-memory row stride in elements: 256 + 16 bytes
+
+// ONE: nk <= 64 -- a single key block whose K and V fragments are read once, before the query tiles
+template <bool ONE>
+__global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
+                                                          const uint16_t* __restrict__ v, int ldkv, uint16_t* __restrict__ out, int ldo,
+                                                          int nq, int nk, float scale_log2e) {
+    extern __shared__ uint4 smem4[];
+    uint16_t* Ks = reinterpret_cast<uint16_t*>(smem4);
+    uint16_t* Vs = Ks + (size_t)nk * KV_LD;
     const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
     const uint16_t* qb = q + (size_t)b * nq * ldq + h * D;
-    const uint16_t* kb = k + (size_t)b * nk * ldkv + h * D;
-    const uint16_t* vb = v + (size_t)b * nk * ldkv + h * D;
     uint16_t* ob = out + (size_t)b * nq * ldo + h * D;
-    for (int m0 = 0; m0 < nq; m0 += 16) {
-        const int r0 = m0 + g, r1 = r0 + 8;                                   // the two query rows this lane holds pieces of
-        uint32_t a[4];                                                        // A fragment: {row r0, dims 2tg..}, {r1, same}, {r0, dims 8+2tg..}, {r1, same}
+    for (int idx = threadIdx.x; idx < nk * 16; idx += 256) {                  // 16 chunks of 16 bytes per 128-wide row
+        const int t = idx >> 4, c = idx & 15;
+        const size_t row = ((size_t)b * nk + t) * ldkv;
+        *reinterpret_cast<uint4*>(Ks + t * KV_LD + c * 8) = __ldg(reinterpret_cast<const uint4*>(k + row) + c);
+        *reinterpret_cast<uint4*>(Vs + t * KV_LD + c * 8) = __ldg(reinterpret_cast<const uint4*>(v + row) + c);
+    }
+    const uint16_t* kb = Ks + h * D;
+    const uint16_t* vb = Vs + h * D;
+    uint32_t kf[8][2], vf[4][2][2];
+    auto load_kv = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                                         // S tile j: keys k0 + 8j .. + 7; B fragment = K[key 8j + g][dims 2tg.., 8 + 2tg..]
+            const int key = k0 + 8 * j + g;
+            kf[j][0] = kf[j][1] = 0u;
+            if (key < nk) {
+                kf[j][0] = *reinterpret_cast<const uint32_t*>(kb + key * KV_LD + tg * 2);
+                kf[j][1] = *reinterpret_cast<const uint32_t*>(kb + key * KV_LD + tg * 2 + 8);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {                                      // P V step kk: B fragment = V[keys key0, key0 + 1 | key0 + 8, key0 + 9][dim 8nt + g]
+            const int key0 = k0 + 16 * kk + tg * 2;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint16_t* vp = vb + key0 * KV_LD + nt * 8 + g;
+                const uint32_t v00 = key0 < nk ? vp[0] : 0, v01 = key0 + 1 < nk ? vp[KV_LD] : 0;
+                const uint32_t v10 = key0 + 8 < nk ? vp[8 * KV_LD] : 0, v11 = key0 + 9 < nk ? vp[9 * KV_LD] : 0;
+                vf[kk][nt][0] = v00 | (v01 << 16); vf[kk][nt][1] = v10 | (v11 << 16);
+            }
+        }
+    };
+    auto load_q = [&](int m0, uint32_t (&a)[4]) {                             // A fragment: {row r0, dims 2tg..}, {r1, same}, {r0, dims 8 + 2tg..}, {r1, same}
+        const int r0 = m0 + g, r1 = r0 + 8;
         a[0] = r0 < nq ? ld32(qb + (size_t)r0 * ldq + tg * 2) : 0u; a[1] = r1 < nq ? ld32(qb + (size_t)r1 * ldq + tg * 2) : 0u;
         a[2] = r0 < nq ? ld32(qb + (size_t)r0 * ldq + tg * 2 + 8) : 0u; a[3] = r1 < nq ? ld32(qb + (size_t)r1 * ldq + tg * 2 + 8) : 0u;
+    };
+    uint32_t a[4], an[4] = {0u, 0u, 0u, 0u};
+    load_q(0, a);
+    __syncthreads();
+    if (ONE) load_kv(0);
+    for (int m0 = 0; m0 < nq; m0 += 16) {
+        const int r0 = m0 + g, r1 = r0 + 8;                                   // the two query rows this lane holds pieces of
+        if (m0 + 16 < nq) load_q(m0 + 16, an);
         float mrun0 = -1e30f, mrun1 = -1e30f, l0 = 0.f, l1 = 0.f;              // running maxima (quad-uniform), per-lane partial denominators
         float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // O accumulators: dims 8nt + 2tg + {0,1}, rows r0 (0,1) and r1 (2,3)
         for (int k0 = 0; k0 < nk; k0 += 64) {
+            if (!ONE) load_kv(k0);
             float s[8][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {                                     // S tile j: keys k0 + 8j .. + 7; B fragment = K[key 8j + g][dims 2tg.., 8 + 2tg..]
-                const int key = k0 + 8 * j + g;
-                uint32_t b0 = 0u, b1 = 0u;
-                if (key < nk) { b0 = ld32(kb + (size_t)key * ldkv + tg * 2); b1 = ld32(kb + (size_t)key * ldkv + tg * 2 + 8); }
+            for (int j = 0; j < 8; ++j) {
                 s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-                if (k0 + 8 * j < nk) mma16816(s[j], a, b0, b1);               // warp-uniform
+                if (k0 + 8 * j < nk) mma16816(s[j], a, kf[j][0], kf[j][1]);   // warp-uniform
             }
             float mx0 = -1e30f, mx1 = -1e30f;
 #pragma unroll
@@ -241,14 +207,8 @@ __global__ void __launch_bounds__(256) k_attention_mma(const uint16_t* __restric
                     uint32_t pa[4];
                     pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]); pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
                     pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]); pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-                    const int key0 = k0 + 16 * kk + tg * 2;                   // B fragment = V[keys key0, key0 + 1 | key0 + 8, key0 + 9][dim 8nt + g]
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const uint16_t* vp = vb + (size_t)key0 * ldkv + nt * 8 + g;
-                        const uint32_t v00 = key0 < nk ? __ldg(vp) : 0, v01 = key0 + 1 < nk ? __ldg(vp + ldkv) : 0;
-                        const uint32_t v10 = key0 + 8 < nk ? __ldg(vp + 8 * (size_t)ldkv) : 0, v11 = key0 + 9 < nk ? __ldg(vp + 9 * (size_t)ldkv) : 0;
-                        mma16816(o[nt], pa, v00 | (v01 << 16), v10 | (v11 << 16));
-                    }
+                    mma16816(o[0], pa, vf[kk][0][0], vf[kk][0][1]);
+                    mma16816(o[1], pa, vf[kk][1][0], vf[kk][1][1]);
                 }
             }
         }
@@ -260,6 +220,8 @@ __global__ void __launch_bounds__(256) k_attention_mma(const uint16_t* __restric
             if (r0 < nq) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * ldo + nt * 8 + tg * 2) = pack2(o[nt][0] * i0, o[nt][1] * i0);
             if (r1 < nq) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * ldo + nt * 8 + tg * 2) = pack2(o[nt][2] * i1, o[nt][3] * i1);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = an[i];
     }
 }
 
@@ -357,6 +319,71 @@ __global__ void __launch_bounds__(256) k_gate(const uint4* __restrict__ wv, uint
     }
 }
 
+// ---- gated FFN, first half: out = sigmoid(x W^T) * (x V^T) in ONE kernel (attention.py:164-167) ------------------------------------------
+// torch.mm + k_gate writes the [rows, 1024] pre-activations to HBM and reads them back (856 + 856 MB per 51-token layer of 8,192 envs,
+// 463 us); here they never leave the accumulators.  Legacy tensor path (mma.m16n8k16, 545 TFLOP/s measured on this GPU with the B
+// fragment re-read from shared memory per MMA, profiles/r13b_mma_rate.txt) -- the tile is 128 rows x K = 128, far below what tcgen05 + TMA
+// need to pay off, and the kernel is bound by its 428 MB of output anyway.
+// Block = 128 rows, warp = 16 rows whose A fragments (K = 128: 8 k-steps) stay in registers for the whole kernel; the weights (nn.Linear
+// layout [512, 128]: exactly the "col" B operand) stream through shared memory in 16 chunks of 32 gate columns (W and V rows of the
+// chunk, 16 kB), double-buffered with cp.async; rows padded to 272 bytes so that a fragment read hits 32 banks.
+constexpr int FF_ROWS = 128, FF_NC = 32, FF_LD = 136;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2) k_ffn_gate(const uint16_t* __restrict__ x, const uint16_t* __restrict__ wg, uint16_t* __restrict__ out,
+                                                     long rows) {
+    __shared__ __align__(16) uint16_t bs[2][2][FF_NC * FF_LD];               // [stage][W | V][32 weight rows x 136]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const long r0 = (long)blockIdx.x * FF_ROWS + warp * 16 + g, r1 = r0 + 8;
+    auto stage = [&](int c, int buf) {                                        // 2 matrices x 32 rows x 16 chunks of 16 bytes, 4 per thread
+        for (int i = threadIdx.x; i < 2 * FF_NC * 16; i += 256) {
+            const int mat = i >> 9, r = (i >> 4) & 31, ch = i & 15;
+            cp_async16(&bs[buf][mat][r * FF_LD + ch * 8], wg + ((size_t)mat * HID + c * FF_NC + r) * E + ch * 8);
+        }
+        cp_async_commit();
+    };
+    stage(0, 0);
+    uint32_t a[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        a[ks][0] = r0 < rows ? ld32(x + r0 * E + ks * 16 + tg * 2) : 0u; a[ks][1] = r1 < rows ? ld32(x + r1 * E + ks * 16 + tg * 2) : 0u;
+        a[ks][2] = r0 < rows ? ld32(x + r0 * E + ks * 16 + tg * 2 + 8) : 0u; a[ks][3] = r1 < rows ? ld32(x + r1 * E + ks * 16 + tg * 2 + 8) : 0u;
+    }
+    for (int c = 0; c < HID / FF_NC; ++c) {
+        if (c + 1 < HID / FF_NC) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();                                                      // chunk c has landed for every thread
+        const uint16_t* bw = bs[c & 1][0] + g * FF_LD + tg * 2;
+        const uint16_t* bv = bs[c & 1][1] + g * FF_LD + tg * 2;
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {                                  // B fragment = weight[column 8nt + g][k 16ks + 2tg.., + 8]
+                const uint16_t* pw = bw + nt * 8 * FF_LD + ks * 16;
+                const uint16_t* pv = bv + nt * 8 * FF_LD + ks * 16;
+                mma16816(acc[nt], a[ks], *reinterpret_cast<const uint32_t*>(pw), *reinterpret_cast<const uint32_t*>(pw + 8));
+                mma16816(acc[4 + nt], a[ks], *reinterpret_cast<const uint32_t*>(pv), *reinterpret_cast<const uint32_t*>(pv + 8));
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {                                      // accumulator (row g | g + 8, columns 8nt + 2tg + {0, 1})
+            const int col = c * FF_NC + nt * 8 + tg * 2;
+            const float y0 = acc[4 + nt][0] / (1.f + __expf(-acc[nt][0])), y1 = acc[4 + nt][1] / (1.f + __expf(-acc[nt][1]));
+            const float y2 = acc[4 + nt][2] / (1.f + __expf(-acc[nt][2])), y3 = acc[4 + nt][3] / (1.f + __expf(-acc[nt][3]));
+            if (r0 < rows) *reinterpret_cast<uint32_t*>(out + r0 * HID + col) = pack2(y0, y1);
+            if (r1 < rows) *reinterpret_cast<uint32_t*>(out + r1 * HID + col) = pack2(y2, y3);
+        }
+        __syncthreads();                                                      // everybody is done with this buffer before chunk c + 2 overwrites it
+    }
+}
+
 // ---- pointer head: warp per env; the 128-wide dot products are warp-cooperative (one coalesced 256-byte row per load) ---------------------
 __global__ void __launch_bounds__(256) k_pointer(const uint2* __restrict__ qk, const uint2* __restrict__ feat, const uint8_t* __restrict__ mask,
                                                  float* __restrict__ logp, int B, int n, float norm, float clip) {
@@ -431,27 +458,25 @@ int dcmp_embed(const float* x, const float* w, const float* bias, uint16_t* out,
 int dcmp_attention(const uint16_t* q, int ldq, const uint16_t* k, const uint16_t* v, int ldkv, uint16_t* out, int ldo, int B, int nq, int nk,
                    float scale, void* stream) {
     if (!q || !k || !v || !out) return fail(-1, "dcmp_attention: null pointer");
-    if (B < 0 || nq < 1 || nk < 1 || nk > ATT_MAX_NK) return fail(-2, "dcmp_attention: need B >= 0, nq >= 1, 1 <= nk <= 220");
+    if (B < 0 || nq < 1 || nk < 1 || nk > ATT_MAX_NK) return fail(-2, "dcmp_attention: need B >= 0, nq >= 1, 1 <= nk <= 400");
     if ((ldq | ldkv | ldo) & 7 || ldq < E || ldkv < E || ldo < E || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out))
         return fail(-1, "dcmp_attention: row strides must be multiples of 8 elements (>= 128) and pointers 16-byte aligned");
     if (B == 0) return 0;
     if (!sm_count()) return fail(-3, "dcmp_attention: no CUDA device (there is no CPU fallback)");
-    const int nkp = (nk + 3) & ~3;
-    const size_t smem = (size_t)2 * H * nkp * D * sizeof(float);
+    const size_t smem = (size_t)2 * nk * KV_LD * sizeof(uint16_t);
     static bool opted[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
     if (!opted[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * H * ATT_MAX_NK * D * (int)sizeof(float));
-        if (e != cudaSuccess) return fail(-4, "cudaFuncSetAttribute(k_attention)", e);
+        const int most = 2 * ATT_MAX_NK * KV_LD * (int)sizeof(uint16_t);
+        cudaError_t e = cudaFuncSetAttribute(k_attention_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        if (e != cudaSuccess) return fail(-4, "cudaFuncSetAttribute(k_attention_mma)", e);
         opted[dev] = true;
     }
-    static const bool simt = getenv("DCMP_ATTENTION_SIMT") != nullptr;       // development A/B: the CUDA-core kernel
-    if (!simt) {
-        k_attention_mma<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
-        return launched("k_attention_mma");
-    }
-    k_attention<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
-    return launched("k_attention");
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nk <= 64) k_attention_mma<true><<<B, 256, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
+    else k_attention_mma<false><<<B, 256, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
+    return launched("k_attention_mma");
 }
 
 int dcmp_attention_q1(const uint16_t* q, int ldq, const uint16_t* k, const uint16_t* v, int ldkv, const uint8_t* mask, uint16_t* out, int ldo,
@@ -489,6 +514,15 @@ int dcmp_gate(const uint16_t* wv, uint16_t* out, long rows, void* stream) {
     k_gate<<<(int)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(wv),
                                                                                           reinterpret_cast<uint4*>(out), chunks);
     return launched("k_gate");
+}
+
+int dcmp_ffn_gate(const uint16_t* x, const uint16_t* wg, uint16_t* out, long rows, void* stream) {
+    if (!x || !wg || !out || rows < 0) return fail(-1, "dcmp_ffn_gate: null pointer or negative row count");
+    if (!aligned16(x) || !aligned16(wg) || !aligned16(out)) return fail(-1, "dcmp_ffn_gate: pointers must be 16-byte aligned");
+    if (rows == 0) return 0;
+    if (!sm_count()) return fail(-3, "dcmp_ffn_gate: no CUDA device (there is no CPU fallback)");
+    k_ffn_gate<<<(unsigned)((rows + FF_ROWS - 1) / FF_ROWS), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, wg, out, rows);
+    return launched("k_ffn_gate");
 }
 
 int dcmp_pointer(const uint16_t* qk, const uint16_t* feat, const uint8_t* mask, float* logp, int B, int n, float norm, float clip, void* stream) {

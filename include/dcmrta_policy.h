@@ -8,7 +8,7 @@
  * (torch.mm -> cuBLASLt) are untouched; dcmrta_b200/policy_fused.py calls these entry points between the GEMMs of a no-grad
  * rollout forward, where the reference module (attention.py) runs eager elementwise / softmax / LayerNorm kernels.
  *
- * Conventions (as include/dcmrta.h): return 0 or a negative code (-1 argument, -2 shape, -4 CUDA; dcmp_last_error() has the
+ * Conventions (as include/dcmrta.h): return 0 or a negative code (-1 argument, -2 shape, -3 no device, -4 CUDA; dcmp_last_error() has the
  * text); plain device pointers, no torch types; `stream` is a cudaStream_t passed as void*; every call is asynchronous on it
  * (and capturable in a CUDA graph).  Activations are bf16 (raw uint16 storage), row-major, one row per token, rows of one env
  * contiguous: row = env * n + token.  Fixed by the reference network (parameters.py:9 EMBEDDING_DIM = 128, attention.py:251-258
@@ -32,7 +32,7 @@ int dcmp_embed(const float* x_d, const float* w_d, const float* bias_d, uint16_t
 /* attention.py:106-153  MultiHeadAttention.forward after the projections, without a mask (the worker never pads, worker.py:63-67):
  * per env and head, out = softmax(scale * Q K^T) V.  Q rows [B * nq] with stride ldq, K and V rows [B * nk] with stride ldkv, head h
  * in columns 16 h .. 16 h + 15 of each; out rows [B * nq] with stride ldo, heads concatenated (the layout W_out consumes).
- * nk <= 220 (K and V of one env are staged in shared memory as fp32). */
+ * nk <= 400 (K and V rows of one env are staged in shared memory). */
 int dcmp_attention(const uint16_t* q_d, int ldq, const uint16_t* k_d, const uint16_t* v_d, int ldkv, uint16_t* out_d, int ldo,
                    int B, int nq, int nk, float scale, void* stream);
 
@@ -48,6 +48,11 @@ int dcmp_add_layernorm(const uint16_t* x_d, const uint16_t* res_d, const float* 
 
 /* attention.py:164-168 GateFFNDense between its GEMMs: wv rows hold [W x | V x] (2 x 512); out[r, :] = sigmoid(W x) * (V x). */
 int dcmp_gate(const uint16_t* wv_d, uint16_t* out_d, long rows, void* stream);
+
+/* attention.py:164-167 the same gate fused with its two GEMMs: out[r, :] = sigmoid(x[r, :] W^T) * (x[r, :] V^T), x rows [rows, 128],
+ * wg [1024, 128] = the nn.Linear weights W (rows 0..511) and V (rows 512..1023) as stored (attention.py:159-160), out [rows, 512].
+ * The [rows, 1024] pre-activations never reach memory. */
+int dcmp_ffn_gate(const uint16_t* x_d, const uint16_t* wg_d, uint16_t* out_d, long rows, void* stream);
 
 /* attention.py:48-81 SingleHeadAttention (the pointer head) after its query projection: u[b, t] = clip * tanh(norm * qk[b, :] . feat[b, t, :]),
  * forbidden keys (mask 1) set to -1e4 (:78-80), logp = log_softmax(u) in fp32.  qk [B, 128] is the current state times W_query W_key^T

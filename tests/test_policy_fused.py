@@ -85,7 +85,7 @@ def test_policy_header_symbols_are_exported_and_bound():
     from dcmrta_b200 import policy_fused as pf
     L = pf.lib()
     names = declared_symbols()
-    assert len(names) == 8
+    assert len(names) == 9
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/dcmrta_policy.h but not exported"
     assert sorted(pf.SIGNATURES) == names
@@ -105,7 +105,7 @@ def test_policy_kernels_validate_arguments_and_have_no_cpu_fallback():
     L = pf.lib()
     buf = (C.c_uint16 * 4096)()
     p = C.addressof(buf) + (-C.addressof(buf)) % 16
-    assert L.dcmp_attention(p, 128, p, p, 128, p, 128, 1, 1, 221, 0.25, None) == -2          # nk over the shared-memory budget
+    assert L.dcmp_attention(p, 128, p, p, 128, p, 128, 1, 1, 401, 0.25, None) == -2          # nk over the shared-memory budget
     assert L.dcmp_attention(p, 100, p, p, 128, p, 128, 1, 1, 4, 0.25, None) == -1            # row stride not a multiple of 8
     assert L.dcmp_attention(p + 2, 128, p, p, 128, p, 128, 1, 1, 4, 0.25, None) == -1        # misaligned
     assert L.dcmp_embed(p, p, p, p, 4, 7, None) == -2
@@ -189,6 +189,20 @@ def test_kernel_add_layernorm_gate_embed(rows):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rows", [1, 16, 127, 129, 4099, 8192 * 51])
+def test_kernel_ffn_gate(rows):
+    """GEMM + gate in one kernel against fp32 torch on the same bf16 operands"""
+    from dcmrta_b200.policy_fused import CudaOps, TorchOps
+    x = _bf(rows, 128, seed=10)
+    wg = _bf(1024, 128, seed=11, scale=1 / math.sqrt(128))
+    out = CudaOps().ffn_gate(x, wg, torch.full((rows, 512), 7.0, dtype=torch.bfloat16, device="cuda"))
+    n = min(rows, 20000)                                 # the fp32 reference of the full-size case on its first and last rows
+    for sl in (slice(0, n), slice(rows - n, rows)):
+        ref = TorchOps().ffn_gate(x[sl], wg, torch.empty(x[sl].shape[0], 512, device="cuda"))
+        _close(out[sl], ref, 1e-3, "ffn_gate")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("B,n", [(11, 51), (8, 21), (3, 201), (2, 256), (9, 1), (5, 33)])
 def test_kernel_pointer(B, n):
     from dcmrta_b200.policy_fused import CudaOps, TorchOps
@@ -220,7 +234,8 @@ def test_fused_forward_matches_the_module(A, T, B):
     ok = ~mask
     assert float((out - spec).abs()[ok].max()) < 0.08, "CUDA kernels vs the same dataflow in torch bf16"
     assert float((out - ref).abs()[ok].max()) < 0.1, "bf16 fused path vs the fp32 module"
-    assert float((out.argmax(1) == ref.argmax(1)).float().mean()) > 0.9
+    chosen = ref.gather(1, out.argmax(1, keepdim=True)).squeeze(1)       # the fused greedy choice, scored by the fp32 module
+    assert float((ref.max(1).values - chosen).max()) < 0.1
     assert torch.allclose(out.exp().sum(1), torch.ones(B, device="cuda"), atol=1e-3)
     # refresh after an update of the parameters: same buffers, new values
     ptrs = {k: v.data_ptr() for k, v in fused.P.items() if torch.is_tensor(v)}
