@@ -117,8 +117,10 @@ __device__ __forceinline__ uint32_t ld32(const uint16_t* p) { return __ldg(reint
 
 constexpr int KV_LD = 136;                                                   // shared-memory row stride in elements: 256 + 16 bytes
 
-// ONE: nk <= 64 -- a single key block whose K and V fragments are read once, before the query tiles
-template <bool ONE>
+// NT = S tiles (of 8 keys) per key block.  nk <= 64: one block of exactly ceil(nk / 8) tiles whose K and V fragments are read once,
+// before the query tiles (ONE) -- a 20-key memory costs 3 tiles of softmax arithmetic and 14 fragment registers, not 8 and 32.
+// nk > 64: blocks of 8 tiles, fragments re-read per block and query tile.
+template <int NT, bool ONE>
 __global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ k,
                                                           const uint16_t* __restrict__ v, int ldkv, uint16_t* __restrict__ out, int ldo,
                                                           int nq, int nk, float scale_log2e) {
@@ -136,10 +138,11 @@ __global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __rest
     }
     const uint16_t* kb = Ks + h * D;
     const uint16_t* vb = Vs + h * D;
-    uint32_t kf[8][2], vf[4][2][2];
+    constexpr int KK = (NT + 1) / 2;                                         // P V steps of 16 keys
+    uint32_t kf[NT][2], vf[KK][2][2];
     auto load_kv = [&](int k0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                                         // S tile j: keys k0 + 8j .. + 7; B fragment = K[key 8j + g][dims 2tg.., 8 + 2tg..]
+        for (int j = 0; j < NT; ++j) {                                        // S tile j: keys k0 + 8j .. + 7; B fragment = K[key 8j + g][dims 2tg.., 8 + 2tg..]
             const int key = k0 + 8 * j + g;
             kf[j][0] = kf[j][1] = 0u;
             if (key < nk) {
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __rest
             }
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {                                      // P V step kk: B fragment = V[keys key0, key0 + 1 | key0 + 8, key0 + 9][dim 8nt + g]
+        for (int kk = 0; kk < KK; ++kk) {                                     // P V step kk: B fragment = V[keys key0, key0 + 1 | key0 + 8, key0 + 9][dim 8nt + g]
             const int key0 = k0 + 16 * kk + tg * 2;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
@@ -173,17 +176,17 @@ __global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __rest
         if (m0 + 16 < nq) load_q(m0 + 16, an);
         float mrun0 = -1e30f, mrun1 = -1e30f, l0 = 0.f, l1 = 0.f;              // running maxima (quad-uniform), per-lane partial denominators
         float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // O accumulators: dims 8nt + 2tg + {0,1}, rows r0 (0,1) and r1 (2,3)
-        for (int k0 = 0; k0 < nk; k0 += 64) {
+        for (int k0 = 0; k0 < nk; k0 += 8 * NT) {
             if (!ONE) load_kv(k0);
-            float s[8][4];
+            float s[2 * KK][4];                                               // (an odd NT leaves one all-zero tile for the last P V step)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 2 * KK; ++j) {
                 s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-                if (k0 + 8 * j < nk) mma16816(s[j], a, kf[j][0], kf[j][1]);   // warp-uniform
+                if (j < NT && k0 + 8 * j < nk) mma16816(s[j], a, kf[j][0], kf[j][1]);   // warp-uniform
             }
             float mx0 = -1e30f, mx1 = -1e30f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NT; ++j) {
                 const int kc = k0 + 8 * j + tg * 2;                           // this lane's two key columns of tile j
                 s[j][0] = kc < nk ? s[j][0] * scale_log2e : -1e30f; s[j][1] = kc + 1 < nk ? s[j][1] * scale_log2e : -1e30f;
                 s[j][2] = kc < nk ? s[j][2] * scale_log2e : -1e30f; s[j][3] = kc + 1 < nk ? s[j][3] * scale_log2e : -1e30f;
@@ -197,12 +200,12 @@ __global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __rest
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {                                     // keys past nk: 2^(-1e30 - m) = 0
+            for (int j = 0; j < NT; ++j) {                                    // keys past nk: 2^(-1e30 - m) = 0
                 s[j][0] = ex2(s[j][0] - mn0); s[j][1] = ex2(s[j][1] - mn0); s[j][2] = ex2(s[j][2] - mn1); s[j][3] = ex2(s[j][3] - mn1);
                 l0 += s[j][0] + s[j][1]; l1 += s[j][2] + s[j][3];
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {                                  // O += P V, 16 keys per step: accumulator tiles 2kk, 2kk + 1 -> one A fragment
+            for (int kk = 0; kk < KK; ++kk) {                                 // O += P V, 16 keys per step: accumulator tiles 2kk, 2kk + 1 -> one A fragment
                 if (k0 + 16 * kk < nk) {                                      // warp-uniform
                     uint32_t pa[4];
                     pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]); pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(256) k_gate(const uint4* __restrict__ wv, uint
         float a[8], b[8], y[8];
         unpack8(__ldg(wv + r * 128 + c), a); unpack8(__ldg(wv + r * 128 + 64 + c), b);
 #pragma unroll
-        for (int d = 0; d < 8; ++d) y[d] = b[d] / (1.f + __expf(-a[d]));
+        for (int d = 0; d < 8; ++d) y[d] = __fdividef(b[d], 1.f + __expf(-a[d]));
         out[i] = pack8(y);
     }
 }
@@ -375,8 +378,8 @@ __global__ void __launch_bounds__(256, 2) k_ffn_gate(const uint16_t* __restrict_
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {                                      // accumulator (row g | g + 8, columns 8nt + 2tg + {0, 1})
             const int col = c * FF_NC + nt * 8 + tg * 2;
-            const float y0 = acc[4 + nt][0] / (1.f + __expf(-acc[nt][0])), y1 = acc[4 + nt][1] / (1.f + __expf(-acc[nt][1]));
-            const float y2 = acc[4 + nt][2] / (1.f + __expf(-acc[nt][2])), y3 = acc[4 + nt][3] / (1.f + __expf(-acc[nt][3]));
+            const float y0 = __fdividef(acc[4 + nt][0], 1.f + __expf(-acc[nt][0])), y1 = __fdividef(acc[4 + nt][1], 1.f + __expf(-acc[nt][1]));
+            const float y2 = __fdividef(acc[4 + nt][2], 1.f + __expf(-acc[nt][2])), y3 = __fdividef(acc[4 + nt][3], 1.f + __expf(-acc[nt][3]));
             if (r0 < rows) *reinterpret_cast<uint32_t*>(out + r0 * HID + col) = pack2(y0, y1);
             if (r1 < rows) *reinterpret_cast<uint32_t*>(out + r1 * HID + col) = pack2(y2, y3);
         }
@@ -468,14 +471,18 @@ int dcmp_attention(const uint16_t* q, int ldq, const uint16_t* k, const uint16_t
     int dev = 0; cudaGetDevice(&dev);
     if (!opted[dev]) {
         const int most = 2 * ATT_MAX_NK * KV_LD * (int)sizeof(uint16_t);
-        cudaError_t e = cudaFuncSetAttribute(k_attention_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        cudaError_t e = cudaFuncSetAttribute(k_attention_mma<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
         if (e != cudaSuccess) return fail(-4, "cudaFuncSetAttribute(k_attention_mma)", e);
-        opted[dev] = true;
+        opted[dev] = true;                                                   // (nk <= 64 needs 34 kB at most: no opt-in)
     }
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (nk <= 64) k_attention_mma<true><<<B, 256, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
-    else k_attention_mma<false><<<B, 256, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
+#define DCMP_ATT(NT) k_attention_mma<NT, true><<<B, 256, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E)
+    switch ((nk + 7) / 8) {
+        case 1: DCMP_ATT(1); break; case 2: DCMP_ATT(2); break; case 3: DCMP_ATT(3); break; case 4: DCMP_ATT(4); break;
+        case 5: DCMP_ATT(5); break; case 6: DCMP_ATT(6); break; case 7: DCMP_ATT(7); break; case 8: DCMP_ATT(8); break;
+        default: k_attention_mma<8, false><<<B, 256, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, nq, nk, scale * LOG2E);
+    }
+#undef DCMP_ATT
     return launched("k_attention_mma");
 }
 

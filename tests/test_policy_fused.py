@@ -139,7 +139,8 @@ def _close(out, ref, atol, what):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,nq,nk", [(5, 51, 51), (3, 20, 20), (4, 51, 20), (2, 101, 30), (2, 64, 201), (1, 1, 1), (3, 33, 7)])
+@pytest.mark.parametrize("B,nq,nk", [(5, 51, 51), (3, 20, 20), (4, 51, 20), (2, 101, 30), (2, 64, 201), (1, 1, 1), (3, 33, 7),
+                                     (2, 17, 9), (2, 5, 33), (2, 48, 41), (2, 40, 64), (2, 16, 65), (1, 70, 400)])
 def test_kernel_attention(B, nq, nk):
     from dcmrta_b200.policy_fused import CudaOps, TorchOps
     qkv = _bf(B * nq, 384, seed=1)                       # q as a column slice of a wider matrix, k / v of another
