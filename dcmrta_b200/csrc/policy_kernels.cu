@@ -184,24 +184,27 @@ __global__ void __launch_bounds__(256, 2) k_attention_mma(const uint16_t* __rest
                 s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
                 if (j < NT && k0 + 8 * j < nk) mma16816(s[j], a, kf[j][0], kf[j][1]);   // warp-uniform
             }
-            float mx0 = -1e30f, mx1 = -1e30f;
+            float mx0 = -1e30f, mx1 = -1e30f;                                  // maxima of the RAW scores (the scale is positive); scaled once, below
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const int kc = k0 + 8 * j + tg * 2;                           // this lane's two key columns of tile j
-                s[j][0] = kc < nk ? s[j][0] * scale_log2e : -1e30f; s[j][1] = kc + 1 < nk ? s[j][1] * scale_log2e : -1e30f;
-                s[j][2] = kc < nk ? s[j][2] * scale_log2e : -1e30f; s[j][3] = kc + 1 < nk ? s[j][3] * scale_log2e : -1e30f;
+                if (!ONE || j == NT - 1) {                                    // only the last tile of a single block can hold keys past nk
+                    const int kc = k0 + 8 * j + tg * 2;                       // this lane's two key columns of tile j
+                    if (kc >= nk) s[j][0] = s[j][2] = -1e30f;
+                    if (kc + 1 >= nk) s[j][1] = s[j][3] = -1e30f;
+                }
                 mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
             }
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            const float mn0 = fmaxf(mrun0, mx0), mn1 = fmaxf(mrun1, mx1);
+            const float mn0 = fmaxf(mrun0, mx0 * scale_log2e), mn1 = fmaxf(mrun1, mx1 * scale_log2e);
             const float c0 = ex2(mrun0 - mn0), c1 = ex2(mrun1 - mn1);          // 0 on the first block, where everything it scales is 0
             mrun0 = mn0; mrun1 = mn1; l0 *= c0; l1 *= c1;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {                                    // keys past nk: 2^(-1e30 - m) = 0
-                s[j][0] = ex2(s[j][0] - mn0); s[j][1] = ex2(s[j][1] - mn0); s[j][2] = ex2(s[j][2] - mn1); s[j][3] = ex2(s[j][3] - mn1);
+            for (int j = 0; j < NT; ++j) {                                    // p = 2^(s scale log2(e) - m); keys past nk: 2^(-1e30 ...) = 0
+                s[j][0] = ex2(fmaf(s[j][0], scale_log2e, -mn0)); s[j][1] = ex2(fmaf(s[j][1], scale_log2e, -mn0));
+                s[j][2] = ex2(fmaf(s[j][2], scale_log2e, -mn1)); s[j][3] = ex2(fmaf(s[j][3], scale_log2e, -mn1));
                 l0 += s[j][0] + s[j][1]; l1 += s[j][2] + s[j][3];
             }
 #pragma unroll
@@ -336,6 +339,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(256, 2) k_ffn_gate(const uint16_t* __restrict__ x, const uint16_t* __restrict__ wg, uint16_t* __restrict__ out,
@@ -360,19 +366,25 @@ __global__ void __launch_bounds__(256, 2) k_ffn_gate(const uint16_t* __restrict_
     for (int c = 0; c < HID / FF_NC; ++c) {
         if (c + 1 < HID / FF_NC) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();                                                      // chunk c has landed for every thread
-        const uint16_t* bw = bs[c & 1][0] + g * FF_LD + tg * 2;
-        const uint16_t* bv = bs[c & 1][1] + g * FF_LD + tg * 2;
+        // B fragments by ldmatrix.x4: four 8x8 matrices = {columns 8(2p) .., k 16ks .. + 7}, {same columns, k + 8}, {columns 8(2p + 1) .., k ..},
+        // {same, k + 8} = b0, b1 of two adjacent n-tiles; lane l supplies the address of row l % 8 of matrix l / 8.  (One 32-bit shared load
+        // per fragment register left the kernel waiting on the shared-memory queue: mio_throttle 3.0 per issue, profiles/r13d.)
+        const int lrow = ((lane >> 4) & 1) * 8 + (lane & 7), lk = ((lane >> 3) & 1) * 8;
+        const uint32_t sw = (uint32_t)__cvta_generic_to_shared(bs[c & 1][0] + lrow * FF_LD + lk);
+        const uint32_t sv = (uint32_t)__cvta_generic_to_shared(bs[c & 1][1] + lrow * FF_LD + lk);
         float acc[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {                                  // B fragment = weight[column 8nt + g][k 16ks + 2tg.., + 8]
-                const uint16_t* pw = bw + nt * 8 * FF_LD + ks * 16;
-                const uint16_t* pv = bv + nt * 8 * FF_LD + ks * 16;
-                mma16816(acc[nt], a[ks], *reinterpret_cast<const uint32_t*>(pw), *reinterpret_cast<const uint32_t*>(pw + 8));
-                mma16816(acc[4 + nt], a[ks], *reinterpret_cast<const uint32_t*>(pv), *reinterpret_cast<const uint32_t*>(pv + 8));
+            for (int pr = 0; pr < 2; ++pr) {                                  // n-tiles 2pr, 2pr + 1 of W and of V
+                uint32_t w[4], u[4];
+                const uint32_t off = (uint32_t)((pr * 16 * FF_LD + ks * 16) * 2);
+                ldmatrix_x4(w, sw + off);
+                ldmatrix_x4(u, sv + off);
+                mma16816(acc[2 * pr], a[ks], w[0], w[1]); mma16816(acc[2 * pr + 1], a[ks], w[2], w[3]);
+                mma16816(acc[4 + 2 * pr], a[ks], u[0], u[1]); mma16816(acc[4 + 2 * pr + 1], a[ks], u[2], u[3]);
             }
         }
 #pragma unroll
