@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(256) k_add_layernorm(const uint2* x, const uin
     }
 }
 
+// A version of this fused with its GEMM (mma.m16n8k16, A fragments in registers, weights streamed through shared memory with cp.async,
+// B fragments by ldmatrix.x4; commit "ffn_gate: B fragments by ldmatrix.x4") kept the [rows, 1024] pre-activations out of HBM but ran at a
+// third of the legacy tensor rate: 1.47 ms per forward against 0.52 (cuBLASLt GEMM) + 0.74 (this kernel); profiles/r13_policy_experiments.txt.
 // ---- out = sigmoid(wv[:, :512]) * wv[:, 512:]: thread per 8 columns -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gate(const uint4* __restrict__ wv, uint4* __restrict__ out, long chunks) {
     const long stride = (long)gridDim.x * 256;
@@ -322,80 +325,6 @@ __global__ void __launch_bounds__(256) k_gate(const uint4* __restrict__ wv, uint
 #pragma unroll
         for (int d = 0; d < 8; ++d) y[d] = __fdividef(b[d], 1.f + __expf(-a[d]));
         out[i] = pack8(y);
-    }
-}
-
-// ---- gated FFN, first half: out = sigmoid(x W^T) * (x V^T) in ONE kernel (attention.py:164-167) ------------------------------------------
-// torch.mm + k_gate writes the [rows, 1024] pre-activations to HBM and reads them back (856 + 856 MB per 51-token layer of 8,192 envs,
-// 463 us); here they never leave the accumulators.  Legacy tensor path (mma.m16n8k16, 545 TFLOP/s measured on this GPU with the B
-// fragment re-read from shared memory per MMA, profiles/r13b_mma_rate.txt) -- the tile is 128 rows x K = 128, far below what tcgen05 + TMA
-// need to pay off, and the kernel is bound by its 428 MB of output anyway.
-// Block = 128 rows, warp = 16 rows whose A fragments (K = 128: 8 k-steps) stay in registers for the whole kernel; the weights (nn.Linear
-// layout [512, 128]: exactly the "col" B operand) stream through shared memory in 16 chunks of 32 gate columns (W and V rows of the
-// chunk, 16 kB), double-buffered with cp.async; rows padded to 272 bytes so that a fragment read hits 32 banks.
-constexpr int FF_ROWS = 128, FF_NC = 32, FF_LD = 136;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
-}
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(256, 2) k_ffn_gate(const uint16_t* __restrict__ x, const uint16_t* __restrict__ wg, uint16_t* __restrict__ out,
-                                                     long rows) {
-    __shared__ __align__(16) uint16_t bs[2][2][FF_NC * FF_LD];               // [stage][W | V][32 weight rows x 136]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-    const long r0 = (long)blockIdx.x * FF_ROWS + warp * 16 + g, r1 = r0 + 8;
-    auto stage = [&](int c, int buf) {                                        // 2 matrices x 32 rows x 16 chunks of 16 bytes, 4 per thread
-        for (int i = threadIdx.x; i < 2 * FF_NC * 16; i += 256) {
-            const int mat = i >> 9, r = (i >> 4) & 31, ch = i & 15;
-            cp_async16(&bs[buf][mat][r * FF_LD + ch * 8], wg + ((size_t)mat * HID + c * FF_NC + r) * E + ch * 8);
-        }
-        cp_async_commit();
-    };
-    stage(0, 0);
-    uint32_t a[8][4];
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-        a[ks][0] = r0 < rows ? ld32(x + r0 * E + ks * 16 + tg * 2) : 0u; a[ks][1] = r1 < rows ? ld32(x + r1 * E + ks * 16 + tg * 2) : 0u;
-        a[ks][2] = r0 < rows ? ld32(x + r0 * E + ks * 16 + tg * 2 + 8) : 0u; a[ks][3] = r1 < rows ? ld32(x + r1 * E + ks * 16 + tg * 2 + 8) : 0u;
-    }
-    for (int c = 0; c < HID / FF_NC; ++c) {
-        if (c + 1 < HID / FF_NC) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-        __syncthreads();                                                      // chunk c has landed for every thread
-        // B fragments by ldmatrix.x4: four 8x8 matrices = {columns 8(2p) .., k 16ks .. + 7}, {same columns, k + 8}, {columns 8(2p + 1) .., k ..},
-        // {same, k + 8} = b0, b1 of two adjacent n-tiles; lane l supplies the address of row l % 8 of matrix l / 8.  (One 32-bit shared load
-        // per fragment register left the kernel waiting on the shared-memory queue: mio_throttle 3.0 per issue, profiles/r13d.)
-        const int lrow = ((lane >> 4) & 1) * 8 + (lane & 7), lk = ((lane >> 3) & 1) * 8;
-        const uint32_t sw = (uint32_t)__cvta_generic_to_shared(bs[c & 1][0] + lrow * FF_LD + lk);
-        const uint32_t sv = (uint32_t)__cvta_generic_to_shared(bs[c & 1][1] + lrow * FF_LD + lk);
-        float acc[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {                                  // n-tiles 2pr, 2pr + 1 of W and of V
-                uint32_t w[4], u[4];
-                const uint32_t off = (uint32_t)((pr * 16 * FF_LD + ks * 16) * 2);
-                ldmatrix_x4(w, sw + off);
-                ldmatrix_x4(u, sv + off);
-                mma16816(acc[2 * pr], a[ks], w[0], w[1]); mma16816(acc[2 * pr + 1], a[ks], w[2], w[3]);
-                mma16816(acc[4 + 2 * pr], a[ks], u[0], u[1]); mma16816(acc[4 + 2 * pr + 1], a[ks], u[2], u[3]);
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {                                      // accumulator (row g | g + 8, columns 8nt + 2tg + {0, 1})
-            const int col = c * FF_NC + nt * 8 + tg * 2;
-            const float y0 = __fdividef(acc[4 + nt][0], 1.f + __expf(-acc[nt][0])), y1 = __fdividef(acc[4 + nt][1], 1.f + __expf(-acc[nt][1]));
-            const float y2 = __fdividef(acc[4 + nt][2], 1.f + __expf(-acc[nt][2])), y3 = __fdividef(acc[4 + nt][3], 1.f + __expf(-acc[nt][3]));
-            if (r0 < rows) *reinterpret_cast<uint32_t*>(out + r0 * HID + col) = pack2(y0, y1);
-            if (r1 < rows) *reinterpret_cast<uint32_t*>(out + r1 * HID + col) = pack2(y2, y3);
-        }
-        __syncthreads();                                                      // everybody is done with this buffer before chunk c + 2 overwrites it
     }
 }
 
@@ -533,15 +462,6 @@ int dcmp_gate(const uint16_t* wv, uint16_t* out, long rows, void* stream) {
     k_gate<<<(int)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(wv),
                                                                                           reinterpret_cast<uint4*>(out), chunks);
     return launched("k_gate");
-}
-
-int dcmp_ffn_gate(const uint16_t* x, const uint16_t* wg, uint16_t* out, long rows, void* stream) {
-    if (!x || !wg || !out || rows < 0) return fail(-1, "dcmp_ffn_gate: null pointer or negative row count");
-    if (!aligned16(x) || !aligned16(wg) || !aligned16(out)) return fail(-1, "dcmp_ffn_gate: pointers must be 16-byte aligned");
-    if (rows == 0) return 0;
-    if (!sm_count()) return fail(-3, "dcmp_ffn_gate: no CUDA device (there is no CPU fallback)");
-    k_ffn_gate<<<(unsigned)((rows + FF_ROWS - 1) / FF_ROWS), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, wg, out, rows);
-    return launched("k_ffn_gate");
 }
 
 int dcmp_pointer(const uint16_t* qk, const uint16_t* feat, const uint8_t* mask, float* logp, int B, int n, float norm, float clip, void* stream) {

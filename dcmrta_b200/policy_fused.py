@@ -23,7 +23,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import os
 
 import torch
 import torch.nn.functional as F
@@ -32,7 +31,6 @@ from . import build as _build
 
 E, H, D, HID = 128, 8, 16, 512
 _LIB = None
-SPLIT_FFN = bool(os.environ.get("DCMP_FFN_SPLIT"))
 
 vp, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_long
 # name -> (restype, argtypes); every symbol include/dcmrta_policy.h declares
@@ -42,7 +40,6 @@ SIGNATURES = {
     "dcmp_attention_q1": (i32, [vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, f32, vp]),
     "dcmp_add_layernorm": (i32, [vp, vp, vp, vp, vp, i64, f32, vp]),
     "dcmp_gate": (i32, [vp, vp, i64, vp]),
-    "dcmp_ffn_gate": (i32, [vp, vp, vp, i64, vp]),
     "dcmp_pointer": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp]),
     "dcmp_last_error": (C.c_char_p, []),
     "dcmp_version": (C.c_char_p, []),
@@ -124,12 +121,6 @@ class CudaOps:
         _check(lib().dcmp_gate(wv.data_ptr(), out.data_ptr(), wv.shape[0], _stream(out)))
         return out
 
-    def ffn_gate(self, x, wg, out):
-        assert x.is_contiguous() and wg.is_contiguous() and out.is_contiguous() and x.shape[1] == E and wg.shape == (2 * HID, E)
-        assert out.shape == (x.shape[0], HID)
-        _check(lib().dcmp_ffn_gate(x.data_ptr(), wg.data_ptr(), out.data_ptr(), x.shape[0], _stream(out)))
-        return out
-
     def pointer(self, qk, feat, mask, out, B, n, norm, clip):
         assert qk.is_contiguous() and feat.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
         assert mask is None or (mask.dtype == torch.uint8 and mask.is_contiguous() and mask.shape == (B, n))
@@ -174,10 +165,6 @@ class TorchOps:
 
     def gate(self, wv, out):
         return out.copy_(torch.sigmoid(wv[:, :self.HID].float()) * wv[:, self.HID:].float())
-
-    def ffn_gate(self, x, wg, out):
-        h = x.float() @ wg.float().t()
-        return out.copy_(torch.sigmoid(h[:, :self.HID]) * h[:, self.HID:])
 
     def pointer(self, qk, feat, mask, out, B, n, norm, clip):
         u = clip * torch.tanh(norm * torch.einsum("be,bne->bn", qk.float(), feat.float().view(B, n, self.E)))
@@ -233,7 +220,6 @@ def pack_parameters(net, dtype=torch.bfloat16, into: dict | None = None) -> dict
             put(name + ".out", mha.w_out.detach().reshape(-1, mha.embedding_dim))
             ffn, ln2 = layer.feedForward.DenseReluDense, layer.feedForward.layer_norm.normalizer
             put(name + ".wv", torch.cat([ffn.W.weight.t(), ffn.V.weight.t()], 1)); put(name + ".w2", ffn.W2.weight.t())
-            put(name + ".wg", torch.cat([ffn.W.weight, ffn.V.weight], 0))  # as stored, [1024, E]: the "col" operand of the fused GEMM + gate
             for tag, ln in (("ln1", ln1), ("ln2", ln2)):
                 put(f"{name}.{tag}.g", ln.weight, torch.float32); put(f"{name}.{tag}.b", ln.bias, torch.float32)
                 P[f"{name}.{tag}.eps"] = ln.eps
@@ -253,11 +239,8 @@ def _forward(ops, P, W, tasks, agents, mask_u8, names):
     ct = ops.embed(tasks.mean(1), P["task_embedding.w"], P["task_embedding.b"], W("ct", B, E))    # = mean_t(task_embedding), the layer is affine
 
     def ffn(name, x1, R):
-        if SPLIT_FFN:                                                         # development A/B: GEMM, then the gate as its own pass
-            wv = ops.mm(x1, P[name + ".wv"], W("wv", R, 2 * HID))
-            g = ops.gate(wv, W("g", R, HID))
-        else:
-            g = ops.ffn_gate(x1, P[name + ".wg"], W("g", R, HID))
+        wv = ops.mm(x1, P[name + ".wv"], W("wv", R, 2 * HID))
+        g = ops.gate(wv, W("g", R, HID))
         f = ops.mm(g, P[name + ".w2"], W("f", R, E))
         return ops.add_layernorm(f, x1, P[name + ".ln2.g"], P[name + ".ln2.b"], W(name + ".y", R, E), P[name + ".ln2.eps"])
 

@@ -49,11 +49,6 @@ int dcmp_add_layernorm(const uint16_t* x_d, const uint16_t* res_d, const float* 
 /* attention.py:164-168 GateFFNDense between its GEMMs: wv rows hold [W x | V x] (2 x 512); out[r, :] = sigmoid(W x) * (V x). */
 int dcmp_gate(const uint16_t* wv_d, uint16_t* out_d, long rows, void* stream);
 
-/* attention.py:164-167 the same gate fused with its two GEMMs: out[r, :] = sigmoid(x[r, :] W^T) * (x[r, :] V^T), x rows [rows, 128],
- * wg [1024, 128] = the nn.Linear weights W (rows 0..511) and V (rows 512..1023) as stored (attention.py:159-160), out [rows, 512].
- * The [rows, 1024] pre-activations never reach memory. */
-int dcmp_ffn_gate(const uint16_t* x_d, const uint16_t* wg_d, uint16_t* out_d, long rows, void* stream);
-
 /* attention.py:48-81 SingleHeadAttention (the pointer head) after its query projection: u[b, t] = clip * tanh(norm * qk[b, :] . feat[b, t, :]),
  * forbidden keys (mask 1) set to -1e4 (:78-80), logp = log_softmax(u) in fp32.  qk [B, 128] is the current state times W_query W_key^T
  * (folded on the host), feat rows [B * n, 128], mask_d [B, n] or NULL, logp_d [B, n] fp32.  n <= 256. */

@@ -85,7 +85,7 @@ def test_policy_header_symbols_are_exported_and_bound():
     from dcmrta_b200 import policy_fused as pf
     L = pf.lib()
     names = declared_symbols()
-    assert len(names) == 9
+    assert len(names) == 8
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/dcmrta_policy.h but not exported"
     assert sorted(pf.SIGNATURES) == names
@@ -187,20 +187,6 @@ def test_kernel_add_layernorm_gate_embed(rows):
         w, bias = torch.randn(128, k, device="cuda"), torch.randn(128, device="cuda")
         _close(cu.embed(obs, w, bias, torch.empty(rows, 128, dtype=torch.bfloat16, device="cuda")),
                th.embed(obs, w, bias, torch.empty(rows, 128, device="cuda")), 1e-5, f"embed k={k}")
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("rows", [1, 16, 127, 129, 4099, 8192 * 51])
-def test_kernel_ffn_gate(rows):
-    """GEMM + gate in one kernel against fp32 torch on the same bf16 operands"""
-    from dcmrta_b200.policy_fused import CudaOps, TorchOps
-    x = _bf(rows, 128, seed=10)
-    wg = _bf(1024, 128, seed=11, scale=1 / math.sqrt(128))
-    out = CudaOps().ffn_gate(x, wg, torch.full((rows, 512), 7.0, dtype=torch.bfloat16, device="cuda"))
-    n = min(rows, 20000)                                 # the fp32 reference of the full-size case on its first and last rows
-    for sl in (slice(0, n), slice(rows - n, rows)):
-        ref = TorchOps().ffn_gate(x[sl], wg, torch.empty(x[sl].shape[0], 512, device="cuda"))
-        _close(out[sl], ref, 1e-3, "ffn_gate")
 
 
 @pytest.mark.gpu

@@ -38,3 +38,7 @@ if [ -n "$do_greedy" ]; then
   timeout 300 python bench.py --policy greedy --steps 1000 --warmup 100 --no-cpu-baseline 2>/dev/null | tee gpurun_out/${tag}_bench_greedy.json | python -c "
 import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('greedy: value %.4g us/pass %.1f frac %.3f e2e %.4g' % (d['value'], d['roofline']['launch_us'], d['roofline']['frac'], d['e2e']['value']))"
 fi
+if [ -n "$do_rollout" ]; then
+  timeout 300 python bench.py --mode rollout --fused --iters 3 2>/dev/null | tee gpurun_out/${tag}_config5.jsonl | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('rollout --fused: value %.4g ms/iter %.1f' % (d['value'], d['ms_per_step']))"
+fi

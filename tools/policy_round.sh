@@ -7,9 +7,8 @@ for opt in "$@"; do eval "do_$opt=1"; done
 ( time timeout 300 python -m pytest tests/test_policy_fused.py -m gpu -x -q ) > gpurun_out/${tag}_pytest_policy_fused.log 2>&1; tail -15 gpurun_out/${tag}_pytest_policy_fused.log
 if [ -n "$do_mma" ]; then nvcc -arch=sm_100a -O3 -o /tmp/mma_rate tools/mma_rate.cu && timeout 60 /tmp/mma_rate | tee gpurun_out/${tag}_mma_rate.txt; fi
 timeout 300 python tools/prof_policy.py 8192 ${PROF_WHICH:-shadow fused} > gpurun_out/${tag}_policy_forward_profile.txt 2>&1; grep "ms per forward" gpurun_out/${tag}_policy_forward_profile.txt
-if [ -n "$do_split" ]; then DCMP_FFN_SPLIT=1 timeout 300 python tools/prof_policy.py 8192 fused 2>&1 | grep "ms per forward\|k_gate\|nvjet_tst_256x192"; fi
 if [ -n "$do_ncu" ]; then
-  timeout 300 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-k_ffn_gate|k_attention_mma}" -c ${NCU_COUNT:-2} -f -o gpurun_out/prof_${tag}_policy python tools/prof_policy.py 8192 fused > gpurun_out/${tag}_ncu_policy.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-k_gate|k_attention_mma}" -c ${NCU_COUNT:-2} -f -o gpurun_out/prof_${tag}_policy python tools/prof_policy.py 8192 fused > gpurun_out/${tag}_ncu_policy.log 2>&1
   ls -la gpurun_out/prof_${tag}_policy.ncu-rep
 fi
 runs=("--fused" "--fused --eager" "--amp"); if [ -n "$do_fusedonly" ]; then runs=("--fused"); fi
