@@ -68,6 +68,8 @@ def parse():
     p.add_argument("--amp", action="store_true", help="--mode rollout/train: the rollouts call a bf16 shadow copy of the policy (the update stays fp32)")
     p.add_argument("--fused", action="store_true", help="--mode rollout/train: the rollouts call policy_fused.FusedPolicy (bf16 GEMMs + the sm_100a "
                    "kernels of include/dcmrta_policy.h between them); the update stays fp32 PyTorch")
+    p.add_argument("--no-compact", action="store_true", help="--mode rollout/train: every decision forwards the whole batch (default: only the envs "
+                   "that are still playing, at 1, 3/4, 1/2, 1/4 of the batch)")
     p.add_argument("--eager", action="store_true", help="--mode rollout/train: eager decision loop instead of the CUDA-graph replay")
     return p.parse_args()
 
@@ -385,17 +387,22 @@ def run_training(args):
     B = args.envs if args.envs != 65536 else 8192
     amp = "fused" if args.fused else args.amp
     cfg = TrainerConfig(agents=args.agents, tasks=args.tasks, envs_per_rank=B, amp=amp, seed=1234, eval_instances=max(world, 64),
-                        graph_rollout=not args.eager)
+                        graph_rollout=not args.eager, **({"rollout_fractions": (1.0,)} if args.no_compact else {}))
     tr = ReinforceTrainer(cfg, device=local)
+
+    forwarded = [0, 0]                                               # policy rows forwarded / of them live, sampled rollouts of the timed iterations
 
     def one():
         if args.mode == "train":
             return tr.iteration()["decisions"]
         tr.env.generate(max_duration=5.0)
         ep = tr.rollout.run(tr.net, "sample", None if cfg.graph_rollout else tr.gen, amp=cfg.amp)
-        return int(ep.active.sum())
+        n = int(ep.active.sum())
+        forwarded[0] += ep.forwarded; forwarded[1] += n
+        return n
 
     one()                                                            # warm-up (allocator, cuBLAS handles, autotune)
+    forwarded[:] = [0, 0]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -419,7 +426,9 @@ def run_training(args):
             "config": {"workload": f"BASELINE configs[4]: {B} synthetic {args.agents}A/{args.tasks}T envs per GPU, one episode per env per iteration, "
                                    f"AttentionNet(128) in PyTorch" + (", rollout forward = torch.mm GEMMs + libdcmrta_policy.so kernels" if args.fused else "") + f", mode={args.mode}, decision loop " + ("eager" if args.eager else "replayed from a CUDA graph"), "envs_per_gpu": B, "iterations": args.iters,
                        "parallelism": f"env shards x{world}" + (", one flat NCCL gradient all-reduce per update" if args.mode == "train" else "")},
-            "env_steps_timed": float(cnt.item())}), flush=True)
+            "env_steps_timed": float(cnt.item()),
+            "policy_rows": ({"forwarded": forwarded[0], "live_fraction": forwarded[1] / forwarded[0], "fractions": list(cfg.rollout_fractions) if cfg.graph_rollout else [1.0]}
+                            if forwarded[0] else None)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,6 +13,7 @@ decision of an episode is reward - greedy-baseline reward of the same instance (
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 
 import torch
@@ -36,6 +37,7 @@ class Episodes:
     leader: torch.Tensor | None = None      # [L,B]      i32  (agent id, buffer slot 5 of the reference)
     active: torch.Tensor | None = None      # [L,B]      bool: env b took its t-th decision
     logp: torch.Tensor | None = None        # [L,B,T+1]  f32 log-probabilities of every decision (run(keep_logp=True) only)
+    forwarded: int = 0                      # env rows the policy was called on, summed over the decisions (B * length without compaction)
 
 
 class BatchedRollout:
@@ -137,7 +139,7 @@ class BatchedRollout:
         reward = metrics[:, 0].clone()
         if was_training:
             net.train()
-        ep = Episodes(reward=reward, metrics=metrics, ended=ended, length=t)
+        ep = Episodes(reward=reward, metrics=metrics, ended=ended, length=t, forwarded=t * env.B)
         if self.record:
             ep.agent_obs, ep.task_obs, ep.mask = self.agent_obs[:t], self.task_obs[:t], self.mask[:t]
             ep.action, ep.leader, ep.active = self.action[:t], self.leader[:t], self.active[:t]
@@ -155,9 +157,16 @@ class GraphedRollout(BatchedRollout):
     The env writes each observation into one of two fixed ping-pong slots (graph nodes have fixed addresses); a captured index_copy_
     files it into the episode buffer at a decision counter that lives on the device.  `unroll` is even: the env alternates two
     ended-episode counters from pass to pass, and a replay must leave that parity where the capture found it.  Sampling uses the default
-    CUDA generator (graph-safe Philox offsets); seed it with torch.cuda.manual_seed."""
+    CUDA generator (graph-safe Philox offsets); seed it with torch.cuda.manual_seed.
 
-    def __init__(self, env: BatchedTaskEnv, horizon: int, record: bool = True, check_every: int = 16, unroll: int = 8):
+    `fractions`: forward only the envs that are still playing.  Episodes of one batch end at different decisions (20A/50T: 120 +- 9, the
+    longest of 8,192 near 150), so late in a rollout most rows of a full-batch forward belong to finished envs.  For every fraction f < 1
+    the loop is also captured with the policy called on ceil(f B) gathered rows -- an index list of the live envs, padded with one finished
+    env (whose action the step ignores), rebuilt at the done-flag poll that already synchronises every `check_every` decisions -- and each
+    replay picks the smallest capture that holds the live envs.  Envs only ever finish between two polls, so the list stays valid."""
+
+    def __init__(self, env: BatchedTaskEnv, horizon: int, record: bool = True, check_every: int = 16, unroll: int = 8,
+                 fractions: tuple = (1.0,)):
         assert unroll >= 2 and unroll % 2 == 0
         horizon = -(-int(horizon) // unroll) * unroll                # whole replays
         super().__init__(env, horizon, record, check_every)
@@ -166,13 +175,21 @@ class GraphedRollout(BatchedRollout):
         self.pp = [(torch.zeros(B, A, 6, dtype=torch.float32, device=dev), torch.zeros(B, T + 1, 5, dtype=torch.float32, device=dev),
                     torch.ones(B, T + 1, dtype=torch.uint8, device=dev)) for _ in range(2)]
         self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.sizes = sorted({B} | {max(1, math.ceil(B * f - 1e-9)) for f in fractions if 0 < f < 1})       # rows per forward, ascending
+        self.live = {n: torch.zeros(n, dtype=torch.int64, device=dev) for n in self.sizes if n < B}            # the index lists
         self._graphs = {}
 
-    def _decision(self, net, mode, amp, s):
+    def _decision(self, net, mode, amp, s, rows=None):
         env = self.env
         a, k, m = self.pp[s]
-        logp = self._logp(net, amp, k, a, m.view(torch.bool))
-        act = sample_actions(logp.float()) if mode == "sample" else greedy_actions(logp)
+        if rows is None or rows == env.B:
+            logp = self._logp(net, amp, k, a, m.view(torch.bool))
+            act = sample_actions(logp.float()) if mode == "sample" else greedy_actions(logp)
+        else:
+            idx = self.live[rows]
+            logp = self._logp(net, amp, k.index_select(0, idx), a.index_select(0, idx), m.index_select(0, idx).view(torch.bool))
+            sub = sample_actions(logp.float()) if mode == "sample" else greedy_actions(logp)
+            act = torch.zeros(env.B, dtype=torch.int32, device=env.device).index_copy_(0, idx, sub)     # envs off the list are done: ignored
         if self.record:
             self.agent_obs.index_copy_(0, self.t_dev, a.unsqueeze(0)); self.task_obs.index_copy_(0, self.t_dev, k.unsqueeze(0))
             self.mask.index_copy_(0, self.t_dev, m.unsqueeze(0)); self.action.index_copy_(0, self.t_dev, act.unsqueeze(0))
@@ -182,12 +199,15 @@ class GraphedRollout(BatchedRollout):
         env.step(act)
         self.t_dev.add_(1)
 
-    def _graph(self, net, mode, amp):
-        """net: the module the loop calls (the bf16 shadow when amp); its parameters keep their addresses, so refreshing them between
-        replays is all an update of the policy needs."""
-        key = (id(net), mode, amp)
+    def _graph(self, net, mode, amp, rows=None):
+        """net: the module the loop calls (the bf16 shadow / FusedPolicy when amp); its parameters keep their addresses, so refreshing them
+        between replays is all an update of the policy needs.  rows: policy rows per decision (None = every env)."""
+        rows = self.env.B if rows is None else rows
+        key = (id(net), mode, amp, rows)
         if key not in self._graphs:
             env = self.env
+            if rows < env.B:
+                self.live[rows].copy_(torch.arange(rows, device=env.device))     # any valid list for the warm-up
             side = torch.cuda.Stream(device=env.device)
             side.wait_stream(torch.cuda.current_stream(env.device))
             with torch.cuda.stream(side):                            # warm-up off the capture: allocator, cuBLAS handles, the env's one-time setup
@@ -195,13 +215,13 @@ class GraphedRollout(BatchedRollout):
                 env.reset()
                 self.t_dev.zero_()
                 for u in range(2):
-                    self._decision(net, mode, amp, u % 2)
+                    self._decision(net, mode, amp, u % 2, rows)
             torch.cuda.current_stream(env.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             self.t_dev.zero_()
             with torch.cuda.graph(g):
                 for u in range(self.unroll):
-                    self._decision(net, mode, amp, u % 2)
+                    self._decision(net, mode, amp, u % 2, rows)
             self._graphs[key] = g
         return self._graphs[key]
 
@@ -212,16 +232,28 @@ class GraphedRollout(BatchedRollout):
         assert not env.auto_reset
         was_training = net.training
         net.eval()
-        g = self._graph(self._forward_net(net, amp), mode, amp)
+        fnet = self._forward_net(net, amp)
+        # all captured before the episode starts (a warm-up resets the env), the full batch FIRST: the policy's workspaces are allocated by
+        # the largest forward and only sliced by the smaller ones, so no capture ever holds a buffer that a later one replaced
+        graphs = {n: self._graph(fnet, mode, amp, n) for n in sorted(self.sizes, reverse=True)}
         env.set_output_buffers(*self.pp[0])
         env.reset()
         self.t_dev.zero_()
-        t = 0
+        t, rows, forwarded = 0, env.B, 0
         while t < self.horizon:
-            g.replay()
+            graphs[rows].replay()
             t += self.unroll
-            if t % self.check_every < self.unroll and bool(env.done.all()):
-                break
+            forwarded += rows * self.unroll
+            if t % self.check_every < self.unroll:
+                alive = torch.logical_not(env.done)
+                n = int(alive.sum())                                 # the loop's only host synchronisation
+                if n == 0:
+                    break
+                rows = min(r for r in self.sizes if r >= n)
+                if rows < env.B:                                     # the live envs, then one finished env repeated
+                    idx = self.live[rows]
+                    idx.copy_(env.done.nonzero()[:1, 0].expand(rows))
+                    idx[:n] = alive.nonzero().squeeze(1)
         ended = env.done.clone()
         metrics = env.episode_metrics()
         if not bool(ended.all()):
@@ -229,7 +261,7 @@ class GraphedRollout(BatchedRollout):
             metrics = torch.where(ended.unsqueeze(1), metrics, live)
         if was_training:
             net.train()
-        ep = Episodes(reward=metrics[:, 0].clone(), metrics=metrics, ended=ended, length=t)
+        ep = Episodes(reward=metrics[:, 0].clone(), metrics=metrics, ended=ended, length=t, forwarded=forwarded)
         if self.record:
             ep.agent_obs, ep.task_obs, ep.mask = self.agent_obs[:t], self.task_obs[:t], self.mask[:t]
             ep.action, ep.leader, ep.active = self.action[:t], self.leader[:t], self.active[:t]

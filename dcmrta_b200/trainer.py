@@ -123,6 +123,8 @@ class TrainerConfig:
     # "frozen" is what the reference's variable names suggest: the separately kept baseline network.
     baseline_net: str = "local"
     graph_rollout: bool = True       # replay the decision loop from a CUDA graph (rollout.GraphedRollout); False = eager loop, explicit generator
+    # graphed rollouts forward only the envs that are still playing, at these fractions of the batch (GraphedRollout.fractions); (1.0,) = always all
+    rollout_fractions: tuple = (1.0, 0.75, 0.5, 0.25)
     seed: int = 0
     eval_instances: int = EVAL_INSTANCES
 
@@ -148,7 +150,11 @@ class ReinforceTrainer:
         self.env = BatchedTaskEnv(B, cfg.agents, cfg.tasks, seed=cfg.seed, first_gid=first_gid, **kw)
         self.base_env = BatchedTaskEnv(B, cfg.agents, cfg.tasks, seed=cfg.seed + 1, first_gid=first_gid, **kw)
         horizon = cfg.horizon or 4 * (cfg.agents + cfg.tasks)
-        Rollout = GraphedRollout if cfg.graph_rollout else BatchedRollout
+        if cfg.graph_rollout:
+            def Rollout(*a, **k):
+                return GraphedRollout(*a, fractions=cfg.rollout_fractions, **k)
+        else:
+            Rollout = BatchedRollout
         self.rollout = Rollout(self.env, horizon, record=True, check_every=8)      # every pass past the longest episode is a wasted forward
         self.base_rollout = Rollout(self.base_env, horizon, record=False, check_every=8)
         self.gen = torch.Generator(device=self.device)

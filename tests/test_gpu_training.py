@@ -275,6 +275,52 @@ def test_graphed_rollout_records_what_the_env_did():
     env.close(); env2.close()
 
 
+def test_graphed_rollout_forwards_only_live_envs():
+    """GraphedRollout(fractions=...): late in a rollout the policy is called on a gathered list of the envs that are still playing.  The
+    record must still replay decision by decision, every chosen action must be legal for ITS env (a misrouted action would hit another
+    env's mask), fewer rows than B x length must have been forwarded, and a greedy rollout must choose what the network says for the
+    recorded observation of each env, also where the list is in use."""
+    from dcmrta_b200 import BatchedTaskEnv
+    from dcmrta_b200.policy import AttentionNet
+    from dcmrta_b200.rollout import GraphedRollout, clone_instances
+    B, A, T = 300, 10, 20
+    torch.manual_seed(0)
+    net = AttentionNet(6, 5, 32).cuda().eval()
+    env = BatchedTaskEnv(B, A, T, auto_reset=False, seed=5)
+    env.generate()
+    ro = GraphedRollout(env, horizon=4 * (A + T), record=True, check_every=4, unroll=4, fractions=(1.0, 0.75, 0.5, 0.25, 0.05))
+    assert ro.sizes == [15, 75, 150, 225, 300]
+    torch.cuda.manual_seed(7)
+    ep = ro.run(net, "sample")
+    assert bool(ep.ended.all())
+    assert ep.forwarded < B * ep.length and ep.forwarded >= int(ep.active.sum())
+    assert torch.equal(ep.active.sum(0).double(), ep.metrics[:, 7])
+    assert not bool((ep.mask.gather(2, ep.action.long().unsqueeze(2)).squeeze(2).bool() & ep.active).any())
+    env2 = BatchedTaskEnv(B, A, T, auto_reset=False, seed=5)
+    clone_instances(env, env2)
+    env2.reset(leaders=ep.leader[0])
+    for t in range(ep.length):
+        act = ep.active[t]
+        assert torch.equal(env2.agent_obs[act], ep.agent_obs[t][act]), t
+        assert torch.equal(env2.task_obs[act], ep.task_obs[t][act]), t
+        assert torch.equal(env2.mask_u8[act], ep.mask[t][act]), t
+        more = t + 1 < ep.length
+        nxt = torch.where(ep.active[t + 1], ep.leader[t + 1], torch.full_like(ep.leader[0], -1)) if more else torch.full_like(ep.leader[0], -1)
+        env2.step(ep.action[t], next_leaders=nxt)
+    assert torch.equal(env2.episode_metrics(), ep.metrics)
+    g = ro.run(net, "greedy")
+    assert bool(g.ended.all()) and g.forwarded < B * g.length
+    agree, total = 0, 0
+    with torch.no_grad():
+        for t in range(g.length):
+            act = g.active[t]
+            if 0 < int(act.sum()) <= 150:                                  # decisions taken while a gathered list was in use
+                want = net(g.task_obs[t][act], g.agent_obs[t][act], g.mask[t][act].view(torch.bool)).argmax(1).int()
+                agree += int((want == g.action[t][act]).sum()); total += int(act.sum())
+    assert total > 0 and agree >= 0.995 * total, (agree, total)
+    env.close(); env2.close()
+
+
 def test_bf16_shadow_rollout_follows_the_fp32_weights():
     """amp=True: the decision loop calls a bf16 shadow copy of the network; the copy is refreshed from the fp32 weights at the start of every
     run, so a rollout after an update plays the UPDATED policy (also through the CUDA graph, whose nodes keep the shadow's addresses)."""

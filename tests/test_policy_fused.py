@@ -246,7 +246,8 @@ def test_rollouts_with_the_fused_policy():
     for Rollout in (BatchedRollout, GraphedRollout):
         env = BatchedTaskEnv(B, A, T, auto_reset=False, seed=11)
         env.generate()
-        ro = Rollout(env, horizon=4 * (A + T), record=True)
+        more = {"fractions": (1.0, 0.5, 0.25)} if Rollout is GraphedRollout else {}      # the graphed loop also gathers the live envs
+        ro = Rollout(env, horizon=4 * (A + T), record=True, **more)
         torch.cuda.manual_seed(5)
         kw = {"keep_logp": True} if Rollout is BatchedRollout else {}
         ep = ro.run(net, "sample", amp="fused", **kw)
@@ -260,6 +261,8 @@ def test_rollouts_with_the_fused_policy():
                 ref = net(ep.task_obs[t], ep.agent_obs[t], ep.mask[t].view(torch.bool))
             ok = ~ep.mask[t].view(torch.bool) & ep.active[t].unsqueeze(1)
             assert float((ep.logp[t] - ref).abs()[ok].max()) < 0.1
-        greedy = Rollout(env, horizon=4 * (A + T), record=False).run(net, "greedy", amp="fused")
+        greedy = Rollout(env, horizon=4 * (A + T), record=False, **more).run(net, "greedy", amp="fused")
         assert bool(greedy.ended.all())
+        if more:
+            assert ep.forwarded < B * ep.length and greedy.forwarded < B * greedy.length
         env.close()
