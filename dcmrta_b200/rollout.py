@@ -189,7 +189,10 @@ class GraphedRollout(BatchedRollout):
             idx = self.live[rows]
             logp = self._logp(net, amp, k.index_select(0, idx), a.index_select(0, idx), m.index_select(0, idx).view(torch.bool))
             sub = sample_actions(logp.float()) if mode == "sample" else greedy_actions(logp)
-            act = torch.zeros(env.B, dtype=torch.int32, device=env.device).index_copy_(0, idx, sub)     # envs off the list are done: ignored
+            # Envs off the list are done and the step ignores their action -- except in the warm-up before the capture, where the list is
+            # arbitrary: give them their first legal action there too (a forbidden depot move would send the whole team home, end the
+            # episode and advance the env's Philox episode index, so the recorded rollout would no longer replay on a fresh env).
+            act = torch.argmax((m == 0).int(), 1).to(torch.int32).index_copy_(0, idx, sub)
         if self.record:
             self.agent_obs.index_copy_(0, self.t_dev, a.unsqueeze(0)); self.task_obs.index_copy_(0, self.t_dev, k.unsqueeze(0))
             self.mask.index_copy_(0, self.t_dev, m.unsqueeze(0)); self.action.index_copy_(0, self.t_dev, act.unsqueeze(0))
