@@ -69,7 +69,7 @@ def parse():
     p.add_argument("--fused", action="store_true", help="--mode rollout/train: the rollouts call policy_fused.FusedPolicy (bf16 GEMMs + the sm_100a "
                    "kernels of include/dcmrta_policy.h between them); the update stays fp32 PyTorch")
     p.add_argument("--no-compact", action="store_true", help="--mode rollout/train: every decision forwards the whole batch (default: only the envs "
-                   "that are still playing, at 1, 3/4, 1/2, 1/4 of the batch)")
+                   "that are still playing, at the fractions of the batch TrainerConfig.rollout_fractions names)")
     p.add_argument("--eager", action="store_true", help="--mode rollout/train: eager decision loop instead of the CUDA-graph replay")
     return p.parse_args()
 

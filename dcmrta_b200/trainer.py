@@ -123,8 +123,10 @@ class TrainerConfig:
     # "frozen" is what the reference's variable names suggest: the separately kept baseline network.
     baseline_net: str = "local"
     graph_rollout: bool = True       # replay the decision loop from a CUDA graph (rollout.GraphedRollout); False = eager loop, explicit generator
-    # graphed rollouts forward only the envs that are still playing, at these fractions of the batch (GraphedRollout.fractions); (1.0,) = always all
-    rollout_fractions: tuple = (1.0, 0.75, 0.5, 0.25)
+    # graphed rollouts forward only the envs that are still playing, at these fractions of the batch (GraphedRollout.fractions); (1.0,) = always all.
+    # Episode lengths of one batch spread by +-7 % (20A/50T: 120 +- 9 decisions, the longest of 8,192 near 150): with these eight sizes and a poll
+    # every 8 decisions 96 % of the forwarded rows are live (79 % without, 92 % with four sizes; simulated on 3,000 oracle episodes).
+    rollout_fractions: tuple = (1.0, 0.85, 0.7, 0.5, 0.35, 0.2, 0.1, 0.03)
     seed: int = 0
     eval_instances: int = EVAL_INSTANCES
 
