@@ -6,7 +6,8 @@
   torchrun --nproc-per-node N bench.py --gpus N ...               N > 1 (one rank per GPU, env shards, no collective on the data path);
                                                                   launched plainly with --gpus N > 1 it re-executes itself under torchrun
   python bench.py --total-envs 1048576 --agents A --tasks T --gpus N     BASELINE configs[3]: a fixed job sharded evenly (strong scaling)
-  python bench.py --mode rollout|train [--amp] --gpus N                   BASELINE configs[4]: the attention policy in the loop
+  python bench.py --mode rollout|train [--fused|--amp] --gpus N           BASELINE configs[4]: the attention policy in the loop (--fused: the rollouts
+                                                                          call policy_fused.FusedPolicy; --no-compact: every decision forwards every env)
 
 A "step" is one pass of the hot path over one batch: ONE leader decision for every env of the batch (dcm_step:
 apply the choice, coalition/feasibility update, agent update, slot advance, leader choice, observation + mask for the

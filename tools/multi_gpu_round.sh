@@ -21,8 +21,9 @@ for shape in "10 20" "20 50" "30 100" "50 200"; do set -- $shape
   run --gpus $N --total-envs 1048576 --agents $1 --tasks $2 --steps 300 --warmup 30 --preroll 300 --no-e2e --no-cpu-baseline | tee -a gpurun_out/${tag}_config4.jsonl | show
 done
 if [ -n "$do_train" ]; then
+  run --gpus $N --mode rollout --fused --iters 3 | tee -a gpurun_out/${tag}_config5.jsonl | show
   run --gpus $N --mode rollout --amp --iters 3 | tee -a gpurun_out/${tag}_config5.jsonl | show
   run --gpus $N --mode rollout --iters 1 | tee -a gpurun_out/${tag}_config5.jsonl | show
-  run --gpus $N --mode train --amp --iters 1 | tee -a gpurun_out/${tag}_config5.jsonl | show
+  run --gpus $N --mode train --fused --iters 1 | tee -a gpurun_out/${tag}_config5.jsonl | show
 fi
 tail -5 gpurun_out/${tag}_err.log 2>/dev/null | cut -c1-300
