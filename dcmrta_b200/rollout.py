@@ -148,6 +148,16 @@ class BatchedRollout:
         return ep
 
 
+def sub_batch_sizes(B: int, fractions) -> list:
+    """Rows per policy forward the graphed loop is captured at, ascending: the whole batch and ceil(f B) for every fraction 0 < f < 1."""
+    return sorted({int(B)} | {max(1, math.ceil(B * f - 1e-9)) for f in fractions if 0 < f < 1})
+
+
+def rows_for(sizes, n_live: int) -> int:
+    """The smallest captured size that holds n_live envs."""
+    return min(r for r in sizes if r >= n_live)
+
+
 class GraphedRollout(BatchedRollout):
     """BatchedRollout whose decision loop -- policy forward, sampling, experience recording, dcm_step -- is captured ONCE in a CUDA graph
     of `unroll` decisions and replayed: the loop issues hundreds of small kernels per decision, and at a few thousand envs the eager
@@ -175,7 +185,7 @@ class GraphedRollout(BatchedRollout):
         self.pp = [(torch.zeros(B, A, 6, dtype=torch.float32, device=dev), torch.zeros(B, T + 1, 5, dtype=torch.float32, device=dev),
                     torch.ones(B, T + 1, dtype=torch.uint8, device=dev)) for _ in range(2)]
         self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.sizes = sorted({B} | {max(1, math.ceil(B * f - 1e-9)) for f in fractions if 0 < f < 1})       # rows per forward, ascending
+        self.sizes = sub_batch_sizes(B, fractions)                                                           # rows per forward, ascending
         self.live = {n: torch.zeros(n, dtype=torch.int64, device=dev) for n in self.sizes if n < B}            # the index lists
         self._graphs = {}
 
@@ -252,7 +262,7 @@ class GraphedRollout(BatchedRollout):
                 n = int(alive.sum())                                 # the loop's only host synchronisation
                 if n == 0:
                     break
-                rows = min(r for r in self.sizes if r >= n)
+                rows = rows_for(self.sizes, n)
                 if rows < env.B:                                     # the live envs, then one finished env repeated
                     idx = self.live[rows]
                     idx.copy_(env.done.nonzero()[:1, 0].expand(rows))
