@@ -70,3 +70,20 @@ int main(){ DcmLayout L = dcm_make_layout(20,50,5); printf("%d %d %d %zu\n", L.d
     dyn, sta, stage, hdr = map(int, subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
     assert hdr == 48 and dyn % 16 == 0 and sta % 16 == 0
     assert (dyn, sta, stage) == (3520, 1280, 1552)
+
+
+def test_sass_shows_the_hardware_paths_the_design_names():
+    """DESIGN.md 4 / 9 by mnemonic (B200_PROFILING.md): the observation tile kernel moves its spans with TMA bulk copies against an mbarrier
+    (UBLKCP.S.G in, UBLKCP.G.S out, SYNCS.*.TRANS64), k_step stages its gathers with cp.async (LDGSTS); the policy's attention runs on the
+    tensor cores through the legacy path (HMMA.16816.F32.BF16: a 51 x 51 x 16 problem is below tcgen05's smallest tile).  No tcgen05 / UTCMMA
+    anywhere: the step is not a contraction and the policy's dense GEMMs are cuBLASLt's."""
+    import subprocess
+    from dcmrta_b200 import build, library_path
+    build.build_policy()
+    env_sass = subprocess.run(["cuobjdump", "-sass", str(library_path())], capture_output=True, text=True).stdout
+    for m in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.ARRIVE.TRANS64", "LDGSTS.E.64"):
+        assert m in env_sass, m
+    assert "HMMA" not in env_sass and "UTCMMA" not in env_sass and "UTCHMMA" not in env_sass
+    pol_sass = subprocess.run(["cuobjdump", "-sass", str(build.POLICY_SO)], capture_output=True, text=True).stdout
+    assert pol_sass.count("HMMA.16816.F32.BF16") >= 16 and "MUFU.EX2" in pol_sass
+    assert "UTCMMA" not in pol_sass and "UTCHMMA" not in pol_sass
